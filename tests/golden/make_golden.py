@@ -1,0 +1,153 @@
+"""Generate golden vectors by running the UNMODIFIED reference (read-only at
+/root/reference) in the build container.  The reference cannot travel to the GPU
+box, so its outputs are committed here as small .npz fixtures.
+
+    python tests/golden/make_golden.py            # rewrites tests/golden/*.npz
+
+The reference is imported with arithmetic-free stub modules for packages that
+are absent from this image (yacs, kornia, skimage, imgaug, pydegensac) — recipe
+from SURVEY.md Appendix A.  Weights and images come from geoformer_b200.synth,
+which is reference-independent, so the GPU box can rebuild the same inputs.
+"""
+import copy
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from geoformer_b200 import synth  # noqa: E402
+
+
+def import_reference():
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    class CfgNode(dict):
+        def __getattr__(self, k):
+            try:
+                return self[k]
+            except KeyError:
+                raise AttributeError(k)
+
+        def __setattr__(self, k, v):
+            self[k] = v
+
+        def clone(self):
+            return copy.deepcopy(self)
+
+    stub("yacs"); stub("yacs.config", CfgNode=CfgNode)
+    stub("kornia"); stub("kornia.geometry"); stub("kornia.geometry.subpix", dsnt=None)
+    stub("kornia.utils"); stub("kornia.utils.grid", create_meshgrid=None)
+    stub("skimage"); stub("skimage.feature", peak_local_max=None)
+    stub("imgaug"); stub("imgaug.augmenters")
+    sys.modules["imgaug"].augmenters = sys.modules["imgaug.augmenters"]
+    stub("pydegensac")
+    sys.path.insert(0, "/root/reference")
+    from model.full_model import GeoFormer
+    from model.loftr_src.loftr.utils.cvpr_ds_config import default_cfg
+    from model.geo_config import default_cfg as geo_cfg
+    return GeoFormer, default_cfg, geo_cfg
+
+
+def build_reference(sd, coarse_thr, fine_thr=0.1):
+    GeoFormer, default_cfg, geo_cfg = import_reference()
+    g = dict(geo_cfg)
+    g["coarse_thr"] = coarse_thr
+    g["fine_thr"] = fine_thr
+    model = GeoFormer(copy.deepcopy(default_cfg), g).eval()
+    ref_sd = model.state_dict()
+    assert set(ref_sd) == set(sd), (set(ref_sd) ^ set(sd))
+    for k in ref_sd:
+        assert tuple(ref_sd[k].shape) == tuple(sd[k].shape), k
+    missing = model.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=True)
+    return model
+
+
+def run_reference(model, im0, im1):
+    cap = {}
+    hooks = []
+
+    def grab(name):
+        def fn(mod, inp, out):
+            cap.setdefault(name, []).append(out)
+        return fn
+
+    for nm in ("backbone", "loftr_coarse", "geo_module", "fine_preprocess", "loftr_fine"):
+        hooks.append(getattr(model, nm).register_forward_hook(grab(nm)))
+    with torch.no_grad():
+        data = model({"image0": im0.clone(), "image1": im1.clone()})
+    for h in hooks:
+        h.remove()
+    return data, cap
+
+
+def npify(d):
+    return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
+
+
+def small_case(name, h, w, regime, n, seed0, randomize_norm, coarse_thr=0.0, fine_thr=0.1):
+    sd = synth.make_state_dict(seed=7, randomize_norm=randomize_norm)
+    model = build_reference(sd, coarse_thr, fine_thr)
+    im0, im1 = synth.make_pairs(n, h, w, regime, seed0)
+    data, cap = run_reference(model, im0, im1)
+    fc, ff = cap["backbone"][0]
+    g0, g1 = cap["geo_module"][0]
+    c0, c1 = cap["loftr_coarse"][0]
+    out = dict(
+        meta=np.array([h, w, n, seed0, int(randomize_norm)]), regime=np.array(regime),
+        coarse_thr=np.array(coarse_thr), fine_thr=np.array(fine_thr),
+        cnn_c=fc, fine_sub=ff[:, ::8, ::4, ::4],            # subsampled fine map keeps the fixture small
+        coarse0=c0, coarse1=c1, geo0=g0, geo1=g1,
+        dect_conf=data["dect_conf_matrix"], conf=data["conf_matrix"],
+        b_ids=data["b_ids"], i_ids=data["i_ids"], j_ids=data["j_ids"],
+        mkpts0_c=data["mkpts0_c"], mkpts1_c=data["mkpts1_c"],
+        mkpts0_f=data["mkpts0_f"], mkpts1_f=data["mkpts1_f"], mconf=data["mconf"], m_bids=data["m_bids"],
+        fine_matrix=data["fine_matrix"][:64],
+    )
+    if "fine_preprocess" in cap:
+        a, b = cap["fine_preprocess"][0]
+        out.update(fine_in0=a[:16], fine_in1=b[:16])
+    if "loftr_fine" in cap:
+        a, b = cap["loftr_fine"][0]
+        out.update(fine_out0=a[:16], fine_out1=b[:16])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **npify(out))
+    print(name, "M_c", len(data["b_ids"]), "M_f", len(data["mkpts0_f"]))
+
+
+def full_case(name, h, w, regime, seed0, coarse_thr=0.0):
+    """Full-size case: only match lists and scalar summaries are stored."""
+    sd = synth.make_state_dict(seed=0)
+    model = build_reference(sd, coarse_thr)
+    im0, im1 = synth.make_pairs(1, h, w, regime, seed0)
+    data, cap = run_reference(model, im0, im1)
+    out = dict(
+        meta=np.array([h, w, 1, seed0, 0]), regime=np.array(regime), coarse_thr=np.array(coarse_thr),
+        i_ids=data["i_ids"].to(torch.int32), j_ids=data["j_ids"].to(torch.int32),
+        mkpts0_f=data["mkpts0_f"].to(torch.int16), mkpts1_f=data["mkpts1_f"].to(torch.int16),
+        mconf=data["mconf"],
+        dect_conf_max=data["dect_conf_matrix"].max(), conf_max=data["conf_matrix"].max(),
+        conf_rowsum_head=data["conf_matrix"][0, :16].sum(-1),
+        geo0_head=cap["geo_module"][0][0][0, :4, :8], coarse0_head=cap["loftr_coarse"][0][0][0, :4, :8],
+    )
+    assert torch.equal(data["mkpts0_f"].to(torch.int16).float(), data["mkpts0_f"])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **npify(out))
+    print(name, "M_c", len(data["b_ids"]), "M_f", len(data["mkpts0_f"]))
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    small_case("small_dense", 96, 128, "dense", 2, 0, True)
+    small_case("small_shift", 96, 128, "shift", 1, 10, True)
+    small_case("small_rect_thr", 64, 96, "dense", 1, 20, False, coarse_thr=0.2)   # zero-match corner
+    if "--full" in sys.argv or True:
+        full_case("full_dense_480x640", 480, 640, "dense", 0)
