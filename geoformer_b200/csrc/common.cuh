@@ -1,0 +1,40 @@
+// Shared helpers for the sm_100a kernels of libgeoformer_sm100.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+
+#include "../../include/geoformer_b200.h"
+
+#define GF_CHECK_LAUNCH()                                   \
+  do {                                                      \
+    cudaError_t e__ = cudaGetLastError();                   \
+    if (e__ != cudaSuccess) return gf_set_error(GF_ERR_LAUNCH, cudaGetErrorString(e__)); \
+  } while (0)
+
+int gf_set_error(int code, const char* msg);
+
+static inline int gf_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+namespace gf {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float elu1(float x) {   // elu(x) + 1  (linear_attention.py:11-12)
+  return x > 0.f ? x + 1.f : expf(x);              // expm1(x)+1 == exp(x) up to 1 ulp
+}
+
+}  // namespace gf

@@ -1,0 +1,175 @@
+// Fine-level kernels (loftr_module/fine_preprocess.py:41-56, model/fine_matching2.py:52-126).
+#include "common.cuh"
+
+#include <atomic>
+
+namespace gf {
+extern std::atomic<int64_t> g_launches;
+
+// 5x5 stride-4 pad-2 window of the NHWC fine map around coarse token (row r, col c): pixels
+// (stride*r + ky - half, stride*c + kx - half); slot = ky*window + kx; zero outside (F.unfold padding).
+// One CTA per match, one thread per float4 of channels.
+__global__ void fine_gather_kernel(const float* __restrict__ fine, int hf, int wf, int c, const int64_t* __restrict__ b_ids,
+                                   const int64_t* __restrict__ tok_ids, int wc, int stride, int window,
+                                   float* __restrict__ out) {
+  const int64_t m = blockIdx.x;
+  const int b = (int)b_ids[m];
+  const int tok = (int)tok_ids[m];
+  const int cy = (tok / wc) * stride, cx = (tok % wc) * stride;
+  const int half = window / 2;
+  const int c4 = c >> 2;
+  float4* o = reinterpret_cast<float4*>(out + m * window * window * c);
+  for (int e = threadIdx.x; e < window * window * c4; e += blockDim.x) {
+    const int slot = e / c4, q = e - slot * c4;
+    const int py = cy + slot / window - half, px = cx + slot % window - half;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (py >= 0 && py < hf && px >= 0 && px < wf)
+      v = reinterpret_cast<const float4*>(fine + (((int64_t)b * hf + py) * wf + px) * c)[q];
+    o[e] = v;
+  }
+}
+
+// Per match: S = f0 f1^T / (C * T), conf = softmax(S,1)*softmax(S,2), global arg-max (first on ties), thr.
+// blockDim = 128; WW <= 25; C <= 128.
+__global__ void __launch_bounds__(128)
+fine_match_kernel(const float* __restrict__ f0, const float* __restrict__ f1, int ww, int c, float inv_temp, float thr,
+                  int* __restrict__ sel, int* __restrict__ fi, int* __restrict__ fj, float* __restrict__ fconf,
+                  float* __restrict__ fine_matrix) {
+  __shared__ float a[25][129], b[25][129];
+  __shared__ float S[25][26];
+  __shared__ float rmax[25], rsum[25], cmax[25], csum[25];
+  __shared__ float best_v[4];
+  __shared__ int best_i[4];
+  const int64_t m = blockIdx.x;
+  const int tid = threadIdx.x;
+  const float norm = 1.f / sqrtf((float)c);
+  for (int e = tid; e < ww * c; e += 128) {
+    const int r = e / c, k = e - r * c;
+    a[r][k] = f0[(m * ww + r) * c + k] * norm;     // feat / C**.5 (fine_matching2.py:52)
+    b[r][k] = f1[(m * ww + r) * c + k] * norm;
+  }
+  __syncthreads();
+  for (int e = tid; e < ww * ww; e += 128) {
+    const int i = e / ww, j = e - i * ww;
+    float acc = 0.f;
+    for (int k = 0; k < c; ++k) acc = fmaf(a[i][k], b[j][k], acc);
+    S[i][j] = acc * inv_temp;
+  }
+  __syncthreads();
+  if (tid < ww) {                       // softmax over dim=2 (row i, across j)
+    float mx = -INFINITY;
+    for (int j = 0; j < ww; ++j) mx = fmaxf(mx, S[tid][j]);
+    float su = 0.f;
+    for (int j = 0; j < ww; ++j) su += expf(S[tid][j] - mx);
+    rmax[tid] = mx; rsum[tid] = su;
+  } else if (tid >= 32 && tid < 32 + ww) {   // softmax over dim=1 (column j, across i)
+    const int j = tid - 32;
+    float mx = -INFINITY;
+    for (int i = 0; i < ww; ++i) mx = fmaxf(mx, S[i][j]);
+    float su = 0.f;
+    for (int i = 0; i < ww; ++i) su += expf(S[i][j] - mx);
+    cmax[j] = mx; csum[j] = su;
+  }
+  __syncthreads();
+  float bv = -1.f;
+  int bi = 0x7fffffff;
+  for (int e = tid; e < ww * ww; e += 128) {
+    const int i = e / ww, j = e - i * ww;
+    const float s = S[i][j];
+    const float cf = (expf(s - cmax[j]) / csum[j]) * (expf(s - rmax[i]) / rsum[i]);
+    if (fine_matrix) fine_matrix[m * ww * ww + e] = cf;
+    if (cf > bv) { bv = cf; bi = e; }   // e increases per thread -> keeps the first index on ties
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if ((tid & 31) == 0) { best_v[tid >> 5] = bv; best_i[tid >> 5] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 4; ++w)
+      if (best_v[w] > bv || (best_v[w] == bv && best_i[w] < bi)) { bv = best_v[w]; bi = best_i[w]; }
+    const bool keep = bv > thr;
+    sel[m] = keep ? 1 : 0;
+    fi[m] = bi / ww; fj[m] = bi % ww;
+    fconf[m] = bv;
+  }
+}
+
+// Ordered compaction of kept fine matches (single CTA, 1024 threads, running base).
+//   mkpts_f = ([cell % W - W/2, cell / W - W/2] + mkpts_c / coarse_scale * c2f_scale) * fine_scale
+__global__ void __launch_bounds__(1024)
+compact_fine_kernel(const int* __restrict__ sel, const int* __restrict__ fi, const int* __restrict__ fj,
+                    const float* __restrict__ fconf, const float* __restrict__ k0c, const float* __restrict__ k1c,
+                    const int64_t* __restrict__ b_ids, int64_t m, int window, float coarse_scale, float c2f, float fine_scale,
+                    float* __restrict__ k0f, float* __restrict__ k1f, float* __restrict__ mconf,
+                    int64_t* __restrict__ m_bids, int* __restrict__ total) {
+  __shared__ int warp_tot[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int half = window / 2;
+  int base = 0;
+  for (int64_t i0 = 0; i0 < m; i0 += 1024) {
+    const int64_t i = i0 + threadIdx.x;
+    const bool flag = i < m && sel[i] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int off = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) { const int v = warp_tot[w]; if (w < warp) off += v; tot += v; }
+    __syncthreads();
+    if (flag) {
+      const int pos = base + off + __popc(bal & ((1u << lane) - 1u));
+      const int ci = fi[i], cj = fj[i];
+      const float c0x = k0c[2 * i] / coarse_scale * c2f, c0y = k0c[2 * i + 1] / coarse_scale * c2f;
+      const float c1x = k1c[2 * i] / coarse_scale * c2f, c1y = k1c[2 * i + 1] / coarse_scale * c2f;
+      k0f[2 * pos] = ((float)(ci % window - half) + c0x) * fine_scale;
+      k0f[2 * pos + 1] = ((float)(ci / window - half) + c0y) * fine_scale;
+      k1f[2 * pos] = ((float)(cj % window - half) + c1x) * fine_scale;
+      k1f[2 * pos + 1] = ((float)(cj / window - half) + c1y) * fine_scale;
+      mconf[pos] = fconf[i];
+      m_bids[pos] = b_ids[i];
+    }
+    base += tot;
+  }
+  if (threadIdx.x == 0) *total = base;
+}
+
+}  // namespace gf
+
+using namespace gf;
+#define STREAM ((cudaStream_t)stream)
+
+extern "C" int gf_fine_gather(const float* fine_nhwc, int hf, int wf, int c, const int64_t* b_ids,
+                              const int64_t* tok_ids, int64_t m, int wc, int stride, int window, float* out,
+                              gf_stream_t stream) {
+  if (m < 0 || c <= 0 || (c % 4) || window <= 0) return gf_set_error(GF_ERR_ARG, "gf_fine_gather: bad shape");
+  if (m == 0) return GF_OK;
+  fine_gather_kernel<<<(unsigned)m, 128, 0, STREAM>>>(fine_nhwc, hf, wf, c, b_ids, tok_ids, wc, stride, window, out);
+  g_launches++;
+  GF_CHECK_LAUNCH();
+  return GF_OK;
+}
+
+extern "C" int gf_fine_match(const float* f0, const float* f1, int64_t m, int ww, int c, float temperature, float thr,
+                             int* sel, int* fi, int* fj, float* fconf, float* fine_matrix, gf_stream_t stream) {
+  if (m < 0 || ww <= 0 || ww > 25 || c <= 0 || c > 128) return gf_set_error(GF_ERR_ARG, "gf_fine_match: ww <= 25, c <= 128");
+  if (m == 0) return GF_OK;
+  fine_match_kernel<<<(unsigned)m, 128, 0, STREAM>>>(f0, f1, ww, c, 1.f / temperature, thr, sel, fi, fj, fconf, fine_matrix);
+  g_launches++;
+  GF_CHECK_LAUNCH();
+  return GF_OK;
+}
+
+extern "C" int gf_compact_fine(const int* sel, const int* fi, const int* fj, const float* fconf, const float* mkpts0_c,
+                               const float* mkpts1_c, const int64_t* b_ids, int64_t m, int window, float coarse_scale,
+                               float c2f_scale, float fine_scale, float* mkpts0_f, float* mkpts1_f, float* mconf,
+                               int64_t* m_bids, int* total, gf_stream_t stream) {
+  if (m < 0 || window <= 0) return gf_set_error(GF_ERR_ARG, "gf_compact_fine: bad shape");
+  compact_fine_kernel<<<1, 1024, 0, STREAM>>>(sel, fi, fj, fconf, mkpts0_c, mkpts1_c, b_ids, m, window, coarse_scale,
+                                              c2f_scale, fine_scale, mkpts0_f, mkpts1_f, mconf, m_bids, total);
+  g_launches++;
+  GF_CHECK_LAUNCH();
+  return GF_OK;
+}

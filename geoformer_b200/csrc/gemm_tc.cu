@@ -1,0 +1,337 @@
+// tcgen05 GEMM core of libgeoformer_sm100.so.
+//
+//   Y[b][M,N] = epilogue( [A | A2][b][M, K] * B[b][N, K]^T )          (both operands K-major)
+//
+// One persistent CTA per SM, warp-specialised (guide "Canonical Blackwell GEMM" anatomy):
+//   warp 0      TMA producer   : cp.async.bulk.tensor (128B-swizzled boxes) into a 4..6 stage smem ring
+//   warp 1      MMA issuer     : one elected lane issues tcgen05.mma (M=128, N=BN, K=32 bytes per instruction),
+//                                accumulating in TMEM; double-buffered accumulator (2 x BN columns)
+//   warps 2..5  epilogue       : tcgen05.ld (thread == output row), fused bias / activation / LayerNorm /
+//                                residual, direct global stores
+// kind::tf32 consumes fp32 activations straight from HBM (no conversion pass); kind::f16 is used by the
+// split-fp16 similarity.  Tile: 128 x BN x (128 bytes of K).
+#include "common.cuh"
+#include "ptx.cuh"
+
+#include <atomic>
+
+namespace gf {
+
+struct GemmParams {
+  float* Y;
+  int64_t ldy;
+  int64_t y_batch_stride;
+  int M, N, batches;
+  int kblocks1, kblocks2;
+  int epi, act_cols;
+  const float* bias;
+  const float* rowbias;
+  int rowbias_group;
+  const float* gamma;
+  const float* beta;
+  const float* residual;
+  int64_t ldres;
+  float out_scale;
+  const int* m_dev;
+  int tiles_n;
+};
+
+constexpr int kBM = 128;
+constexpr int kStageABytes = kBM * 128;
+
+template <int BN> struct GemmCfg {
+  static constexpr int kStageBBytes = BN * 128;
+  static constexpr int kStageBytes = kStageABytes + kStageBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float apply_act(float x, int epi, bool in_act_cols) {
+  if (epi & GF_EPI_RELU) x = fmaxf(x, 0.f);
+  if (epi & GF_EPI_TANH) x = tanhf(x);
+  if ((epi & GF_EPI_ELU1) && in_act_cols) x = elu1(x);
+  return x;
+}
+
+template <int KIND, int BN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int BKE = (KIND == 0) ? 32 : 64;   // elements per 128-byte K block
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  int m_live = p.M;
+  if (p.m_dev != nullptr) m_live = min(p.M, max(0, *p.m_dev));
+  const int tiles_m = (m_live + kBM - 1) / kBM;
+  const int total_tiles = p.batches * tiles_m * p.tiles_n;
+  const int kblocks = p.kblocks1 + p.kblocks2;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmA2);
+    ptx::prefetch_tmap(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < Cfg::kStages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+      for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], 4); }
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n_blk = t % p.tiles_n;
+        const int rest = t / p.tiles_n;
+        const int m_blk = rest % tiles_m;
+        const int batch = rest / tiles_m;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + kStageABytes;
+          ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (kb < p.kblocks1) ptx::tma_load_3d(sa, &tmA, &full_bar[stage], kb * BKE, m_blk * kBM, batch);
+          else                 ptx::tma_load_3d(sa, &tmA2, &full_bar[stage], (kb - p.kblocks1) * BKE, m_blk * kBM, batch);
+          ptx::tma_load_3d(sb, &tmB, &full_bar[stage], kb * BKE, n_blk * BN, batch);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc(KIND == 0 ? 2 : 0, kBM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_addr(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + kStageABytes;
+          const uint64_t adesc = ptx::umma_desc_sw128(sa);
+          const uint64_t bdesc = ptx::umma_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // advance 32 bytes of K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+            ptx::umma<KIND>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tmem_full[acc]);              // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (warps 2..5) ------------------------------
+    const int quad = warp & 3;                           // TMEM lane quadrant this warp may access
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int n_blk = t % p.tiles_n;
+      const int rest = t / p.tiles_n;
+      const int m_blk = rest % tiles_m;
+      const int batch = rest / tiles_m;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const int row = m_blk * kBM + quad * 32 + lane;
+      const bool row_ok = row < m_live;
+      const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
+      float* yrow = p.Y + (int64_t)batch * p.y_batch_stride + (int64_t)row * p.ldy;
+      const float* rrow = p.residual ? p.residual + (int64_t)row * p.ldres : nullptr;
+      const float* rb = p.rowbias ? p.rowbias + (int64_t)(row / p.rowbias_group) * p.N : nullptr;
+      const int col0 = n_blk * BN;
+      float mean = 0.f, rstd = 1.f;
+      if (p.epi & GF_EPI_LN) {
+        // LayerNorm over the full row (BN == N): two extra sweeps over TMEM (mean, then centred variance)
+        float s = 0.f;
+        for (int c = 0; c < BN; c += 32) {
+          float v[32];
+          ptx::tmem_ld_32x32(t_row + c, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s += v[j] * p.out_scale;
+        }
+        mean = s * (1.f / BN);
+        float q = 0.f;
+        for (int c = 0; c < BN; c += 32) {
+          float v[32];
+          ptx::tmem_ld_32x32(t_row + c, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { const float d = v[j] * p.out_scale - mean; q += d * d; }
+        }
+        rstd = rsqrtf(q * (1.f / BN) + 1e-5f);
+      }
+      for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        ptx::tmem_ld_32x32(t_row + c, v);
+        ptx::tmem_ld_wait();
+        const int gc = col0 + c;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = v[j] * p.out_scale;
+          const int col = gc + j;
+          if (col < p.N) {
+            if (p.bias) x += __ldg(p.bias + col);
+            if (rb && row_ok) x += __ldg(rb + col);
+            x = apply_act(x, p.epi, col < p.act_cols);
+            if (p.epi & GF_EPI_LN) x = (x - mean) * rstd * __ldg(p.gamma + col) + __ldg(p.beta + col);
+            if (rrow && row_ok) x += __ldg(rrow + col);
+          }
+          v[j] = x;
+        }
+        if (row_ok) {
+          if (gc + 32 <= p.N && (p.ldy & 3) == 0 && (p.y_batch_stride & 3) == 0) {
+            float4* dst = reinterpret_cast<float4*>(yrow + gc);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            for (int j = 0; j < 32; ++j) if (gc + j < p.N) yrow[gc + j] = v[j];
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int g_num_sms = 0;
+std::atomic<int64_t> g_launches{0};
+
+int init_driver(int device) {
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return gf_set_error(GF_ERR_LAUNCH, "cudaGetDeviceProperties failed");
+  if (prop.major != 10) return gf_set_error(GF_ERR_DEVICE, "libgeoformer_sm100 needs an sm_100 (B200) device");
+  g_num_sms = prop.multiProcessorCount;
+  if (cudaSetDevice(device) != cudaSuccess) return gf_set_error(GF_ERR_LAUNCH, "cudaSetDevice failed");
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr)
+    return gf_set_error(GF_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not found");
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return GF_OK;
+}
+int num_sms() { return g_num_sms; }
+
+// 3-D K-major operand map: dims {K, rows, batches}; box {128 bytes of K, box_rows, 1}; 128B swizzle; OOB -> 0
+static int make_tmap(CUtensorMap* m, const void* base, int esize, int64_t k, int64_t rows, int64_t batches,
+                     int64_t row_stride_elems, int64_t batch_stride_elems, int box_rows) {
+  if (!g_encode) return gf_set_error(GF_ERR_DRIVER, "gf_init() was not called");
+  cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, (cuuint64_t)batches};
+  cuuint64_t strides[2] = {(cuuint64_t)(row_stride_elems * esize), (cuuint64_t)(batch_stride_elems * esize)};
+  if (batches == 1) strides[1] = strides[0] * (cuuint64_t)rows;
+  cuuint32_t box[3] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapDataType dt = esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = g_encode(m, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return gf_set_error(GF_ERR_DRIVER, "cuTensorMapEncodeTiled failed");
+  return GF_OK;
+}
+
+template <int KIND, int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const GemmParams& p,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  auto kern = gemm_tc_kernel<KIND, BN>;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+      return gf_set_error(GF_ERR_LAUNCH, "cudaFuncSetAttribute(smem) failed");
+    attr_set = true;
+  }
+  const int64_t tiles = (int64_t)p.batches * gf_cdiv(p.M, kBM) * p.tiles_n;
+  if (tiles == 0) return GF_OK;
+  const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
+  kern<<<grid, 192, Cfg::kSmemBytes, stream>>>(ta, ta2, tb, p);
+  g_launches++;
+  GF_CHECK_LAUNCH();
+  return GF_OK;
+}
+
+}  // namespace gf
+
+using namespace gf;
+
+extern "C" int gf_linear_tf32(const float* A, const float* A2, const float* W, float* Y, int64_t M, int N, int K1,
+                              int K2, int epi, int act_cols, const float* bias, const float* rowbias,
+                              int rowbias_group, const float* gamma, const float* beta, const float* residual,
+                              const int* m_dev, gf_stream_t stream) {
+  if (M < 0 || N <= 0 || K1 <= 0 || K2 < 0 || (N % 128) || (K1 % 32) || (K2 % 32) || M > 0x7fffff00LL)
+    return gf_set_error(GF_ERR_ARG, "gf_linear_tf32: need N % 128 == 0, K % 32 == 0");
+  if ((epi & GF_EPI_LN) && !(N == 128 || N == 256)) return gf_set_error(GF_ERR_ARG, "gf_linear_tf32: LN epilogue needs N in {128,256}");
+  if ((epi & GF_EPI_LN) && (!gamma || !beta)) return gf_set_error(GF_ERR_ARG, "gf_linear_tf32: LN epilogue needs gamma/beta");
+  if (K2 > 0 && !A2) return gf_set_error(GF_ERR_ARG, "gf_linear_tf32: A2 missing");
+  if (rowbias && rowbias_group <= 0) return gf_set_error(GF_ERR_ARG, "gf_linear_tf32: rowbias_group");
+  if (M == 0) return GF_OK;
+  const int BN = (N % 256 == 0) ? 256 : 128;
+  CUtensorMap ta, ta2, tb;
+  int rc;
+  if ((rc = make_tmap(&ta, A, 4, K1, M, 1, K1, 0, kBM))) return rc;
+  if (K2 > 0) { if ((rc = make_tmap(&ta2, A2, 4, K2, M, 1, K2, 0, kBM))) return rc; } else ta2 = ta;
+  if ((rc = make_tmap(&tb, W, 4, K1 + K2, N, 1, K1 + K2, 0, BN))) return rc;
+  GemmParams p{};
+  p.Y = Y; p.ldy = N; p.y_batch_stride = 0; p.M = (int)M; p.N = N; p.batches = 1;
+  p.kblocks1 = K1 / 32; p.kblocks2 = K2 / 32; p.epi = epi; p.act_cols = act_cols;
+  p.bias = bias; p.rowbias = rowbias; p.rowbias_group = rowbias_group > 0 ? rowbias_group : 1;
+  p.gamma = gamma; p.beta = beta; p.residual = residual; p.ldres = N; p.out_scale = 1.f; p.m_dev = m_dev;
+  p.tiles_n = N / BN;
+  if (BN == 256) return launch_gemm<0, 256>(ta, ta2, tb, p, (cudaStream_t)stream);
+  return launch_gemm<0, 128>(ta, ta2, tb, p, (cudaStream_t)stream);
+}
+
+extern "C" int gf_similarity_f16x3(const void* a3, const void* b3, float* sim, int n, int l, int s, int c3,
+                                   float out_scale, gf_stream_t stream) {
+  if (n <= 0 || l <= 0 || s <= 0 || c3 <= 0 || (c3 % 64)) return gf_set_error(GF_ERR_ARG, "gf_similarity_f16x3: c3 % 64 != 0");
+  CUtensorMap ta, tb;
+  int rc;
+  constexpr int BN = 256;
+  if ((rc = make_tmap(&ta, a3, 2, c3, l, n, c3, (int64_t)l * c3, kBM))) return rc;
+  if ((rc = make_tmap(&tb, b3, 2, c3, s, n, c3, (int64_t)s * c3, BN))) return rc;
+  GemmParams p{};
+  p.Y = sim; p.ldy = s; p.y_batch_stride = (int64_t)l * s; p.M = l; p.N = s; p.batches = n;
+  p.kblocks1 = c3 / 64; p.kblocks2 = 0; p.epi = 0; p.act_cols = 0; p.rowbias_group = 1; p.ldres = s;
+  p.out_scale = out_scale; p.tiles_n = gf_cdiv(s, BN);
+  return launch_gemm<1, 256>(ta, ta, tb, p, (cudaStream_t)stream);
+}

@@ -1,0 +1,271 @@
+// Geometrized attention kernels (model/geo_module.py:51-94, utils/common_utils.py:65-91,166-181,
+// utils/homography.py:86-105, model/geo_transformer/transformer.py:111-139, geo_attention.py:72-100).
+#include "common.cuh"
+
+#include <atomic>
+
+namespace gf {
+extern std::atomic<int64_t> g_launches;
+
+// ---------------------------------------------------------------------------------------------
+// window token table.  One thread per (sample, source token).
+//   centre = H * (x, y, 1) with x = col*scale, y = row*scale (fp32, z==0 -> 1e-6)
+//   slot w = r*window + c : (kx, ky) = centre + ((c-half)*scale, (r-half)*scale)
+//   out of [0,W) x [0,H)  -> -1 ;  else token = (int(ky)/scale) * w_dst_c + int(kx)/scale
+// ---------------------------------------------------------------------------------------------
+__global__ void geo_window_table_kernel(const float* __restrict__ hmat, const int* __restrict__ has_h, int n, int l,
+                                        int w_src_c, int h_dst_px, int w_dst_px, int w_dst_c, int scale, int window,
+                                        int* __restrict__ widx) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n * l) return;
+  const int b = (int)(idx / l);
+  const int tok = (int)(idx - (int64_t)b * l);
+  int* out = widx + idx * window * window;
+  if (!has_h[b]) {
+    for (int w = 0; w < window * window; ++w) out[w] = -1;
+    return;
+  }
+  const float* H = hmat + b * 9;
+  const float x = (float)((tok % w_src_c) * scale), y = (float)((tok / w_src_c) * scale);
+  // k = 0,1,2 accumulation order of a 3-term sgemm dot product
+  float wx = __fmaf_rn(H[2], 1.f, __fmaf_rn(H[1], y, __fmul_rn(H[0], x)));
+  float wy = __fmaf_rn(H[5], 1.f, __fmaf_rn(H[4], y, __fmul_rn(H[3], x)));
+  float wz = __fmaf_rn(H[8], 1.f, __fmaf_rn(H[7], y, __fmul_rn(H[6], x)));
+  if (wz == 0.f) wz = 1e-6f;
+  const float cx = __fdiv_rn(wx, wz), cy = __fdiv_rn(wy, wz);
+  const int half = window / 2;
+  for (int r = 0; r < window; ++r) {
+    for (int c = 0; c < window; ++c) {
+      const float kx = __fadd_rn(cx, (float)((c - half) * scale));
+      const float ky = __fadd_rn(cy, (float)((r - half) * scale));
+      const bool oob = (kx < 0.f) | (ky < 0.f) | (kx >= (float)w_dst_px) | (ky >= (float)h_dst_px) | !(kx == kx) | !(ky == ky);
+      int t = -1;
+      if (!oob) t = ((int)ky / scale) * w_dst_c + ((int)kx / scale);
+      out[r * window + c] = t;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// self attention against anchor tokens: flash-style online softmax, fp32 FFMA.
+// grid (ceil(l/64), heads, n); 256 threads as 16x16, each thread owns a 4x4 block of the 64x64 score tile
+// and a 4x4 block of the 64x64 output tile (dim == 64).
+// ---------------------------------------------------------------------------------------------
+constexpr int kSA = 64;          // queries per CTA == keys per tile == head dim
+constexpr int kSAPad = kSA + 4;
+
+__global__ void __launch_bounds__(256)
+geo_self_attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
+                          const float* __restrict__ v, int ldv, float* __restrict__ out, int l, int heads,
+                          const int* __restrict__ anchor_idx, const int* __restrict__ anchor_cnt, int anchor_cap,
+                          float softmax_scale) {
+  extern __shared__ float sh[];
+  float* Qs = sh;                         // [64][64]
+  float* Kt = Qs + kSA * kSA;             // [64 d][68 keys]
+  float* Vs = Kt + kSA * kSAPad;          // [64 keys][68]
+  float* Ps = Vs + kSA * kSAPad;          // [64 q][68]
+  const int n = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kSA;
+  const int cnt = anchor_cnt[n];
+  const int c = heads * kSA;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  if (cnt == 0) {
+    for (int e = tid; e < kSA * kSA; e += 256) {
+      const int r = e >> 6, d = e & 63;
+      if (q0 + r < l) out[((int64_t)n * l + q0 + r) * c + h * kSA + d] = 0.f;
+    }
+    return;
+  }
+  for (int e = tid; e < kSA * kSA; e += 256) {
+    const int r = e >> 6, d = e & 63;
+    Qs[e] = (q0 + r < l) ? q[((int64_t)n * l + q0 + r) * ldq + h * kSA + d] : 0.f;
+  }
+  float m_run[4], l_run[4], o[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m_run[i] = -INFINITY; l_run[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+  }
+  const int* aidx = anchor_idx + (int64_t)n * anchor_cap;
+  for (int k0 = 0; k0 < cnt; k0 += kSA) {
+    __syncthreads();   // previous tile fully consumed (also covers the Qs fill on the first iteration)
+    for (int e = tid; e < kSA * kSA; e += 256) {
+      const int r = e >> 6, d = e & 63;
+      float kv = 0.f, vv = 0.f;
+      if (k0 + r < cnt) {
+        const int64_t tok = (int64_t)n * l + aidx[k0 + r];
+        kv = k[tok * ldk + h * kSA + d];
+        vv = v[tok * ldv + h * kSA + d];
+      }
+      Kt[d * kSAPad + r] = kv;
+      Vs[r * kSAPad + d] = vv;
+    }
+    __syncthreads();
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < kSA; ++d) {
+      const float4 kk = *reinterpret_cast<const float4*>(&Kt[d * kSAPad + 4 * tx]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float qv = Qs[(4 * ty + i) * kSA + d];
+        s[i][0] = fmaf(qv, kk.x, s[i][0]); s[i][1] = fmaf(qv, kk.y, s[i][1]);
+        s[i][2] = fmaf(qv, kk.z, s[i][2]); s[i][3] = fmaf(qv, kk.w, s[i][3]);
+      }
+    }
+    float alpha[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[i][j] = (k0 + 4 * tx + j < cnt) ? s[i][j] * softmax_scale : -INFINITY;
+        mx = fmaxf(mx, s[i][j]);
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      const float m_new = fmaxf(m_run[i], mx);      // finite: every tile has >= 1 live key
+      alpha[i] = expf(m_run[i] - m_new);
+      float rs = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s[i][j] = expf(s[i][j] - m_new); rs += s[i][j]; }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, off);
+      l_run[i] = l_run[i] * alpha[i] + rs;
+      m_run[i] = m_new;
+      *reinterpret_cast<float4*>(&Ps[(4 * ty + i) * kSAPad + 4 * tx]) = make_float4(s[i][0], s[i][1], s[i][2], s[i][3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[i][j] *= alpha[i];
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < kSA; ++kk) {
+      const float4 vv = *reinterpret_cast<const float4*>(&Vs[kk * kSAPad + 4 * tx]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float pv = Ps[(4 * ty + i) * kSAPad + kk];
+        o[i][0] = fmaf(pv, vv.x, o[i][0]); o[i][1] = fmaf(pv, vv.y, o[i][1]);
+        o[i][2] = fmaf(pv, vv.z, o[i][2]); o[i][3] = fmaf(pv, vv.w, o[i][3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = q0 + 4 * ty + i;
+    if (r < l) {
+      const float inv = 1.f / l_run[i];
+      *reinterpret_cast<float4*>(&out[((int64_t)n * l + r) * c + h * kSA + 4 * tx]) =
+          make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cross attention: one warp per query token, all heads; lane owns 8 consecutive channels
+// (heads*dim == 256, dim == 64 -> 8 lanes per head).  Keys/values are gathered rows of the
+// once-projected K/V of the other image (project-then-gather; the reference gathers-then-projects,
+// which is the same arithmetic per row but 25x the FLOPs).
+// ---------------------------------------------------------------------------------------------
+__global__ void geo_cross_attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ kp, int ldk,
+                                           const float* __restrict__ vp, int ldv, float* __restrict__ out, int n, int l,
+                                           int s, const int* __restrict__ widx, int window2, float softmax_scale) {
+  const int64_t tok = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (tok >= (int64_t)n * l) return;
+  const int b = (int)(tok / l);
+  const int* wi = widx + tok * window2;
+  const float4 q0 = *reinterpret_cast<const float4*>(q + tok * ldq + lane * 8);
+  const float4 q1 = *reinterpret_cast<const float4*>(q + tok * ldq + lane * 8 + 4);
+  float sc[25];
+  int id[25];
+  float mx = -INFINITY;
+  int live = 0;
+#pragma unroll
+  for (int w = 0; w < 25; ++w) {
+    const int t = w < window2 ? wi[w] : -1;
+    id[w] = t;
+    float d = 0.f;
+    if (t >= 0) {
+      const float* kr = kp + ((int64_t)b * s + t) * ldk + lane * 8;
+      const float4 k0 = *reinterpret_cast<const float4*>(kr);
+      const float4 k1 = *reinterpret_cast<const float4*>(kr + 4);
+      d = q0.x * k0.x + q0.y * k0.y + q0.z * k0.z + q0.w * k0.w + q1.x * k1.x + q1.y * k1.y + q1.z * k1.z + q1.w * k1.w;
+      ++live;
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 4);
+    // masked_fill_(~mask, -1e8) happens BEFORE the 1/sqrt(D) temperature (geo_attention.py:83-91)
+    sc[w] = (t >= 0 ? d : -1e8f) * softmax_scale;
+    if (w < window2) mx = fmaxf(mx, sc[w]);
+  }
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (live > 0) {          // all-masked rows are zeroed (geo_attention.py:98-100)
+    float den = 0.f;
+#pragma unroll
+    for (int w = 0; w < 25; ++w) {
+      if (w < window2) { sc[w] = expf(sc[w] - mx); den += sc[w]; }
+    }
+    const float inv = 1.f / den;
+#pragma unroll
+    for (int w = 0; w < 25; ++w) {
+      if (w < window2 && id[w] >= 0) {
+        const float p = sc[w] * inv;
+        const float* vr = vp + ((int64_t)b * s + id[w]) * ldv + lane * 8;
+        const float4 v0 = *reinterpret_cast<const float4*>(vr);
+        const float4 v1 = *reinterpret_cast<const float4*>(vr + 4);
+        acc[0] = fmaf(p, v0.x, acc[0]); acc[1] = fmaf(p, v0.y, acc[1]); acc[2] = fmaf(p, v0.z, acc[2]); acc[3] = fmaf(p, v0.w, acc[3]);
+        acc[4] = fmaf(p, v1.x, acc[4]); acc[5] = fmaf(p, v1.y, acc[5]); acc[6] = fmaf(p, v1.z, acc[6]); acc[7] = fmaf(p, v1.w, acc[7]);
+      }
+    }
+  }
+  float* o = out + tok * 256 + lane * 8;
+  *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
+}  // namespace gf
+
+using namespace gf;
+#define STREAM ((cudaStream_t)stream)
+
+extern "C" int gf_geo_window_table(const float* hmat, const int* has_h, int n, int h_src_c, int w_src_c, int h_dst_px,
+                                   int w_dst_px, int w_dst_c, int scale, int window, int* widx, gf_stream_t stream) {
+  if (n <= 0 || h_src_c <= 0 || w_src_c <= 0 || scale <= 0 || window <= 0 || window > 5)
+    return gf_set_error(GF_ERR_ARG, "gf_geo_window_table: bad shape");
+  const int l = h_src_c * w_src_c;
+  geo_window_table_kernel<<<gf_cdiv((int64_t)n * l, 128), 128, 0, STREAM>>>(hmat, has_h, n, l, w_src_c, h_dst_px, w_dst_px,
+                                                                          w_dst_c, scale, window, widx);
+  g_launches++;
+  GF_CHECK_LAUNCH();
+  return GF_OK;
+}
+
+extern "C" int gf_geo_self_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                                     float* out, int n, int l, int heads, int dim, const int* anchor_idx,
+                                     const int* anchor_cnt, int anchor_cap, gf_stream_t stream) {
+  if (n <= 0 || l <= 0 || heads <= 0 || dim != 64) return gf_set_error(GF_ERR_ARG, "gf_geo_self_attention: dim must be 64");
+  const size_t smem = (size_t)(kSA * kSA + 3 * kSA * kSAPad) * sizeof(float);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(geo_self_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  geo_self_attention_kernel<<<dim3(gf_cdiv(l, kSA), heads, n), 256, smem, STREAM>>>(
+      q, ldq, k, ldk, v, ldv, out, l, heads, anchor_idx, anchor_cnt, anchor_cap, 1.f / sqrtf((float)dim));
+  g_launches++;
+  GF_CHECK_LAUNCH();
+  return GF_OK;
+}
+
+extern "C" int gf_geo_cross_attention(const float* q, int ldq, const float* kproj, int ldk, const float* vproj, int ldv,
+                                      float* out, int n, int l, int s, int heads, int dim, const int* widx, int window2,
+                                      gf_stream_t stream) {
+  if (n <= 0 || l <= 0 || s <= 0 || heads * dim != 256 || dim != 64 || window2 <= 0 || window2 > 25)
+    return gf_set_error(GF_ERR_ARG, "gf_geo_cross_attention: needs heads*dim == 256, dim == 64, window <= 25");
+  geo_cross_attention_kernel<<<gf_cdiv((int64_t)n * l, 4), 128, 0, STREAM>>>(q, ldq, kproj, ldk, vproj, ldv, out, n, l, s,
+                                                                            widx, window2, 1.f / sqrtf((float)dim));
+  g_launches++;
+  GF_CHECK_LAUNCH();
+  return GF_OK;
+}

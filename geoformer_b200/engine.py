@@ -1,0 +1,372 @@
+"""Host-side orchestration of the GeoFormer hot path on one B200.
+
+Follows the stage order of the reference ``model/full_model.py:39-123``; every stage except the
+CNN backbone (cuDNN through torch for now) and the host RANSAC
+(``cv2.findHomography``, geo_module.py:48, kept for parity by construction) runs in hand-written
+sm_100a kernels reached through the C ABI (``geoformer_b200.ops``).
+"""
+from __future__ import annotations
+
+import math
+import os
+from concurrent.futures import ThreadPoolExecutor
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .ops import EPI_ELU1, EPI_LN, EPI_RELU, EPI_TANH
+
+_POOL: Optional[ThreadPoolExecutor] = None
+
+
+def _pool() -> ThreadPoolExecutor:
+    global _POOL
+    if _POOL is None:
+        _POOL = ThreadPoolExecutor(max_workers=max(2, min(16, os.cpu_count() or 2)))
+    return _POOL
+
+
+# --------------------------------------------------------------------------------------------
+# weight packing
+# --------------------------------------------------------------------------------------------
+def _fold_bn(w: torch.Tensor, sd: Dict[str, torch.Tensor], bn: str, eps: float = 1e-5):
+    """conv + eval-mode BN -> conv with bias: w' = w * g/sqrt(v+eps), b' = beta - mean * g/sqrt(v+eps)."""
+    s = sd[bn + ".weight"].double() / torch.sqrt(sd[bn + ".running_var"].double() + eps)
+    wf = (w.double() * s[:, None, None, None]).float()
+    bf = (sd[bn + ".bias"].double() - sd[bn + ".running_mean"].double() * s).float()
+    return wf, bf
+
+
+class PackedWeights:
+    """Device-resident, kernel-ready weights derived from a reference-schema state dict."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], device: torch.device, backbone_dtype: torch.dtype):
+        f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
+        self.device = device
+        self.backbone_dtype = backbone_dtype
+
+        def enc(prefix: str, n_layers: int):
+            layers = []
+            for i in range(n_layers):
+                p = f"{prefix}.layers.{i}."
+                wq, wk, wv = sd[p + "q_proj.weight"], sd[p + "k_proj.weight"], sd[p + "v_proj.weight"]
+                layers.append(dict(
+                    wq=f32(wq), wkv=f32(torch.cat([wk, wv], 0)), wqkv=f32(torch.cat([wq, wk, wv], 0)),
+                    wm=f32(sd[p + "merge.weight"]), w1=f32(sd[p + "mlp.0.weight"]), w2=f32(sd[p + "mlp.2.weight"]),
+                    n1w=f32(sd[p + "norm1.weight"]), n1b=f32(sd[p + "norm1.bias"]),
+                    n2w=f32(sd[p + "norm2.weight"]), n2b=f32(sd[p + "norm2.bias"])))
+            return layers
+
+        self.coarse = enc("loftr_coarse", 8)
+        self.geo = enc("geo_module.des_transformer", 4)
+        self.fine = enc("loftr_fine", 2)
+        wm = sd["fine_preprocess.merge_feat.weight"]
+        cf = wm.shape[0]
+        self.fp = dict(wd=f32(sd["fine_preprocess.down_proj.weight"]), bd=f32(sd["fine_preprocess.down_proj.bias"]),
+                       wa=f32(wm[:, :cf]), wb=f32(wm[:, cf:]), bm=f32(sd["fine_preprocess.merge_feat.bias"]))
+
+        # backbone: BN folded, channels-last, tensor-core dtype (cuDNN through torch)
+        def conv(name, bn=None):
+            w = sd["backbone." + name + ".weight"]
+            b = None
+            if bn is not None:
+                w, b = _fold_bn(w, {k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")}, bn)
+            w = w.detach().to(device=device, dtype=backbone_dtype).contiguous(memory_format=torch.channels_last)
+            b = None if b is None else b.to(device=device, dtype=backbone_dtype)
+            return w, b
+
+        bb = {"conv1": conv("conv1", "bn1")}
+        for li in (1, 2, 3):
+            for bi in (0, 1):
+                p = f"layer{li}.{bi}"
+                bb[p + ".conv1"] = conv(p + ".conv1", p + ".bn1")
+                bb[p + ".conv2"] = conv(p + ".conv2", p + ".bn2")
+                if li > 1 and bi == 0:
+                    bb[p + ".down"] = conv(p + ".downsample.0", p + ".downsample.1")
+        bb["layer3_outconv"] = conv("layer3_outconv")
+        bb["layer2_outconv"] = conv("layer2_outconv")
+        bb["layer2_outconv2.0"] = conv("layer2_outconv2.0", "layer2_outconv2.1")
+        bb["layer2_outconv2.3"] = conv("layer2_outconv2.3")
+        bb["layer1_outconv"] = conv("layer1_outconv")
+        bb["layer1_outconv2.0"] = conv("layer1_outconv2.0", "layer1_outconv2.1")
+        bb["layer1_outconv2.3"] = conv("layer1_outconv2.3")
+        self.bb = bb
+        self._pe: Dict[Tuple[int, int, int], torch.Tensor] = {}
+
+    def pos_table(self, c: int, h: int, w: int) -> torch.Tensor:
+        """[h*w, c] sinusoidal table in token-major layout.  Bug-compatible with the reference
+        (position_encoding.py:28: ``-ln(1e4) / d_model // 2`` == -1.0, i.e. div_term[k] = exp(-2k))."""
+        key = (c, h, w)
+        if key not in self._pe:
+            ypos = torch.ones(h, w).cumsum(0).float().unsqueeze(0)
+            xpos = torch.ones(h, w).cumsum(1).float().unsqueeze(0)
+            div = torch.exp(torch.arange(0, c // 2, 2).float() * (-math.log(10000.0) / c // 2))[:, None, None]
+            pe = torch.zeros(c, h, w)
+            pe[0::4] = torch.sin(xpos * div); pe[1::4] = torch.cos(xpos * div)
+            pe[2::4] = torch.sin(ypos * div); pe[3::4] = torch.cos(ypos * div)
+            self._pe[key] = pe.permute(1, 2, 0).reshape(h * w, c).contiguous().to(self.device)
+        return self._pe[key]
+
+
+# --------------------------------------------------------------------------------------------
+# backbone (resnet_fpn.py:100-118) — cuDNN, channels-last, BN folded
+# --------------------------------------------------------------------------------------------
+def backbone_forward(pw: PackedWeights, img: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[B,1,H,W] fp32 -> coarse NHWC [B,H/8,W/8,256] fp32, fine NHWC [B,H/2,W/2,128] fp32 (both contiguous)."""
+    bb = pw.bb
+    x = img.to(pw.backbone_dtype).contiguous(memory_format=torch.channels_last)
+
+    def cv(name, t, stride=1, pad=1):
+        w, b = bb[name]
+        return F.conv2d(t, w, b, stride, pad)
+
+    def block(p, t, stride):
+        y = F.relu_(cv(p + ".conv1", t, stride))
+        y = cv(p + ".conv2", y)
+        if (p + ".down") in bb:
+            t = cv(p + ".down", t, stride, 0)
+        return F.relu_(y.add_(t))
+
+    x0 = F.relu_(cv("conv1", x, 2, 3))
+    x1 = block("layer1.1", block("layer1.0", x0, 1), 1)
+    x2 = block("layer2.1", block("layer2.0", x1, 2), 1)
+    x3 = block("layer3.1", block("layer3.0", x2, 2), 1)
+    x3o = cv("layer3_outconv", x3, 1, 0)
+    x2o = cv("layer2_outconv", x2, 1, 0)
+    x2o = x2o + F.interpolate(x3o, size=x2o.shape[2:], mode="bilinear", align_corners=True)
+    x2o = cv("layer2_outconv2.3", F.leaky_relu_(cv("layer2_outconv2.0", x2o), 0.01))
+    x1o = cv("layer1_outconv", x1, 1, 0)
+    x1o = x1o + F.interpolate(x2o, size=x1o.shape[2:], mode="bilinear", align_corners=True)
+    x1o = cv("layer1_outconv2.3", F.leaky_relu_(cv("layer1_outconv2.0", x1o), 0.01))
+    coarse = x3o.permute(0, 2, 3, 1).float().contiguous()
+    fine = x1o.permute(0, 2, 3, 1).float().contiguous()
+    return coarse, fine
+
+
+# --------------------------------------------------------------------------------------------
+# transformer layers
+# --------------------------------------------------------------------------------------------
+def _post_attention(lw: dict, x2d: torch.Tensor, msg: torch.Tensor, act: int) -> torch.Tensor:
+    """merge -> LN1 -> MLP(cat[x, msg]) -> LN2 -> residual   (transformer.py:53-60)."""
+    m1 = ops.linear(msg, lw["wm"], epi=EPI_LN, gamma=lw["n1w"], beta=lw["n1b"])
+    h = ops.linear(x2d, lw["w1"], a2=m1, epi=act)
+    return ops.linear(h, lw["w2"], epi=EPI_LN, gamma=lw["n2w"], beta=lw["n2b"], residual=x2d)
+
+
+def loftr_layer(lw: dict, x: torch.Tensor, src: torch.Tensor, heads: int) -> torch.Tensor:
+    """LoFTR encoder layer with linear attention; x [n,L,C], src [n,S,C] -> [n,L,C]."""
+    n, l, c = x.shape
+    s = src.shape[1]
+    d = c // heads
+    x2d = x.reshape(n * l, c)
+    if x is src:
+        qkv = ops.linear(x2d, lw["wqkv"], epi=EPI_ELU1, act_cols=2 * c)          # [Q=elu+1 | K=elu+1 | V]
+        q, k, v, ldq, ldk = qkv, qkv[:, c:], qkv[:, 2 * c:], 3 * c, 3 * c
+    else:
+        q = ops.linear(x2d, lw["wq"], epi=EPI_ELU1, act_cols=c)
+        kv = ops.linear(src.reshape(n * s, c), lw["wkv"], epi=EPI_ELU1, act_cols=c)
+        k, v, ldq, ldk = kv, kv[:, c:], c, 2 * c
+    msg = ops.linattn(q, ldq, k, ldk, v, ldk, n, l, s, heads, d)
+    return _post_attention(lw, x2d, msg, EPI_RELU).view(n, l, c)
+
+
+def coarse_transformer(pw: PackedWeights, x0: torch.Tensor, x1: torch.Tensor, names, heads: int):
+    """loftr_module/transformer.py:82-104.  Same-size pairs run both images as one 2n-sample batch."""
+    n = x0.shape[0]
+    same = x0.shape == x1.shape
+    if same:
+        X = torch.cat([x0, x1], 0)
+        x0, x1 = X[:n], X[n:]
+    for lw, name in zip(pw.coarse, names):
+        if name == "self":
+            if same:
+                X = loftr_layer(lw, X, X, heads)
+                x0, x1 = X[:n], X[n:]
+            else:
+                x0 = loftr_layer(lw, x0, x0, heads)
+                x1 = loftr_layer(lw, x1, x1, heads)
+        else:
+            y0 = loftr_layer(lw, x0, x1, heads)
+            y1 = loftr_layer(lw, x1, y0, heads)       # sees the UPDATED feat0 (transformer.py:99-100)
+            if same:
+                X = torch.cat([y0, y1], 0)
+                x0, x1 = X[:n], X[n:]
+            else:
+                x0, x1 = y0, y1
+    return x0, x1
+
+
+def fine_layer(lw: dict, x: torch.Tensor, src: torch.Tensor, heads: int) -> torch.Tensor:
+    """LoFTR layer at the fine level: x/src [m, 25, 128]; one CTA per window for the attention."""
+    m, t, c = x.shape
+    d = c // heads
+    x2d = x.reshape(m * t, c)
+    if x is src:
+        qkv = ops.linear(x2d, lw["wqkv"], epi=EPI_ELU1, act_cols=2 * c)
+        q, k, v, ldq, ldk = qkv, qkv[:, c:], qkv[:, 2 * c:], 3 * c, 3 * c
+    else:
+        q = ops.linear(x2d, lw["wq"], epi=EPI_ELU1, act_cols=c)
+        kv = ops.linear(src.reshape(m * t, c), lw["wkv"], epi=EPI_ELU1, act_cols=c)
+        k, v, ldq, ldk = kv, kv[:, c:], c, 2 * c
+    msg = ops.linattn_window(q, ldq, k, ldk, v, ldk, m, t, heads, d)
+    return _post_attention(lw, x2d, msg, EPI_RELU).view(m, t, c)
+
+
+# --------------------------------------------------------------------------------------------
+# coarse matching
+# --------------------------------------------------------------------------------------------
+def coarse_matching(f0: torch.Tensor, f1: torch.Tensor, thr: float, temperature: float, border: int,
+                    hw0_i, hw0_c, hw1_c, keep_conf: bool):
+    sim = ops.similarity(f0, f1, temperature)
+    conf, crmax, ccmax = ops.dual_softmax_(sim)
+    scale = hw0_i[0] / hw0_c[0]
+    matches, counts = ops.mutual_nearest(conf, crmax, ccmax, thr, border, hw0_c, hw1_c, scale)
+    return matches, counts, (conf if keep_conf else None)
+
+
+# --------------------------------------------------------------------------------------------
+# geo module
+# --------------------------------------------------------------------------------------------
+def _ransac_one(kp0: np.ndarray, kp1: np.ndarray, thr: float):
+    import cv2
+    if len(kp0) <= 8:                                    # geo_module.py:47
+        return None, None
+    M, mask = cv2.findHomography(kp0, kp1, cv2.RANSAC, thr)
+    if M is None:
+        return None, None
+    return M, mask[:, 0] == 1
+
+
+def geo_prepare_host(k0: np.ndarray, k1: np.ndarray, counts: np.ndarray, hw0_c, hw1_c, scale: int, ransac_thr: float):
+    """Host side of geo_module.py:39-94: per-sample RANSAC, homographies (fp64 inverse, fp32 cast),
+    anchor (inlier) token lists in ascending token order (== boolean-mask order)."""
+    n = len(counts)
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    kps = [(k0[offs[b]:offs[b + 1]].astype(np.int64), k1[offs[b]:offs[b + 1]].astype(np.int64)) for b in range(n)]
+    if n > 1:
+        res = list(_pool().map(lambda ab: _ransac_one(ab[0], ab[1], ransac_thr), kps))
+    else:
+        res = [_ransac_one(kps[0][0], kps[0][1], ransac_thr)]
+    hm = np.zeros((2, n, 9), dtype=np.float32)
+    has_h = np.zeros(n, dtype=np.int32)
+    anchors0: List[np.ndarray] = []
+    anchors1: List[np.ndarray] = []
+    for b, ((a, c), (M, inl)) in enumerate(zip(kps, res)):
+        if M is not None:
+            has_h[b] = 1
+            hm[0, b] = M.astype(np.float32).reshape(9)
+            hm[1, b] = torch.inverse(torch.from_numpy(M)[None])[0].to(torch.float32).numpy().reshape(9)
+            a, c = a[inl], c[inl]
+        anchors0.append(np.unique((a[:, 1] // scale) * hw0_c[1] + (a[:, 0] // scale)))
+        anchors1.append(np.unique((c[:, 1] // scale) * hw1_c[1] + (c[:, 0] // scale)))
+    cap = max(1, max(len(x) for x in anchors0 + anchors1))
+    aidx = np.zeros((2, n, cap), dtype=np.int32)
+    acnt = np.zeros((2, n), dtype=np.int32)
+    for b in range(n):
+        aidx[0, b, :len(anchors0[b])] = anchors0[b]; acnt[0, b] = len(anchors0[b])
+        aidx[1, b, :len(anchors1[b])] = anchors1[b]; acnt[1, b] = len(anchors1[b])
+    return hm, has_h, aidx, acnt
+
+
+def geo_self_layer(lw: dict, x: torch.Tensor, aidx: torch.Tensor, acnt: torch.Tensor, heads: int) -> torch.Tensor:
+    """All tokens attend to the anchor tokens of their own image (geo_transformer/transformer.py:111-124)."""
+    n, l, c = x.shape
+    x2d = x.reshape(n * l, c)
+    qkv = ops.linear(x2d, lw["wqkv"])
+    att = ops.geo_self_attention(qkv, 3 * c, qkv[:, c:], 3 * c, qkv[:, 2 * c:], 3 * c, n, l, heads, c // heads, aidx, acnt)
+    y = _post_attention(lw, x2d, att, EPI_TANH)
+    ops.select_rows_(y, x2d, acnt, n, l, c)            # samples without anchors keep their features
+    return y.view(n, l, c)
+
+
+def geo_cross_layer(lw: dict, x0: torch.Tensor, x1: torch.Tensor, widx_in1: torch.Tensor, widx_in0: torch.Tensor,
+                    has_h: torch.Tensor, heads: int):
+    """Each token attends to its 25-token projected window in the other image; both directions read the
+    PRE-layer features (geo_transformer/transformer.py:126-139)."""
+    n, l, c = x0.shape
+    s = x1.shape[1]
+    d = c // heads
+    a2d, b2d = x0.reshape(n * l, c), x1.reshape(n * s, c)
+    qkv0 = ops.linear(a2d, lw["wqkv"])
+    qkv1 = ops.linear(b2d, lw["wqkv"])
+    att0 = ops.geo_cross_attention(qkv0, 3 * c, qkv1[:, c:], 3 * c, qkv1[:, 2 * c:], 3 * c, n, l, s, heads, d, widx_in1)
+    att1 = ops.geo_cross_attention(qkv1, 3 * c, qkv0[:, c:], 3 * c, qkv0[:, 2 * c:], 3 * c, n, s, l, heads, d, widx_in0)
+    y0 = _post_attention(lw, a2d, att0, EPI_TANH)
+    y1 = _post_attention(lw, b2d, att1, EPI_TANH)
+    ops.select_rows_(y0, a2d, has_h, n, l, c)          # samples without a homography skip the layer
+    ops.select_rows_(y1, b2d, has_h, n, s, c)
+    return y0.view(n, l, c), y1.view(n, s, c)
+
+
+def geo_module(pw: PackedWeights, x0: torch.Tensor, x1: torch.Tensor, first: dict, counts, hw0_i, hw1_i, hw0_c, hw1_c,
+               names, heads: int, window: int, ransac_thr: float = 8.0, info: Optional[dict] = None):
+    n = x0.shape[0]
+    dev = x0.device
+    scale = int(hw0_i[0] // hw0_c[0])
+    k0 = first["mkpts0_c"].cpu().numpy()                 # device -> host: RANSAC runs in OpenCV (geo_module.py:48)
+    k1 = first["mkpts1_c"].cpu().numpy()
+    hm, has_h_np, aidx_np, acnt_np = geo_prepare_host(k0, k1, np.asarray(counts), hw0_c, hw1_c, scale, ransac_thr)
+    if info is not None:
+        info.update(has_h=has_h_np.copy(), anchor_cnt=acnt_np.copy(), hmat=hm.copy())
+    hm_d = torch.from_numpy(hm).to(dev, non_blocking=True)
+    has_h = torch.from_numpy(has_h_np).to(dev, non_blocking=True)
+    aidx = torch.from_numpy(aidx_np).to(dev, non_blocking=True)
+    acnt = torch.from_numpy(acnt_np).to(dev, non_blocking=True)
+    x0, x1 = x0.clone(), x1.clone()
+    any_h = bool(has_h_np.any())
+    if any_h:
+        # tokens of image0 look into image1 through H; tokens of image1 look into image0 through H^-1
+        widx_in1 = ops.geo_window_table(hm_d[0], has_h, n, hw0_c, hw1_i, hw1_c[1], scale, window)
+        widx_in0 = ops.geo_window_table(hm_d[1], has_h, n, hw1_c, hw0_i, hw0_c[1], scale, window)
+    for lw, name in zip(pw.geo, names):
+        if name == "self":
+            if acnt_np[0].any():
+                x0 = geo_self_layer(lw, x0, aidx[0], acnt[0], heads)
+            if acnt_np[1].any():
+                x1 = geo_self_layer(lw, x1, aidx[1], acnt[1], heads)
+        elif any_h:
+            x0, x1 = geo_cross_layer(lw, x0, x1, widx_in1, widx_in0, has_h, heads)
+    return x0, x1
+
+
+# --------------------------------------------------------------------------------------------
+# fine level
+# --------------------------------------------------------------------------------------------
+def fine_stage(pw: PackedWeights, fine0: torch.Tensor, fine1: torch.Tensor, g0: torch.Tensor, g1: torch.Tensor,
+               m2: dict, hw0_i, hw0_c, hw1_c, hw0_f, window: int, heads: int, names, temperature: float, thr: float,
+               want_matrix: bool):
+    b_ids, i_ids, j_ids = m2["b_ids"], m2["i_ids"], m2["j_ids"]
+    m = b_ids.shape[0]
+    dev = fine0.device
+    ww = window * window
+    cf = fine0.shape[-1]
+    stride = hw0_f[0] // hw0_c[0]
+    # fine_preprocess.py:41-72.  merge_feat(cat[win, ctx]) = win Wa^T + (ctx Wb^T + b)
+    win = torch.empty((2 * m, ww, cf), device=dev)
+    ops.fine_gather(fine0, b_ids, i_ids, hw0_c[1], stride, window, out=win[:m])
+    ops.fine_gather(fine1, b_ids, j_ids, hw1_c[1], stride, window, out=win[m:])
+    ctx = torch.empty((2 * m, g0.shape[-1]), device=dev)
+    ops.gather_rows(g0, b_ids, i_ids, out=ctx[:m])
+    ops.gather_rows(g1, b_ids, j_ids, out=ctx[m:])
+    cw = ops.linear(ctx, pw.fp["wd"], bias=pw.fp["bd"])                          # down_proj            [2m, 128]
+    cterm = ops.linear(cw, pw.fp["wb"], bias=pw.fp["bm"])                        # coarse half of merge [2m, 128]
+    X = ops.linear(win.view(2 * m * ww, cf), pw.fp["wa"], rowbias=cterm, rowbias_group=ww).view(2 * m, ww, cf)
+    pre = X
+    f0, f1 = X[:m], X[m:]
+    for lw, name in zip(pw.fine, names):
+        if name == "self":
+            X = fine_layer(lw, X, X, heads)
+            f0, f1 = X[:m], X[m:]
+        else:
+            y0 = fine_layer(lw, f0, f1, heads)
+            y1 = fine_layer(lw, f1, y0, heads)
+            f0, f1 = y0, y1
+    coarse_scale = hw0_i[0] / hw0_c[0]
+    c2f = hw0_f[0] / hw0_c[0]
+    fine_scale = hw0_i[0] / hw0_f[0]
+    out, fmat, raw = ops.fine_match(f0.contiguous(), f1.contiguous(), temperature, thr, m2["mkpts0_c"], m2["mkpts1_c"],
+                                    b_ids, window, coarse_scale, c2f, fine_scale, want_matrix)
+    return out, fmat, dict(fine_in=pre, fine_out0=f0, fine_out1=f1, raw=raw)

@@ -1,0 +1,240 @@
+"""Torch-tensor front end of the C ABI (include/geoformer_b200.h).
+
+Every function here launches hand-written sm_100a kernels from libgeoformer_sm100.so on the
+current CUDA stream.  PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+EPI_RELU, EPI_TANH, EPI_ELU1, EPI_LN = 1, 2, 4, 8
+
+# 'tf32' -> tcgen05 kind::tf32 tensor-core path (product default); 'ref' -> fp32 FFMA kernels
+# (accuracy mode for parity runs; same ABI contract).  Both are sm_100a CUDA from this library.
+_LINEAR_IMPL = "tf32"
+_SIM_IMPL = "f16x3"
+
+
+def set_precision(linear: Optional[str] = None, similarity: Optional[str] = None) -> None:
+    global _LINEAR_IMPL, _SIM_IMPL
+    if linear is not None:
+        assert linear in ("tf32", "ref")
+        _LINEAR_IMPL = linear
+    if similarity is not None:
+        assert similarity in ("f16x3", "ref")
+        _SIM_IMPL = similarity
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.GeoFormerLibError("geoformer_b200 ops need CUDA tensors (no CPU fallback)")
+    assert t.dtype == dtype, (t.dtype, dtype)
+    return t
+
+
+def ensure_init(device: torch.device) -> None:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    _lib.init(idx)
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, a2: Optional[torch.Tensor] = None, epi: int = 0, act_cols: int = 0,
+           bias: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None, rowbias_group: int = 0,
+           gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None,
+           residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+           impl: Optional[str] = None) -> torch.Tensor:
+    """y[M,N] = epilogue([a | a2] @ w.T); a [M,K1], a2 [M,K2] (optional), w [N,K1+K2], all contiguous fp32."""
+    _chk(a); _chk(w)
+    m, k1 = a.shape
+    n = w.shape[0]
+    k2 = 0 if a2 is None else a2.shape[1]
+    assert a.is_contiguous() and w.is_contiguous() and w.shape[1] == k1 + k2
+    if a2 is not None:
+        assert a2.is_contiguous() and a2.shape[0] == m
+    if residual is not None:
+        assert residual.is_contiguous() and residual.shape == (m, n)
+    y = out if out is not None else torch.empty((m, n), device=a.device, dtype=torch.float32)
+    fn = "gf_linear_tf32" if (impl or _LINEAR_IMPL) == "tf32" else "gf_linear_ref"
+    _lib.call(fn, a.data_ptr(), _ptr(a2), w.data_ptr(), y.data_ptr(), m, n, k1, k2, epi, act_cols, _ptr(bias),
+              _ptr(rowbias), rowbias_group, _ptr(gamma), _ptr(beta), _ptr(residual), None, _stream())
+    return y
+
+
+def add_posenc(x: torch.Tensor, pe: torch.Tensor) -> torch.Tensor:
+    n, l, c = x.shape
+    assert x.is_contiguous() and pe.is_contiguous() and pe.shape == (l, c)
+    out = torch.empty_like(x)
+    _lib.call("gf_add_posenc", x.data_ptr(), pe.data_ptr(), out.data_ptr(), n, l, c, _stream())
+    return out
+
+
+def linattn(q: torch.Tensor, ldq: int, k: torch.Tensor, ldk: int, v: torch.Tensor, ldv: int, n: int, l: int, s: int,
+            heads: int, dim: int) -> torch.Tensor:
+    """Linear attention.  q/k/v are (views into) row-major buffers with row strides ldq/ldk/ldv (floats)."""
+    dev = q.device
+    nfl = _lib.load().gf_linattn_partial_floats(n, s, heads, dim)
+    partial = torch.empty(nfl, device=dev, dtype=torch.float32)
+    kv = torch.empty((n, heads, dim, dim), device=dev, dtype=torch.float32)
+    ksum = torch.empty((n, heads, dim), device=dev, dtype=torch.float32)
+    _lib.call("gf_linattn_reduce", k.data_ptr(), ldk, v.data_ptr(), ldv, n, s, heads, dim, partial.data_ptr(),
+              kv.data_ptr(), ksum.data_ptr(), _stream())
+    out = torch.empty((n * l, heads * dim), device=dev, dtype=torch.float32)
+    _lib.call("gf_linattn_apply", q.data_ptr(), ldq, kv.data_ptr(), ksum.data_ptr(), out.data_ptr(), n, l, s, heads,
+              dim, _stream())
+    return out
+
+
+def linattn_window(q: torch.Tensor, ldq: int, k: torch.Tensor, ldk: int, v: torch.Tensor, ldv: int, n_windows: int,
+                   tokens: int, heads: int, dim: int) -> torch.Tensor:
+    out = torch.empty((n_windows * tokens, heads * dim), device=q.device, dtype=torch.float32)
+    _lib.call("gf_linattn_window", q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, out.data_ptr(),
+              n_windows, tokens, heads, dim, _stream())
+    return out
+
+
+# ------------------------------------------------------------------ coarse matching
+def similarity(f0: torch.Tensor, f1: torch.Tensor, temperature: float, impl: Optional[str] = None) -> torch.Tensor:
+    """sim[n,l,s] = (f0/sqrt(C)) . (f1/sqrt(C)) / temperature  (coarse_matching.py:110-119)."""
+    _chk(f0); _chk(f1)
+    n, l, c = f0.shape
+    s = f1.shape[1]
+    assert f0.is_contiguous() and f1.is_contiguous()
+    sim = torch.empty((n, l, s), device=f0.device, dtype=torch.float32)
+    in_scale = 1.0 / c ** 0.5
+    if (impl or _SIM_IMPL) == "f16x3":
+        a3 = torch.empty((n, l, 3 * c), device=f0.device, dtype=torch.float16)
+        b3 = torch.empty((n, s, 3 * c), device=f0.device, dtype=torch.float16)
+        _lib.call("gf_pack_split_f16", f0.data_ptr(), a3.data_ptr(), n * l, c, in_scale, 0, _stream())
+        _lib.call("gf_pack_split_f16", f1.data_ptr(), b3.data_ptr(), n * s, c, in_scale, 1, _stream())
+        _lib.call("gf_similarity_f16x3", a3.data_ptr(), b3.data_ptr(), sim.data_ptr(), n, l, s, 3 * c,
+                  1.0 / temperature, _stream())
+    else:
+        _lib.call("gf_similarity_ref", f0.data_ptr(), f1.data_ptr(), sim.data_ptr(), n, l, s, c, in_scale,
+                  1.0 / temperature, _stream())
+    return sim
+
+
+def dual_softmax_(sim: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """In place sim -> conf = softmax(sim,1)*softmax(sim,2).  Returns (conf, conf_row_max, conf_col_max)."""
+    n, l, s = sim.shape
+    dev = sim.device
+    rmax = torch.empty((n, l), device=dev); rsum = torch.empty((n, l), device=dev)
+    cmax = torch.empty((n, s), device=dev); csum = torch.empty((n, s), device=dev)
+    _lib.call("gf_dual_softmax_stats", sim.data_ptr(), n, l, s, rmax.data_ptr(), rsum.data_ptr(), cmax.data_ptr(),
+              csum.data_ptr(), _stream())
+    crmax = torch.empty((n, l), device=dev); ccmax = torch.empty((n, s), device=dev)
+    _lib.call("gf_dual_softmax_conf", sim.data_ptr(), n, l, s, rmax.data_ptr(), rsum.data_ptr(), cmax.data_ptr(),
+              csum.data_ptr(), crmax.data_ptr(), ccmax.data_ptr(), _stream())
+    return sim, crmax, ccmax
+
+
+def conf_row_col_max(conf: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    n, l, s = conf.shape
+    crmax = torch.empty((n, l), device=conf.device); ccmax = torch.empty((n, s), device=conf.device)
+    _lib.call("gf_conf_row_col_max", conf.data_ptr(), n, l, s, crmax.data_ptr(), ccmax.data_ptr(), _stream())
+    return crmax, ccmax
+
+
+def mutual_nearest(conf: torch.Tensor, crmax: torch.Tensor, ccmax: torch.Tensor, thr: float, border: int,
+                   hw0c: Tuple[int, int], hw1c: Tuple[int, int], scale: float):
+    """MNN + threshold + border + ordered compaction.  Returns dict of exact-size tensors and per-sample counts.
+    (One host sync to size the outputs, as the reference's torch.where does.)"""
+    _chk(conf)
+    n, l, s = conf.shape
+    dev = conf.device
+    mj = torch.empty((n, l), device=dev, dtype=torch.int32)
+    mc = torch.empty((n, l), device=dev, dtype=torch.float32)
+    _lib.call("gf_mnn_select", conf.data_ptr(), n, l, s, float(thr), int(border), hw0c[0], hw0c[1], hw1c[0], hw1c[1],
+              crmax.data_ptr(), ccmax.data_ptr(), mj.data_ptr(), mc.data_ptr(), _stream())
+    cap = n * l
+    b_ids = torch.empty(cap, device=dev, dtype=torch.int64); i_ids = torch.empty_like(b_ids); j_ids = torch.empty_like(b_ids)
+    mconf = torch.empty(cap, device=dev); k0 = torch.empty((cap, 2), device=dev); k1 = torch.empty((cap, 2), device=dev)
+    counts = torch.empty(n + 1, device=dev, dtype=torch.int32)
+    _lib.call("gf_compact_coarse", mj.data_ptr(), mc.data_ptr(), n, l, hw0c[1], hw1c[1], float(scale), b_ids.data_ptr(),
+              i_ids.data_ptr(), j_ids.data_ptr(), mconf.data_ptr(), k0.data_ptr(), k1.data_ptr(), counts.data_ptr(),
+              counts.data_ptr() + 4 * n, cap, _stream())
+    counts_h = counts.cpu()
+    total = int(counts_h[n])
+    return dict(b_ids=b_ids[:total], i_ids=i_ids[:total], j_ids=j_ids[:total], m_bids=b_ids[:total],
+                mconf=mconf[:total], mkpts0_c=k0[:total], mkpts1_c=k1[:total]), counts_h[:n]
+
+
+# ------------------------------------------------------------------ geo attention
+def geo_window_table(hmat: torch.Tensor, has_h: torch.Tensor, n: int, hw_src_c, hw_dst_px, w_dst_c: int, scale: int,
+                     window: int) -> torch.Tensor:
+    l = hw_src_c[0] * hw_src_c[1]
+    widx = torch.empty((n, l, window * window), device=hmat.device, dtype=torch.int32)
+    _lib.call("gf_geo_window_table", hmat.data_ptr(), has_h.data_ptr(), n, hw_src_c[0], hw_src_c[1], hw_dst_px[0],
+              hw_dst_px[1], w_dst_c, scale, window, widx.data_ptr(), _stream())
+    return widx
+
+
+def geo_self_attention(q, ldq, k, ldk, v, ldv, n, l, heads, dim, anchor_idx, anchor_cnt) -> torch.Tensor:
+    out = torch.empty((n * l, heads * dim), device=q.device, dtype=torch.float32)
+    _lib.call("gf_geo_self_attention", q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, out.data_ptr(), n, l,
+              heads, dim, anchor_idx.data_ptr(), anchor_cnt.data_ptr(), anchor_idx.shape[1], _stream())
+    return out
+
+
+def geo_cross_attention(q, ldq, kp, ldk, vp, ldv, n, l, s, heads, dim, widx) -> torch.Tensor:
+    out = torch.empty((n * l, heads * dim), device=q.device, dtype=torch.float32)
+    _lib.call("gf_geo_cross_attention", q.data_ptr(), ldq, kp.data_ptr(), ldk, vp.data_ptr(), ldv, out.data_ptr(), n,
+              l, s, heads, dim, widx.data_ptr(), widx.shape[2], _stream())
+    return out
+
+
+def select_rows_(dst: torch.Tensor, src: torch.Tensor, flag: torch.Tensor, n: int, l: int, c: int) -> None:
+    """dst[b] = src[b] for samples with flag[b] == 0 (per-sample skipped layers)."""
+    _lib.call("gf_select_rows", dst.data_ptr(), src.data_ptr(), flag.data_ptr(), n, l, c, _stream())
+
+
+# ------------------------------------------------------------------ fine level
+def fine_gather(fine_nhwc: torch.Tensor, b_ids, tok_ids, wc: int, stride: int, window: int,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _, hf, wf, c = fine_nhwc.shape
+    assert fine_nhwc.is_contiguous()
+    m = b_ids.shape[0]
+    if out is None:
+        out = torch.empty((m, window * window, c), device=fine_nhwc.device, dtype=torch.float32)
+    _lib.call("gf_fine_gather", fine_nhwc.data_ptr(), hf, wf, c, b_ids.data_ptr(), tok_ids.data_ptr(), m, wc, stride,
+              window, out.data_ptr(), _stream())
+    return out
+
+
+def gather_rows(feat: torch.Tensor, b_ids, tok_ids, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _, l, c = feat.shape
+    assert feat.is_contiguous()
+    m = b_ids.shape[0]
+    if out is None:
+        out = torch.empty((m, c), device=feat.device, dtype=torch.float32)
+    _lib.call("gf_gather_rows", feat.data_ptr(), l, c, b_ids.data_ptr(), tok_ids.data_ptr(), m, out.data_ptr(), _stream())
+    return out
+
+
+def fine_match(f0: torch.Tensor, f1: torch.Tensor, temperature: float, thr: float, mkpts0_c, mkpts1_c, b_ids,
+               window: int, coarse_scale: float, c2f: float, fine_scale: float, want_matrix: bool = False):
+    m, ww, c = f0.shape
+    dev = f0.device
+    sel = torch.empty(m, device=dev, dtype=torch.int32); fi = torch.empty_like(sel); fj = torch.empty_like(sel)
+    fconf = torch.empty(m, device=dev)
+    fmat = torch.empty((m, ww, ww), device=dev) if want_matrix else None
+    _lib.call("gf_fine_match", f0.data_ptr(), f1.data_ptr(), m, ww, c, float(temperature), float(thr), sel.data_ptr(),
+              fi.data_ptr(), fj.data_ptr(), fconf.data_ptr(), _ptr(fmat), _stream())
+    k0 = torch.empty((m, 2), device=dev); k1 = torch.empty((m, 2), device=dev); mconf = torch.empty(m, device=dev)
+    mb = torch.empty(m, device=dev, dtype=torch.int64); total = torch.empty(1, device=dev, dtype=torch.int32)
+    _lib.call("gf_compact_fine", sel.data_ptr(), fi.data_ptr(), fj.data_ptr(), fconf.data_ptr(), mkpts0_c.data_ptr(),
+              mkpts1_c.data_ptr(), b_ids.data_ptr(), m, window, float(coarse_scale), float(c2f), float(fine_scale),
+              k0.data_ptr(), k1.data_ptr(), mconf.data_ptr(), mb.data_ptr(), total.data_ptr(), _stream())
+    t = int(total.item())
+    return dict(mkpts0_f=k0[:t], mkpts1_f=k1[:t], mconf=mconf[:t], m_bids=mb[:t]), fmat, (sel, fi, fj, fconf)

@@ -1,0 +1,168 @@
+/* libgeoformer_sm100.so — C ABI of the B200-native GeoFormer matching hot path.
+ *
+ * The reference (ruc-aimc-lab/GeoFormer) is pure Python/PyTorch and has no FFI; these entry
+ * points replace the ATen call sites of model/full_model.py::GeoFormer.forward (SURVEY.md §2.2,
+ * K2..K16).  Each function cites the reference lines whose arithmetic it implements.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller (PyTorch) owns every buffer, including workspaces;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return 0 on success, a negative GF_ERR_* otherwise; never throws, never exits;
+ *     gf_last_error() returns a thread-local message for the last failure;
+ *   - token features are row-major [rows, C] fp32; index outputs are int64 where the reference
+ *     returns int64 tensors.
+ */
+#ifndef GEOFORMER_B200_H_
+#define GEOFORMER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GF_ABI_VERSION 1
+
+#define GF_OK 0
+#define GF_ERR_ARG (-1)      /* invalid argument / unsupported shape */
+#define GF_ERR_LAUNCH (-2)   /* CUDA launch or runtime error */
+#define GF_ERR_DRIVER (-3)   /* driver entry point (cuTensorMapEncodeTiled) unavailable */
+#define GF_ERR_DEVICE (-4)   /* not an sm_100 device */
+
+/* epilogue flags for gf_linear_* (applied in this order):
+ *   acc -> +bias[col] -> +rowbias[row / rowbias_group][col] -> activation -> LayerNorm -> +residual[row][col] */
+#define GF_EPI_RELU 1        /* all columns */
+#define GF_EPI_TANH 2        /* all columns */
+#define GF_EPI_ELU1 4        /* elu(x)+1 on columns [0, act_cols) only */
+#define GF_EPI_LN 8          /* LayerNorm over the full row (requires N == 128 or 256), eps 1e-5 */
+
+typedef void* gf_stream_t;
+
+int gf_abi_version(void);
+const char* gf_last_error(void);
+/* Binds the calling thread's current device; verifies sm_100; resolves the TMA descriptor encoder. */
+int gf_init(int device);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t gf_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Linear layers (nn.Linear call sites: loftr_module/transformer.py:49-58, geo_transformer/
+ * transformer.py:52-64, fine_preprocess.py:60-72).
+ *   Y[M,N] = epilogue( [A | A2][M, K1+K2] * W[N, K1+K2]^T )
+ * A2/K2 implement `torch.cat([x, message], dim=2)` (transformer.py:57) without materialising it.
+ * gf_linear_tf32: TMA -> tcgen05.mma kind::tf32 -> TMEM -> fused epilogue.  N % 128 == 0, K % 32 == 0.
+ * gf_linear_ref : plain fp32 FFMA kernel with the same contract (accuracy reference / debugging).
+ * m_dev (optional): device int32 holding the live row count (<= M); tiles beyond it are skipped.
+ */
+int gf_linear_tf32(const float* A, const float* A2, const float* W, float* Y, int64_t M, int N, int K1, int K2,
+                   int epi, int act_cols, const float* bias, const float* rowbias, int rowbias_group,
+                   const float* gamma, const float* beta, const float* residual, const int* m_dev,
+                   gf_stream_t stream);
+int gf_linear_ref(const float* A, const float* A2, const float* W, float* Y, int64_t M, int N, int K1, int K2,
+                  int epi, int act_cols, const float* bias, const float* rowbias, int rowbias_group,
+                  const float* gamma, const float* beta, const float* residual, const int* m_dev,
+                  gf_stream_t stream);
+
+/* out[n,l,c] = x[n,l,c] + pe[l,c]  (position_encoding.py:42 on the NHWC-flattened coarse map) */
+int gf_add_posenc(const float* x, const float* pe, float* out, int n, int64_t l, int c, gf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Linear attention (loftr_module/linear_attention.py:33-49).  Q and K arrive already mapped through
+ * elu(x)+1 (fused into the projection epilogue).  Row strides (ldq/ldk/ldv, in floats) let the caller
+ * point into a fused [rows, 3C] projection buffer.
+ *   reduce: KV[n,h,d,v] = sum_s K[n,s,h,d] * (V[n,s,h,v] / S);  Ksum[n,h,d] = sum_s K[n,s,h,d]
+ *           (two deterministic stages; `partial` is a workspace of gf_linattn_partial_floats())
+ *   apply : out[n,l,h,v] = (sum_d Q[n,l,h,d] KV[n,h,d,v]) / (Q[n,l,h,:].Ksum[n,h,:] + 1e-6) * S
+ */
+int64_t gf_linattn_partial_floats(int n, int s, int heads, int dim);
+int gf_linattn_reduce(const float* K, int ldk, const float* V, int ldv, int n, int s, int heads, int dim,
+                      float* partial, float* KV, float* Ksum, gf_stream_t stream);
+int gf_linattn_apply(const float* Q, int ldq, const float* KV, const float* Ksum, float* out, int n, int l, int s,
+                     int heads, int dim, gf_stream_t stream);
+/* Fine-level variant (25 tokens, 8 heads x 16, one CTA per match; both phases fused). src_offset lets
+ * the cross layer pair match m of the query tensor with match m of the source tensor. */
+int gf_linattn_window(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, float* out,
+                      int64_t n_windows, int tokens, int heads, int dim, gf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Coarse matching (utils/coarse_matching.py:110-125 and 161-212).
+ * Split-fp16 operands: x*scale = hi + lo (fp16 each); role 0 (left operand) packs [hi | hi | lo],
+ * role 1 (right operand) packs [hi | lo | hi] so that one K=3C fp16 tensor-core GEMM evaluates
+ * hi*hi + hi*lo + lo*hi with fp32 accumulation (max-abs error on the logits <= 1e-3).
+ */
+int gf_pack_split_f16(const float* x, void* out_f16, int64_t rows, int c, float scale, int role, gf_stream_t stream);
+/* sim[n,l,s] = (A3[n,l,:] . B3[n,s,:]) * out_scale   — batched tcgen05 kind::f16 GEMM, K = c3 */
+int gf_similarity_f16x3(const void* a3, const void* b3, float* sim, int n, int l, int s, int c3, float out_scale,
+                        gf_stream_t stream);
+/* sim from fp32 features with plain FFMA (accuracy reference) */
+int gf_similarity_ref(const float* f0, const float* f1, float* sim, int n, int l, int s, int c, float in_scale,
+                      float out_scale, gf_stream_t stream);
+/* row (dim=2) and column (dim=1) soft-max statistics of sim: max and sum(exp(x-max)) */
+int gf_dual_softmax_stats(const float* sim, int n, int l, int s, float* row_max, float* row_sum, float* col_max,
+                          float* col_sum, gf_stream_t stream);
+/* conf = softmax(sim,1)*softmax(sim,2), written in place over sim; also emits per-row / per-column max of conf */
+int gf_dual_softmax_conf(float* sim_conf, int n, int l, int s, const float* row_max, const float* row_sum,
+                         const float* col_max, const float* col_sum, float* conf_row_max, float* conf_col_max,
+                         gf_stream_t stream);
+/* per-row / per-column max of an existing confidence matrix (used when conf comes from outside) */
+int gf_conf_row_col_max(const float* conf, int n, int l, int s, float* conf_row_max, float* conf_col_max,
+                        gf_stream_t stream);
+/* mutual-nearest + threshold + border selection; match_j[n,l] = first j with
+ * conf>thr && conf==rowmax && conf==colmax && in-border, else -1 (coarse_matching.py:161-188) */
+int gf_mnn_select(const float* conf, int n, int l, int s, float thr, int border, int h0c, int w0c, int h1c, int w1c,
+                  const float* conf_row_max, const float* conf_col_max, int* match_j, float* match_conf,
+                  gf_stream_t stream);
+/* ordered compaction (row-major (b,i), as torch.where) into the reference's output tensors
+ * (coarse_matching.py:186-210).  counts[n] per sample, total[1]; capacity = max rows of the outputs. */
+int gf_compact_coarse(const int* match_j, const float* match_conf, int n, int l, int w0c, int w1c, float scale,
+                      int64_t* b_ids, int64_t* i_ids, int64_t* j_ids, float* mconf, float* mkpts0_c, float* mkpts1_c,
+                      int* counts, int* total, int64_t capacity, gf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Geometrized attention (model/geo_module.py:51-94, utils/common_utils.py:65-91,166-181,
+ * utils/homography.py:86-105, geo_transformer/transformer.py:111-139, geo_attention.py:72-100).
+ */
+/* window token table: for each grid token of the source image (w_src_c columns), project its pixel
+ * centre with hmat[n] (row-major 3x3 fp32) and list the 25 tokens of the other image around it.
+ * widx[n,l,25] = token index, or -1 when the window sample falls outside the other image or has_h[n]==0. */
+int gf_geo_window_table(const float* hmat, const int* has_h, int n, int h_src_c, int w_src_c, int h_dst_px, int w_dst_px,
+                        int w_dst_c, int scale, int window, int* widx, gf_stream_t stream);
+/* self attention against anchor (RANSAC inlier) tokens: full softmax, heads x dim, scale 1/sqrt(dim).
+ * q [n,l,*] rows with stride ldq; k/v rows of the same image with strides ldk/ldv, gathered through
+ * anchor_idx[n, anchor_cap] (first anchor_cnt[n] entries valid).  anchor_cnt[n]==0 leaves out[n] untouched
+ * by writing zeros and setting skipped[n]=1 (the caller keeps the layer input for such samples). */
+int gf_geo_self_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out,
+                          int n, int l, int heads, int dim, const int* anchor_idx, const int* anchor_cnt,
+                          int anchor_cap, gf_stream_t stream);
+/* cross attention: one query token against its 25-token window of the other image (projected K/V rows
+ * kproj/vproj [n, s, heads*dim]); masked entries filled with -1e8, all-masked rows give 0. */
+int gf_geo_cross_attention(const float* q, int ldq, const float* kproj, int ldk, const float* vproj, int ldv,
+                           float* out, int n, int l, int s, int heads, int dim, const int* widx, int window2,
+                           gf_stream_t stream);
+/* rows of samples whose flag[n]==0 are restored from src (layers skipped per sample) */
+int gf_select_rows(float* dst, const float* src, const int* flag, int n, int64_t l, int c, gf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fine level (loftr_module/fine_preprocess.py:41-72, model/fine_matching2.py:52-126).
+ */
+/* 5x5 (stride 4, pad 2) windows of the NHWC fine map around coarse tokens: out[m, w*w, c] */
+int gf_fine_gather(const float* fine_nhwc, int hf, int wf, int c, const int64_t* b_ids, const int64_t* tok_ids,
+                   int64_t m, int wc, int stride, int window, float* out, gf_stream_t stream);
+/* rows out[m,:] = feat[b_ids[m], tok_ids[m], :] */
+int gf_gather_rows(const float* feat, int64_t l, int c, const int64_t* b_ids, const int64_t* tok_ids, int64_t m,
+                   float* out, gf_stream_t stream);
+/* per match: 25x25 similarity, dual softmax, global arg-max, threshold.  sel[m] = 1 if kept;
+ * fi/fj window cells; fconf confidence; optional fine_matrix [m,25,25]. */
+int gf_fine_match(const float* f0, const float* f1, int64_t m, int ww, int c, float temperature, float thr,
+                  int* sel, int* fi, int* fj, float* fconf, float* fine_matrix, gf_stream_t stream);
+/* ordered compaction of kept fine matches into mkpts0_f/mkpts1_f/mconf/m_bids (fine_matching2.py:92-124) */
+int gf_compact_fine(const int* sel, const int* fi, const int* fj, const float* fconf, const float* mkpts0_c,
+                    const float* mkpts1_c, const int64_t* b_ids, int64_t m, int window, float coarse_scale,
+                    float c2f_scale, float fine_scale, float* mkpts0_f, float* mkpts1_f, float* mconf,
+                    int64_t* m_bids, int* total, gf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEOFORMER_B200_H_ */

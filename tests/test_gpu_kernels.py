@@ -1,0 +1,322 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (geoformer_b200.ops -> libgeoformer_sm100.so).
+Each CUDA kernel is compared with the CPU oracle (oracle/geoformer_oracle.py) on identical seeded inputs.
+Tolerances are stated per test; integer / index outputs must be bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import geoformer_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from geoformer_b200 import ops as _ops
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    _ops.ensure_init(torch.device("cuda:0"))
+    return _ops
+
+
+def dev(t):
+    return t.cuda().contiguous()
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+# ------------------------------------------------------------------------------------------- linear
+LIN_CASES = [
+    # (M, N, K1, K2, epi, act_cols, bias, rowbias_group, ln, residual)
+    (300, 256, 256, 0, 0, 0, False, 0, False, False),
+    (1000, 768, 256, 0, 4, 512, False, 0, False, False),      # fused QKV, elu+1 on q,k
+    (77, 512, 256, 256, 1, 0, False, 0, False, False),        # cat[x,msg] -> relu
+    (640, 512, 256, 256, 2, 0, False, 0, False, False),       # tanh
+    (515, 256, 512, 0, 8, 0, False, 0, True, True),           # LN + residual
+    (129, 256, 256, 0, 8, 0, False, 0, True, False),          # LN only
+    (250, 128, 128, 0, 0, 0, True, 25, False, False),         # fine merge: bias + per-window row bias
+    (375, 384, 128, 0, 4, 256, False, 0, False, False),       # fine QKV
+    (200, 128, 256, 0, 8, 0, False, 0, True, True),           # fine LN
+    (128, 128, 256, 0, 0, 0, True, 0, False, False),          # down_proj
+]
+
+
+def _lin_inputs(case, seed):
+    M, N, K1, K2, epi, act_cols, bias, rbg, ln, res = case
+    a = rnd(M, K1, seed=seed)
+    a2 = rnd(M, K2, seed=seed + 1) if K2 else None
+    w = rnd(N, K1 + K2, seed=seed + 2, scale=(K1 + K2) ** -0.5)
+    b = rnd(N, seed=seed + 3) if bias else None
+    rb = rnd((M + rbg - 1) // rbg, N, seed=seed + 4) if rbg else None
+    gamma = 1 + 0.1 * rnd(N, seed=seed + 5) if ln else None
+    beta = 0.1 * rnd(N, seed=seed + 6) if ln else None
+    r = rnd(M, N, seed=seed + 7) if res else None
+    return a, a2, w, b, rb, gamma, beta, r
+
+
+def _lin_torch(case, a, a2, w, b, rb, gamma, beta, r, dtype=torch.float64):
+    M, N, K1, K2, epi, act_cols, bias, rbg, ln, res = case
+    x = a.to(dtype) if a2 is None else torch.cat([a, a2], 1).to(dtype)
+    y = x @ w.to(dtype).T
+    if b is not None:
+        y = y + b.to(dtype)
+    if rb is not None:
+        y = y + rb.to(dtype)[torch.arange(M) // rbg]
+    if epi & 1:
+        y = F.relu(y)
+    if epi & 2:
+        y = torch.tanh(y)
+    if epi & 4:
+        y[:, :act_cols] = F.elu(y[:, :act_cols]) + 1
+    if epi & 8:
+        y = F.layer_norm(y, (N,), gamma.to(dtype), beta.to(dtype), 1e-5)
+    if r is not None:
+        y = y + r.to(dtype)
+    return y.float()
+
+
+@pytest.mark.parametrize("case", LIN_CASES)
+@pytest.mark.parametrize("impl,tol", [("ref", 2e-5), ("tf32", 4e-3)])
+def test_linear(ops, case, impl, tol):
+    """tolerance: fp32 FFMA kernel 2e-5; tcgen05 kind::tf32 (10-bit mantissa operands, fp32 accumulate)
+    4e-3 max-abs on O(1) outputs (K <= 512)."""
+    M, N, K1, K2, epi, act_cols, bias, rbg, ln, res = case
+    a, a2, w, b, rb, gamma, beta, r = _lin_inputs(case, 11)
+    want = _lin_torch(case, a, a2, w, b, rb, gamma, beta, r)
+    d = lambda t: None if t is None else dev(t)
+    got = ops.linear(d(a), d(w), a2=d(a2), epi=epi, act_cols=act_cols, bias=d(b), rowbias=d(rb), rowbias_group=rbg,
+                     gamma=d(gamma), beta=d(beta), residual=d(r), impl=impl).cpu()
+    assert torch.isfinite(got).all()
+    err = (got - want).abs().max().item()
+    assert err <= tol, f"{impl} {case}: max-abs {err}"
+
+
+def test_linear_tf32_large_multi_tile(ops):
+    """More tiles than SMs (persistent scheduler wraps), both accumulator buffers and all smem stages cycle."""
+    M, N, K = 128 * 301 + 5, 512, 512
+    a, w = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5)
+    got = ops.linear(dev(a), dev(w), impl="tf32")
+    ref = ops.linear(dev(a), dev(w), impl="ref")
+    torch.cuda.synchronize()
+    assert (got - ref).abs().max().item() <= 4e-3
+
+
+# ------------------------------------------------------------------------------------------- similarity / conf
+def _feat(n, l, c, seed, rms=3.0, offset=1.5):
+    # coarse features under random init have rms ~3 and a common offset -> logits ~40-95
+    return rnd(n, l, c, seed=seed, scale=rms) + offset
+
+
+@pytest.mark.parametrize("shape", [(2, 300, 333), (1, 4800, 4800), (1, 128, 256)])
+def test_similarity_f16x3_max_abs_1e3(ops, shape):
+    """North-star tolerance: max-abs <= 1e-3 on the similarity logits (vs fp64)."""
+    n, l, s = shape
+    f0, f1 = _feat(n, l, 256, 3), _feat(n, s, 256, 4)
+    want = torch.einsum("nlc,nsc->nls", f0.double() / 16, f1.double() / 16) / 0.1
+    got = ops.similarity(dev(f0), dev(f1), 0.1, impl="f16x3").cpu().double()
+    assert want.abs().max() > 20
+    err = (got - want).abs().max().item()
+    assert err <= 1e-3, err
+    ref = ops.similarity(dev(f0), dev(f1), 0.1, impl="ref").cpu().double()
+    assert (ref - want).abs().max().item() <= 1e-3
+
+
+def test_dual_softmax_conf(ops):
+    n, l, s = 2, 300, 333
+    sim = rnd(n, l, s, seed=5, scale=3.0) + 50
+    want = F.softmax(sim, 1) * F.softmax(sim, 2)
+    conf, crmax, ccmax = ops.dual_softmax_(dev(sim))
+    conf = conf.cpu()
+    assert (conf - want).abs().max().item() <= 1e-6 + 1e-5 * want.max().item()
+    assert torch.equal(crmax.cpu(), conf.max(dim=2)[0])
+    assert torch.equal(ccmax.cpu(), conf.max(dim=1)[0])
+
+
+def _mnn_gpu(ops, conf, thr, border, hw0c, hw1c):
+    c = dev(conf)
+    crmax, ccmax = ops.conf_row_col_max(c)
+    m, counts = ops.mutual_nearest(c, crmax, ccmax, thr, border, hw0c, hw1c, 8.0)
+    return {k: v.cpu() for k, v in m.items()}, counts
+
+
+@pytest.mark.parametrize("thr,border", [(0.0, 0), (0.2, 0), (0.01, 2)])
+def test_mnn_bit_exact_on_golden_conf(ops, golden_dir, thr, border):
+    """Given identical confidence inputs, MNN + threshold + border + compaction are bit-exact (north star)."""
+    z = np.load(os.path.join(golden_dir, "small_dense.npz"))
+    conf = torch.from_numpy(z["conf"])
+    hw = (12, 16)
+    want = O.coarse_match(conf, thr, (96, 128), hw, hw, border)
+    got, counts = _mnn_gpu(ops, conf, thr, border, hw, hw)
+    for k in ("b_ids", "i_ids", "j_ids"):
+        assert torch.equal(got[k], want[k]), k
+    assert torch.equal(got["mconf"], want["mconf"])
+    assert torch.equal(got["mkpts0_c"], want["mkpts0_c"]) and torch.equal(got["mkpts1_c"], want["mkpts1_c"])
+    assert counts.tolist() == [int((want["b_ids"] == b).sum()) for b in range(conf.shape[0])]
+
+
+def test_mnn_ties_and_rectangular(ops):
+    """Exact ties (first j wins, as torch CPU max on bool), all-equal matrix, rectangular L != S, empty result."""
+    g = torch.Generator().manual_seed(9)
+    conf = torch.rand(3, 6 * 7, 5 * 9, generator=g)
+    conf[0, 3, 10] = conf[0, 3, 20] = 2.0            # two row-maxima that are both column maxima -> j = 10
+    conf[1] = 0.25                                   # uniform: every row matches j = 0
+    conf[2, 5, :] = 0.0
+    want = O.coarse_match(conf, 0.1, (48, 56), (6, 7), (5, 9), 0)
+    got, _ = _mnn_gpu(ops, conf, 0.1, 0, (6, 7), (5, 9))
+    for k in ("b_ids", "i_ids", "j_ids", "mconf", "mkpts0_c", "mkpts1_c"):
+        assert torch.equal(got[k], want[k]), k
+    got, counts = _mnn_gpu(ops, conf, 5.0, 0, (6, 7), (5, 9))
+    assert got["b_ids"].numel() == 0 and counts.sum() == 0
+
+
+def test_mnn_random_full_size(ops):
+    """4800x4800 random confidences: sortedness + agreement with the oracle."""
+    g = torch.Generator().manual_seed(10)
+    conf = torch.rand(1, 4800, 4800, generator=g)
+    want = O.coarse_match(conf, 0.5, (480, 640), (60, 80), (60, 80), 0)
+    got, _ = _mnn_gpu(ops, conf, 0.5, 0, (60, 80), (60, 80))
+    assert torch.equal(got["i_ids"], want["i_ids"]) and torch.equal(got["j_ids"], want["j_ids"])
+    assert (got["i_ids"][1:] > got["i_ids"][:-1]).all()
+
+
+# ------------------------------------------------------------------------------------------- linear attention
+def test_linear_attention(ops):
+    n, l, s, h, d = 2, 500, 300, 8, 32
+    q, k, v = rnd(n, l, h, d, seed=1), rnd(n, s, h, d, seed=2), rnd(n, s, h, d, seed=3)
+    want = O.linear_attention(q, k, v).reshape(n * l, h * d)
+    Q, K = F.elu(q) + 1, F.elu(k) + 1
+    got = ops.linattn(dev(Q.reshape(n * l, h * d)), h * d, dev(K.reshape(n * s, h * d)), h * d,
+                      dev(v.reshape(n * s, h * d)), h * d, n, l, s, h, d).cpu()
+    assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
+
+
+def test_linear_attention_window(ops):
+    m, t, h, d = 37, 25, 8, 16
+    q, k, v = rnd(m, t, h, d, seed=1), rnd(m, t, h, d, seed=2), rnd(m, t, h, d, seed=3)
+    want = O.linear_attention(q, k, v).reshape(m * t, h * d)
+    Q, K = F.elu(q) + 1, F.elu(k) + 1
+    got = ops.linattn_window(dev(Q.reshape(m * t, h * d)), h * d, dev(K.reshape(m * t, h * d)), h * d,
+                             dev(v.reshape(m * t, h * d)), h * d, m, t, h, d).cpu()
+    assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
+
+
+# ------------------------------------------------------------------------------------------- geo attention
+def _homographies():
+    eye = np.eye(3)
+    tr = np.array([[1, 0, 16.0], [0, 1, 8.0], [0, 0, 1]])
+    g = np.random.RandomState(0)
+    rand = np.array([[1.02, 0.03, -5.3], [-0.02, 0.97, 7.9], [1e-5, -2e-5, 1.0]]) + g.randn(3, 3) * 1e-6
+    return [eye, tr, rand]
+
+
+def test_geo_window_table(ops):
+    """Index table vs the oracle.  Exact for integer-valued warps; for a general homography the fp32
+    projective warp may round differently from the CPU BLAS 3x3 bmm in the last ulp, which can move a
+    sample across a cell boundary: require >= 99.9% identical entries there."""
+    hw_i, hw_c = (96, 128), (12, 16)
+    Hs = _homographies()
+    n = len(Hs)
+    hm = torch.tensor(np.stack(Hs).reshape(n, 9), dtype=torch.float32)
+    has = torch.tensor([1, 1, 1], dtype=torch.int32)
+    got = ops.geo_window_table(dev(hm), dev(has), n, hw_c, hw_i, hw_c[1], 8, 5).cpu()
+    for b, Hm in enumerate(Hs):
+        c = O.warp_points(O.grid_keypoints(hw_i[0], hw_i[1], 8), torch.from_numpy(Hm).float())
+        win, mask = O.window_table(c, hw_i, 5, 8)
+        want = torch.where(mask, O.window_token_index(win, hw_c[1]), torch.full_like(mask, -1, dtype=torch.long))
+        same = (got[b].long() == want).float().mean().item()
+        assert same == 1.0 if b < 2 else same >= 0.999, (b, same)
+    none = ops.geo_window_table(dev(hm), dev(torch.zeros(3, dtype=torch.int32)), n, hw_c, hw_i, hw_c[1], 8, 5).cpu()
+    assert (none == -1).all()
+
+
+def test_geo_self_attention(ops):
+    n, l, h, d = 3, 200, 4, 64
+    c = h * d
+    qkv = rnd(n * l, 3 * c, seed=4)
+    cnts = [0, 1, 130]
+    g = torch.Generator().manual_seed(1)
+    aidx = torch.zeros(n, 130, dtype=torch.int32)
+    for b, cnt in enumerate(cnts):
+        aidx[b, :cnt] = torch.sort(torch.randperm(l, generator=g)[:cnt])[0].int()
+    dq = dev(qkv)
+    got = ops.geo_self_attention(dq, 3 * c, dq[:, c:], 3 * c, dq[:, 2 * c:], 3 * c, n, l, h, d, dev(aidx),
+                                 dev(torch.tensor(cnts, dtype=torch.int32))).cpu().view(n, l, c)
+    x = qkv.view(n, l, 3 * c)
+    for b, cnt in enumerate(cnts):
+        if cnt == 0:
+            assert (got[b] == 0).all()
+            continue
+        sel = aidx[b, :cnt].long()
+        q = x[b, :, :c].view(1, l, h, d)
+        k = x[b, sel, c:2 * c].view(1, cnt, h, d)
+        v = x[b, sel, 2 * c:].view(1, cnt, h, d)
+        want = O.softmax_attention(q, k, v).view(l, c)
+        assert (got[b] - want).abs().max().item() <= 2e-5
+
+
+def test_geo_cross_attention(ops):
+    n, l, s, h, d = 2, 150, 170, 4, 64
+    c = h * d
+    q, kp, vp = rnd(n * l, c, seed=1), rnd(n * s, c, seed=2), rnd(n * s, c, seed=3)
+    g = torch.Generator().manual_seed(2)
+    widx = torch.randint(-1, s, (n, l, 25), generator=g).int()
+    widx[0, 5] = -1                                       # fully masked row -> zeros
+    widx[1, 7, 1:] = -1                                   # single live key
+    got = ops.geo_cross_attention(dev(q), c, dev(kp), c, dev(vp), c, n, l, s, h, d, dev(widx)).cpu().view(n, l, c)
+    for b in range(n):
+        idx = widx[b].long().clamp(min=0)
+        mask = widx[b] >= 0
+        kk = kp.view(n, s, c)[b][idx].view(l, 25, h, d)
+        vv = vp.view(n, s, c)[b][idx].view(l, 25, h, d)
+        want = O.softmax_attention(q.view(n, l, c)[b].view(l, 1, h, d), kk, vv, kv_mask=mask).view(l, c)
+        assert (got[b] - want).abs().max().item() <= 2e-5
+    assert (got[0, 5] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------- fine level
+def test_fine_gather_exact(ops):
+    n, c, hf, wf, wc = 2, 128, 48, 64, 16
+    fmap = rnd(n, c, hf, wf, seed=6)
+    g = torch.Generator().manual_seed(3)
+    m = 77
+    b_ids = torch.randint(0, n, (m,), generator=g)
+    tok = torch.randint(0, 12 * 16, (m,), generator=g)
+    tok[:4] = torch.tensor([0, 15, 176, 191])           # corners: zero padding
+    want = O.fine_windows(fmap, b_ids, tok, 5, 4)
+    got = ops.fine_gather(dev(fmap.permute(0, 2, 3, 1)), dev(b_ids), dev(tok), wc, 4, 5).cpu()
+    assert torch.equal(got, want)
+
+
+def test_fine_match(ops, golden_dir):
+    """Window features from the reference run (golden) -> identical fine cells / coordinates; confidences 1e-5."""
+    z = np.load(os.path.join(golden_dir, "small_dense.npz"))
+    f0, f1 = torch.from_numpy(z["fine_out0"]), torch.from_numpy(z["fine_out1"])
+    m = f0.shape[0]
+    k0c, k1c = torch.from_numpy(z["mkpts0_c"][:m]), torch.from_numpy(z["mkpts1_c"][:m])
+    b_ids = torch.from_numpy(z["b_ids"][:m])
+    conf = O.dual_softmax_conf(f0, f1, 0.1)
+    want = O.fine_match(conf, 0.1, k0c, k1c, b_ids, (96, 128), (12, 16), (48, 64), 5)
+    out, fmat, raw = ops.fine_match(dev(f0), dev(f1), 0.1, 0.1, dev(k0c), dev(k1c), dev(b_ids), 5, 8.0, 4.0, 2.0, True)
+    assert (fmat.cpu() - conf).abs().max().item() <= 1e-5
+    assert torch.equal(out["mkpts0_f"].cpu(), want["mkpts0_f"]) and torch.equal(out["mkpts1_f"].cpu(), want["mkpts1_f"])
+    assert torch.equal(out["m_bids"].cpu(), want["m_bids"])
+    assert (out["mconf"].cpu() - want["mconf"]).abs().max().item() <= 1e-5
+
+
+def test_fine_match_threshold_and_random(ops):
+    m = 500
+    f0, f1 = rnd(m, 25, 128, seed=7, scale=2.0), rnd(m, 25, 128, seed=8, scale=2.0)
+    k0c = torch.randint(0, 60, (m, 2), generator=torch.Generator().manual_seed(4)).float() * 8
+    k1c = torch.randint(0, 60, (m, 2), generator=torch.Generator().manual_seed(5)).float() * 8
+    b_ids = torch.zeros(m, dtype=torch.long)
+    conf = O.dual_softmax_conf(f0, f1, 0.1)
+    want = O.fine_match(conf, 0.1, k0c, k1c, b_ids, (480, 640), (60, 80), (240, 320), 5)
+    out, _, raw = ops.fine_match(dev(f0), dev(f1), 0.1, 0.1, dev(k0c), dev(k1c), dev(b_ids), 5, 8.0, 4.0, 2.0)
+    assert 0 < want["mkpts0_f"].shape[0] < m              # the threshold bites
+    assert torch.equal(out["mkpts0_f"].cpu(), want["mkpts0_f"]) and torch.equal(out["mkpts1_f"].cpu(), want["mkpts1_f"])
+    assert (out["mkpts0_f"].cpu() % 2 == 0).all()
