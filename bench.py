@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""Benchmark of the GeoFormer matching hot path (BASELINE.json metric: 640x480 pairs/s on B200;
+conf-matrix tensor-pipe fraction of peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the full forward (backbone -> coarse transformer -> coarse matching ->
+host RANSAC -> geo transformer -> coarse matching -> fine stage) over one batch of synthetic
+HPatches-shaped 640x480 pairs.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import copy
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from geoformer_b200 import synth  # noqa: E402
+
+H, W, BATCH = 480, 640, 16
+METRIC, UNIT = "pairs_per_sec_640x480", "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--regime", default="dense", choices=["dense", "shift"])
+    ap.add_argument("--backbone", default=os.environ.get("GF_BACKBONE", "bf16"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stage-times", action="store_true", help="print a per-stage CUDA-event breakdown to stderr")
+    return ap.parse_args()
+
+
+def workload_config(args, extra=None):
+    cfg = {"workload": f"HPatches-shaped synthetic 640x480 pairs, batch {args.batch}, regime '{args.regime}' "
+                       f"(image1 == image0: heaviest match count), random-init weights, coarse_thr 0.0",
+           "image_hw": [H, W], "pairs_per_step": args.batch, "coarse_tokens": (H // 8) * (W // 8),
+           "cache": "working set per step (sim matrix 1.5 GB, activations > 3 GB) >> 126 MB L2; no explicit flush"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------- reference arm / CPU baseline
+def cpu_forward_pairs_per_sec(steps, warmup, regime):
+    """The reference's CPU implementation of the path == the oracle port (the reference is pure PyTorch and cannot
+    travel to the GPU box; the oracle restates it op for op and is pinned to it by tests/golden).  Each step is a
+    bounded sample of the workload: ONE 640x480 pair (about 5 s of CPU work)."""
+    from oracle import geoformer_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth.make_state_dict(0)
+    times = []
+    for i in range(warmup + steps):
+        im0, im1 = synth.make_pairs(1, H, W, regime, 100 + i)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            out = O.forward(sd, im0, im1, dict(coarse_thr=0.0))
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return 1.0 / float(np.mean(times)), torch.get_num_threads(), float(np.mean(times)), int(out["mkpts0_f"].shape[0])
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 4)), max(0, min(args.warmup, 1))
+    v, cores, spp, mf = cpu_forward_pairs_per_sec(steps, warmup, args.regime)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": 1e3 * spp, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, {"pairs_per_step": 1}),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{steps} single-pair 640x480 forwards of the CPU oracle port after {warmup} warm-up "
+                                       f"(the reference is pure PyTorch; /root/reference is absent on the GPU box)"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- our arm
+def build_model(device, backbone):
+    from geoformer_b200.model.full_model import GeoFormer
+    from geoformer_b200.model.geo_config import default_cfg as geo_cfg
+    from geoformer_b200.model.loftr_src.loftr.utils.cvpr_ds_config import default_cfg
+    g = dict(geo_cfg)
+    g["coarse_thr"] = 0.0
+    m = GeoFormer(copy.deepcopy(default_cfg), g)
+    ckpt = {"state_dict": {"matcher." + k: v for k, v in synth.make_state_dict(0).items()}}   # checkpoint-shaped, as the wrapper loads it
+    m.load_state_dict(ckpt["state_dict"], strict=False)
+    m.backbone_precision = backbone
+    return m.eval().to(device)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from geoformer_b200 import _lib, ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    model = build_model(device, args.backbone)
+
+    # a small pool of distinct batches, resident in HBM (value) and in pinned host memory (e2e)
+    pool = 2
+    host = [synth.make_pairs(args.batch, H, W, args.regime, 1000 * rank + 100 * p) for p in range(pool)]
+    host = [(a.pin_memory(), b.pin_memory()) for a, b in host]
+    dev = [(a.to(device), b.to(device)) for a, b in host]
+
+    def step_resident(i):
+        a, b = dev[i % pool]
+        d = model({"image0": a, "image1": b})
+        return d
+
+    def step_e2e(i):
+        a, b = host[i % pool]
+        d = model({"image0": a.to(device, non_blocking=True), "image1": b.to(device, non_blocking=True)})
+        k0, k1, cf = d["mkpts0_f"].cpu(), d["mkpts1_f"].cpu(), d["mconf"].cpu()      # what match_pairs() reads back
+        return d, k0.numel() * 4 + k1.numel() * 4 + cf.numel() * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        e0.record()
+        outs = [fn(i) for i in range(steps)]
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, outs, _lib.launch_count() - l0
+
+    for i in range(args.warmup):
+        step_resident(i)
+        step_e2e(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.PROFILE.enable("similarity")
+    ms, outs, launches = timed(step_resident, args.steps)
+    sim_ms = ops.PROFILE.collect("similarity")            # per-launch CUDA-event durations of the conf-matrix GEMM
+    ops.PROFILE.disable()
+    ms_e2e, outs_e2e, _ = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    mc = float(np.mean([o["b_ids"].shape[0] for o in outs])) / args.batch
+    mf = float(np.mean([o["mkpts0_f"].shape[0] for o in outs])) / args.batch
+    d2h = int(np.mean([o[1] for o in outs_e2e]))
+    if world > 1:
+        # the path's only exchange step: gather match counts / lists (here: counts + last step's list sizes) to all ranks
+        t = torch.tensor([mc, mf], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        mc, mf = (t / world).tolist()
+    if args.stage_times and rank == 0:
+        stage_breakdown(model, dev[0])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pairs = args.batch * args.steps * world
+    value = pairs / (ms / 1e3)
+    e2e = pairs / (ms_e2e / 1e3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    L = (H // 8) * (W // 8)
+    flops = 2.0 * L * L * 256 * args.batch                                   # algorithmic: 2*L*S*C per pair per launch
+    sim_avg_ms = float(np.mean(sim_ms)) if len(sim_ms) else float("nan")
+    achieved = flops / (sim_avg_ms * 1e-3) / 1e12
+    roof = {"kernel": "gemm_tc_kernel<kind::f16, 128x256> (coarse similarity, split-fp16 K=768)",
+            "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
+            "algorithmic_flops_per_launch": flops, "issued_flops_per_launch": 3 * flops,
+            "avg_launch_ms": sim_avg_ms, "launches_timed": len(sim_ms), "traffic": None}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32/f16x3 (bf16 cuDNN backbone)" if args.backbone == "bf16" else f"tf32/f16x3 ({args.backbone} backbone)",
+            "data": "synthetic",
+            "config": workload_config(args, {"matches_coarse_per_pair": mc, "matches_fine_per_pair": mf,
+                                             "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective"}),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * args.batch * H * W * 4, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+    if not args.no_cpu_baseline and world == 1:
+        v, cores, spp, _ = cpu_forward_pairs_per_sec(2, 1, args.regime)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "2 single-pair 640x480 forwards of the CPU oracle port after 1 warm-up "
+                                          f"({spp:.2f} s/pair)"}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def stage_breakdown(model, batch):
+    """Per-stage CUDA-event timing (diagnostic; stderr)."""
+    from geoformer_b200 import ops
+    ops.PROFILE.enable("*")
+    model({"image0": batch[0], "image1": batch[1]})
+    torch.cuda.synchronize()
+    rows = ops.PROFILE.summary()
+    ops.PROFILE.disable()
+    tot = sum(v[1] for k, v in rows.items() if k.startswith("stage:"))
+    for k, (cnt, ms) in sorted(rows.items(), key=lambda kv: (not kv[0].startswith("stage:"), -kv[1][1])):
+        sys.stderr.write(f"  {k:36s} x{cnt:4d}  {ms:9.3f} ms  {100 * ms / tot:5.1f}%\n")
+    sys.stderr.write(f"  {'sum of stages':36s}        {tot:9.3f} ms\n")
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

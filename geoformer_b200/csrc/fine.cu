@@ -32,7 +32,7 @@ __global__ void fine_gather_kernel(const float* __restrict__ fine, int hf, int w
 // Per match: S = f0 f1^T / (C * T), conf = softmax(S,1)*softmax(S,2), global arg-max (first on ties), thr.
 // blockDim = 128; WW <= 25; C <= 128.
 __global__ void __launch_bounds__(128)
-fine_match_kernel(const float* __restrict__ f0, const float* __restrict__ f1, int ww, int c, float inv_temp, float thr,
+fine_match_kernel(const float* __restrict__ f0, const float* __restrict__ f1, int ww, int c, float temperature, float thr,
                   int* __restrict__ sel, int* __restrict__ fi, int* __restrict__ fj, float* __restrict__ fconf,
                   float* __restrict__ fine_matrix) {
   __shared__ float a[25][129], b[25][129];
@@ -42,18 +42,18 @@ fine_match_kernel(const float* __restrict__ f0, const float* __restrict__ f1, in
   __shared__ int best_i[4];
   const int64_t m = blockIdx.x;
   const int tid = threadIdx.x;
-  const float norm = 1.f / sqrtf((float)c);
+  const float norm = sqrtf((float)c);
   for (int e = tid; e < ww * c; e += 128) {
     const int r = e / c, k = e - r * c;
-    a[r][k] = f0[(m * ww + r) * c + k] * norm;     // feat / C**.5 (fine_matching2.py:52)
-    b[r][k] = f1[(m * ww + r) * c + k] * norm;
+    a[r][k] = f0[(m * ww + r) * c + k] / norm;     // feat / C**.5 (fine_matching2.py:52)
+    b[r][k] = f1[(m * ww + r) * c + k] / norm;
   }
   __syncthreads();
   for (int e = tid; e < ww * ww; e += 128) {
     const int i = e / ww, j = e - i * ww;
     float acc = 0.f;
     for (int k = 0; k < c; ++k) acc = fmaf(a[i][k], b[j][k], acc);
-    S[i][j] = acc * inv_temp;
+    S[i][j] = acc / temperature;
   }
   __syncthreads();
   if (tid < ww) {                       // softmax over dim=2 (row i, across j)
@@ -156,7 +156,7 @@ extern "C" int gf_fine_match(const float* f0, const float* f1, int64_t m, int ww
                              int* sel, int* fi, int* fj, float* fconf, float* fine_matrix, gf_stream_t stream) {
   if (m < 0 || ww <= 0 || ww > 25 || c <= 0 || c > 128) return gf_set_error(GF_ERR_ARG, "gf_fine_match: ww <= 25, c <= 128");
   if (m == 0) return GF_OK;
-  fine_match_kernel<<<(unsigned)m, 128, 0, STREAM>>>(f0, f1, ww, c, 1.f / temperature, thr, sel, fi, fj, fconf, fine_matrix);
+  fine_match_kernel<<<(unsigned)m, 128, 0, STREAM>>>(f0, f1, ww, c, temperature, thr, sel, fi, fj, fconf, fine_matrix);
   g_launches++;
   GF_CHECK_LAUNCH();
   return GF_OK;

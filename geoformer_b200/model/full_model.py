@@ -139,31 +139,37 @@ class GeoFormer(nn.Module):
         data.update({"bs": torch.tensor(n), "hw0_i": torch.tensor(hw0_i), "hw1_i": torch.tensor(hw1_i)})
         stages = {} if self.capture else None
 
+        R = ops.PROFILE.region
         # 1. CNN (resnet_fpn.py:100-118)
-        if hw0_i == hw1_i:
-            c, f = engine.backbone_forward(pw, torch.cat([img0, img1], 0))
-            c0, c1, f0, f1 = c[:n], c[n:], f[:n], f[n:]
-        else:
-            (c0, f0), (c1, f1) = engine.backbone_forward(pw, img0), engine.backbone_forward(pw, img1)
+        with R("stage:backbone"):
+            if hw0_i == hw1_i:
+                c, f = engine.backbone_forward(pw, torch.cat([img0, img1], 0))
+                c0, c1, f0, f1 = c[:n], c[n:], f[:n], f[n:]
+            else:
+                (c0, f0), (c1, f1) = engine.backbone_forward(pw, img0), engine.backbone_forward(pw, img1)
         hw0_c, hw1_c, hw0_f, hw1_f = tuple(c0.shape[1:3]), tuple(c1.shape[1:3]), tuple(f0.shape[1:3]), tuple(f1.shape[1:3])
         data.update({"hw0_c": torch.tensor(hw0_c), "hw1_c": torch.tensor(hw1_c),
                      "hw0_f": torch.tensor(hw0_f), "hw1_f": torch.tensor(hw1_f)})
         dc = c0.shape[-1]
 
         # 2. positional encoding + coarse transformer (full_model.py:69-84)
-        x0 = ops.add_posenc(c0.reshape(n, -1, dc), pw.pos_table(dc, *hw0_c))
-        x1 = ops.add_posenc(c1.reshape(n, -1, dc), pw.pos_table(dc, *hw1_c))
-        t0, t1 = engine.coarse_transformer(pw, x0, x1, cfg["coarse"]["layer_names"], cfg["coarse"]["nhead"])
+        with R("stage:coarse_transformer"):
+            x0 = ops.add_posenc(c0.reshape(n, -1, dc), pw.pos_table(dc, *hw0_c))
+            x1 = ops.add_posenc(c1.reshape(n, -1, dc), pw.pos_table(dc, *hw1_c))
+            t0, t1 = engine.coarse_transformer(pw, x0, x1, cfg["coarse"]["layer_names"], cfg["coarse"]["nhead"])
 
         # 3. coarse matching -> geo module -> coarse matching (full_model.py:87-90)
         thr = cfg["match_coarse"]["thr"]
         temp = cfg["match_coarse"]["dsmax_temperature"]
-        m1, counts1, conf1 = engine.coarse_matching(t0.contiguous(), t1.contiguous(), thr, temp, 0, hw0_i, hw0_c, hw1_c,
-                                                    self.materialize)
+        with R("stage:coarse_matching_1"):
+            m1, counts1, conf1 = engine.coarse_matching(t0.contiguous(), t1.contiguous(), thr, temp, 0, hw0_i, hw0_c,
+                                                        hw1_c, self.materialize)
         ginfo = {} if self.capture else None
-        g0, g1 = engine.geo_module(pw, x0, x1, m1, counts1, hw0_i, hw1_i, hw0_c, hw1_c, gcfg["layer_names"],
-                                   gcfg["nhead"], gcfg["window_size"], info=ginfo)
-        m2, counts2, conf2 = engine.coarse_matching(g0, g1, thr, temp, 0, hw0_i, hw0_c, hw1_c, self.materialize)
+        with R("stage:geo_module(+host RANSAC)"):
+            g0, g1 = engine.geo_module(pw, x0, x1, m1, counts1, hw0_i, hw1_i, hw0_c, hw1_c, gcfg["layer_names"],
+                                       gcfg["nhead"], gcfg["window_size"], info=ginfo)
+        with R("stage:coarse_matching_2"):
+            m2, counts2, conf2 = engine.coarse_matching(g0, g1, thr, temp, 0, hw0_i, hw0_c, hw1_c, self.materialize)
         data.update(m2)
         if self.materialize:
             data.update({"dect_conf_matrix": conf1, "conf_matrix": conf2})
@@ -176,9 +182,10 @@ class GeoFormer(nn.Module):
                          "fine_matrix": torch.empty(0, w * w, w * w, device=img0.device)})
             fstages = {}
         else:
-            out, fmat, fstages = engine.fine_stage(pw, f0, f1, g0, g1, m2, hw0_i, hw0_c, hw1_c, hw0_f, w,
-                                                   cfg["fine"]["nhead"], cfg["fine"]["layer_names"],
-                                                   gcfg["fine_temperature"], gcfg["fine_thr"], self.materialize)
+            with R("stage:fine"):
+                out, fmat, fstages = engine.fine_stage(pw, f0, f1, g0, g1, m2, hw0_i, hw0_c, hw1_c, hw0_f, w,
+                                                       cfg["fine"]["nhead"], cfg["fine"]["layer_names"],
+                                                       gcfg["fine_temperature"], gcfg["fine_thr"], self.materialize)
             data.update(out)
             if self.materialize:
                 data["fine_matrix"] = fmat

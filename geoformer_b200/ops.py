@@ -29,6 +29,56 @@ def set_precision(linear: Optional[str] = None, similarity: Optional[str] = None
         _SIM_IMPL = similarity
 
 
+class _Profile:
+    """Optional CUDA-event instrumentation (bench.py): regions are timed on the launching stream."""
+
+    def __init__(self):
+        self.pattern = None
+        self.records = {}
+
+    def enable(self, pattern: str) -> None:
+        self.pattern, self.records = pattern, {}
+
+    def disable(self) -> None:
+        self.pattern = None
+
+    def on(self, name: str) -> bool:
+        return self.pattern is not None and (self.pattern == "*" or self.pattern in name)
+
+    class _Region:
+        def __init__(self, prof, name):
+            self.prof, self.name = prof, name
+
+        def __enter__(self):
+            if self.prof.on(self.name):
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e1 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+            else:
+                self.e0 = None
+            return self
+
+        def __exit__(self, *exc):
+            if self.e0 is not None:
+                self.e1.record()
+                self.prof.records.setdefault(self.name, []).append((self.e0, self.e1))
+            return False
+
+    def region(self, name: str):
+        return _Profile._Region(self, name)
+
+    def collect(self, name: str):
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for k, v in self.records.items() if name in k for a, b in v]
+
+    def summary(self):
+        torch.cuda.synchronize()
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.records.items()}
+
+
+PROFILE = _Profile()
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -66,8 +116,9 @@ def linear(a: torch.Tensor, w: torch.Tensor, a2: Optional[torch.Tensor] = None, 
         assert residual.is_contiguous() and residual.shape == (m, n)
     y = out if out is not None else torch.empty((m, n), device=a.device, dtype=torch.float32)
     fn = "gf_linear_tf32" if (impl or _LINEAR_IMPL) == "tf32" else "gf_linear_ref"
-    _lib.call(fn, a.data_ptr(), _ptr(a2), w.data_ptr(), y.data_ptr(), m, n, k1, k2, epi, act_cols, _ptr(bias),
-              _ptr(rowbias), rowbias_group, _ptr(gamma), _ptr(beta), _ptr(residual), None, _stream())
+    with PROFILE.region(f"k:linear[{n}x{k1 + k2}]"):
+        _lib.call(fn, a.data_ptr(), _ptr(a2), w.data_ptr(), y.data_ptr(), m, n, k1, k2, epi, act_cols, _ptr(bias),
+                  _ptr(rowbias), rowbias_group, _ptr(gamma), _ptr(beta), _ptr(residual), None, _stream())
     return y
 
 
@@ -117,8 +168,9 @@ def similarity(f0: torch.Tensor, f1: torch.Tensor, temperature: float, impl: Opt
         b3 = torch.empty((n, s, 3 * c), device=f0.device, dtype=torch.float16)
         _lib.call("gf_pack_split_f16", f0.data_ptr(), a3.data_ptr(), n * l, c, in_scale, 0, _stream())
         _lib.call("gf_pack_split_f16", f1.data_ptr(), b3.data_ptr(), n * s, c, in_scale, 1, _stream())
-        _lib.call("gf_similarity_f16x3", a3.data_ptr(), b3.data_ptr(), sim.data_ptr(), n, l, s, 3 * c,
-                  1.0 / temperature, _stream())
+        with PROFILE.region("k:similarity"):
+            _lib.call("gf_similarity_f16x3", a3.data_ptr(), b3.data_ptr(), sim.data_ptr(), n, l, s, 3 * c,
+                      1.0 / temperature, _stream())
     else:
         _lib.call("gf_similarity_ref", f0.data_ptr(), f1.data_ptr(), sim.data_ptr(), n, l, s, c, in_scale,
                   1.0 / temperature, _stream())
