@@ -201,9 +201,9 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ops.PROFILE.enable("similarity")
+    ops.PROFILE.enable("similarity_f16x3")
     ms, outs, launches = timed(step_resident, args.steps)
-    sim_ms = ops.PROFILE.collect("similarity")            # per-launch CUDA-event durations of the conf-matrix GEMM
+    sim_ms = ops.PROFILE.collect("similarity_f16x3")            # per-launch CUDA-event durations of the conf-matrix GEMM
     ops.PROFILE.disable()
     ms_e2e, outs_e2e, _ = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None

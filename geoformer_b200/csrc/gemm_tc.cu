@@ -7,7 +7,7 @@
 //   warp 1      MMA issuer     : one elected lane issues tcgen05.mma (M=128, N=BN, K=32 bytes per instruction),
 //                                accumulating in TMEM; double-buffered accumulator (2 x BN columns)
 //   warps 2..5  epilogue       : tcgen05.ld (thread == output row), fused bias / activation / LayerNorm /
-//                                residual, direct global stores
+//                                residual; 32x32 boxes staged in swizzled smem and written with TMA stores
 // kind::tf32 consumes fp32 activations straight from HBM (no conversion pass); kind::f16 is used by the
 // split-fp16 similarity.  Tile: 128 x BN x (128 bytes of K).
 #include "common.cuh"
@@ -34,6 +34,7 @@ struct GemmParams {
   float out_scale;
   const int* m_dev;
   int tiles_n;
+  int tma_store;   // 1: epilogue stages 32x32 boxes in swizzled smem and TMA-stores them (needs ldy % 4 == 0)
 };
 
 constexpr int kBM = 128;
@@ -44,25 +45,27 @@ template <int BN> struct GemmCfg {
   static constexpr int kStageBytes = kStageABytes + kStageBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : 6;
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 4 * 2 * 4096;   // per epilogue warp: 2 x (32 rows x 128 B) output boxes
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ float apply_act(float x, int epi, bool in_act_cols) {
-  if (epi & GF_EPI_RELU) x = fmaxf(x, 0.f);
-  if (epi & GF_EPI_TANH) x = tanhf(x);
-  if ((epi & GF_EPI_ELU1) && in_act_cols) x = elu1(x);
-  return x;
+// tanh(x) = sign(x) * (1 - 2 / (exp(2|x|) + 1)); abs error ~1e-7 (well below the tf32 operand rounding)
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float e = __expf(2.f * fabsf(x));
+  const float t = 1.f - __fdividef(2.f, e + 1.f);
+  return copysignf(t, x);
 }
 
 template <int KIND, int BN>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int BKE = (KIND == 0) ? 32 : 64;   // elements per 128-byte K block
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full = empty_bar + Cfg::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -81,6 +84,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmA2);
     ptx::prefetch_tmap(&tmB);
+    ptx::prefetch_tmap(&tmY);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -150,6 +154,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------ epilogue (warps 2..5) ------------------------------
     const int quad = warp & 3;                           // TMEM lane quadrant this warp may access
     int acc = 0; uint32_t acc_phase = 0;
+    uint32_t chunk_ctr = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int n_blk = t % p.tiles_n;
       const int rest = t / p.tiles_n;
@@ -164,6 +169,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const float* rrow = p.residual ? p.residual + (int64_t)row * p.ldres : nullptr;
       const float* rb = p.rowbias ? p.rowbias + (int64_t)(row / p.rowbias_group) * p.N : nullptr;
       const int col0 = n_blk * BN;
+      uint8_t* wstage = staging + (warp - 2) * 8192;     // this warp's two 4 KB boxes
+      // residual tile slice of this lane for one 32x32 chunk: 8 coalesced float4 (4 rows x 128 B per instruction);
+      // software-pipelined one chunk ahead so that the global-load latency hides behind the previous chunk
+      float4 rnext[8];
+      auto fetch_residual = [&](int gcol, float4* dst) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + (lane >> 3), ch = lane & 7;
+          const int grow = m_blk * kBM + quad * 32 + rr;
+          dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (grow < m_live && gcol + ch * 4 < p.N)
+            dst[it] = __ldg(reinterpret_cast<const float4*>(p.residual + (int64_t)grow * p.ldres + gcol + ch * 4));
+        }
+      };
+      const bool stage_res = p.tma_store && p.residual != nullptr;
+      if (stage_res) fetch_residual(col0, rnext);
       float mean = 0.f, rstd = 1.f;
       if (p.epi & GF_EPI_LN) {
         // LayerNorm over the full row (BN == N): two extra sweeps over TMEM (mean, then centred variance)
@@ -187,31 +208,101 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         rstd = rsqrtf(q * (1.f / BN) + 1e-5f);
       }
       for (int c = 0; c < BN; c += 32) {
+        const int gc = col0 + c;
+        if (gc >= p.N) break;                              // column tail of the last tile (warp-uniform)
+        uint8_t* box = wstage + (chunk_ctr & 1) * 4096;
+        ++chunk_ctr;
+        if (p.tma_store) {
+          if (lane == 0) ptx::bulk_wait_read<1>();         // the store issued 2 chunks ago no longer reads this box
+          __syncwarp();
+          if (stage_res) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + (lane >> 3), ch = lane & 7;
+              *reinterpret_cast<float4*>(box + rr * 128 + ((ch ^ (rr & 7)) << 4)) = rnext[it];
+            }
+            if (c + 32 < BN && gc + 32 < p.N) fetch_residual(gc + 32, rnext);
+            __syncwarp();
+          }
+        }
         float v[32];
         ptx::tmem_ld_32x32(t_row + c, v);
         ptx::tmem_ld_wait();
-        const int gc = col0 + c;
+        // Epilogue math as warp-uniform branches around whole 32-element loops: only the taken
+        // variant issues instructions (a predicated all-in-one body cost ~280 issue slots per element).
+        const bool full = gc + 32 <= p.N;
+        if (p.out_scale != 1.f) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = v[j] * p.out_scale;
-          const int col = gc + j;
-          if (col < p.N) {
-            if (p.bias) x += __ldg(p.bias + col);
-            if (rb && row_ok) x += __ldg(rb + col);
-            x = apply_act(x, p.epi, col < p.act_cols);
-            if (p.epi & GF_EPI_LN) x = (x - mean) * rstd * __ldg(p.gamma + col) + __ldg(p.beta + col);
-            if (rrow && row_ok) x += __ldg(rrow + col);
-          }
-          v[j] = x;
+          for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
         }
-        if (row_ok) {
-          if (gc + 32 <= p.N && (p.ldy & 3) == 0 && (p.y_batch_stride & 3) == 0) {
-            float4* dst = reinterpret_cast<float4*>(yrow + gc);
+        if (p.bias) {
+          if (full) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gc) + j);
+              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+            }
           } else {
-            for (int j = 0; j < 32; ++j) if (gc + j < p.N) yrow[gc + j] = v[j];
+            for (int j = 0; j < 32; ++j) if (gc + j < p.N) v[j] += __ldg(p.bias + gc + j);
           }
+        }
+        if (rb && row_ok) {
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(rb + gc) + j);
+              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j) if (gc + j < p.N) v[j] += __ldg(rb + gc + j);
+          }
+        }
+        if (p.epi & GF_EPI_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (p.epi & GF_EPI_TANH) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[j]);
+        }
+        if ((p.epi & GF_EPI_ELU1) && gc < p.act_cols) {
+          if (gc + 32 <= p.act_cols) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] + 1.f : __expf(v[j]);
+          } else {
+            for (int j = 0; j < 32; ++j) if (gc + j < p.act_cols) v[j] = v[j] > 0.f ? v[j] + 1.f : __expf(v[j]);
+          }
+        }
+        if (p.epi & GF_EPI_LN) {                            // BN == N: chunks are always full
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + gc) + j);
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta + gc) + j);
+            v[4 * j] = (v[4 * j] - mean) * rstd * g4.x + b4.x;
+            v[4 * j + 1] = (v[4 * j + 1] - mean) * rstd * g4.y + b4.y;
+            v[4 * j + 2] = (v[4 * j + 2] - mean) * rstd * g4.z + b4.z;
+            v[4 * j + 3] = (v[4 * j + 3] - mean) * rstd * g4.w + b4.w;
+          }
+        }
+        if (rrow && row_ok && !p.tma_store) {
+          for (int j = 0; j < 32; ++j) if (gc + j < p.N) v[j] += __ldg(rrow + gc + j);
+        }
+        if (p.tma_store) {
+          uint8_t* myrow = box + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4* dst = reinterpret_cast<float4*>(myrow + ((j ^ (lane & 7)) << 4));
+            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (p.residual) { const float4 r4 = *dst; o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
+            *dst = o;
+          }
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_3d(&tmY, box, gc, m_blk * kBM + quad * 32, batch);
+            ptx::bulk_commit();
+          }
+        } else if (row_ok) {
+          for (int j = 0; j < 32; ++j) if (gc + j < p.N) yrow[gc + j] = v[j];
         }
       }
       ptx::tc_fence_before();
@@ -219,6 +310,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) ptx::bulk_wait<0>();                    // all TMA stores of this warp have completed
   }
 
   ptx::tc_fence_before();
@@ -270,9 +362,24 @@ static int make_tmap(CUtensorMap* m, const void* base, int esize, int64_t k, int
   return GF_OK;
 }
 
+// output map: dims {N, M, batches} fp32, box {32 cols, 32 rows, 1}, 128B swizzle (matches the epilogue staging)
+static int make_out_tmap(CUtensorMap* m, float* base, int64_t n, int64_t rows, int64_t batches, int64_t ld,
+                         int64_t batch_stride) {
+  if (!g_encode) return gf_set_error(GF_ERR_DRIVER, "gf_init() was not called");
+  cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)rows, (cuuint64_t)batches};
+  cuuint64_t strides[2] = {(cuuint64_t)(ld * 4), (cuuint64_t)(batch_stride * 4)};
+  if (batches == 1) strides[1] = strides[0] * (cuuint64_t)rows;
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return gf_set_error(GF_ERR_DRIVER, "cuTensorMapEncodeTiled(out) failed");
+  return GF_OK;
+}
+
 template <int KIND, int BN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const GemmParams& p,
-                       cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& ty,
+                       const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   auto kern = gemm_tc_kernel<KIND, BN>;
@@ -284,7 +391,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta2, const CUte
   const int64_t tiles = (int64_t)p.batches * gf_cdiv(p.M, kBM) * p.tiles_n;
   if (tiles == 0) return GF_OK;
   const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
-  kern<<<grid, 192, Cfg::kSmemBytes, stream>>>(ta, ta2, tb, p);
+  kern<<<grid, 192, Cfg::kSmemBytes, stream>>>(ta, ta2, tb, ty, p);
   g_launches++;
   GF_CHECK_LAUNCH();
   return GF_OK;
@@ -317,8 +424,11 @@ extern "C" int gf_linear_tf32(const float* A, const float* A2, const float* W, f
   p.bias = bias; p.rowbias = rowbias; p.rowbias_group = rowbias_group > 0 ? rowbias_group : 1;
   p.gamma = gamma; p.beta = beta; p.residual = residual; p.ldres = N; p.out_scale = 1.f; p.m_dev = m_dev;
   p.tiles_n = N / BN;
-  if (BN == 256) return launch_gemm<0, 256>(ta, ta2, tb, p, (cudaStream_t)stream);
-  return launch_gemm<0, 128>(ta, ta2, tb, p, (cudaStream_t)stream);
+  p.tma_store = 1;
+  CUtensorMap ty;
+  if ((rc = make_out_tmap(&ty, Y, N, M, 1, N, 0))) return rc;
+  if (BN == 256) return launch_gemm<0, 256>(ta, ta2, tb, ty, p, (cudaStream_t)stream);
+  return launch_gemm<0, 128>(ta, ta2, tb, ty, p, (cudaStream_t)stream);
 }
 
 extern "C" int gf_similarity_f16x3(const void* a3, const void* b3, float* sim, int n, int l, int s, int c3,
@@ -333,5 +443,8 @@ extern "C" int gf_similarity_f16x3(const void* a3, const void* b3, float* sim, i
   p.Y = sim; p.ldy = s; p.y_batch_stride = (int64_t)l * s; p.M = l; p.N = s; p.batches = n;
   p.kblocks1 = c3 / 64; p.kblocks2 = 0; p.epi = 0; p.act_cols = 0; p.rowbias_group = 1; p.ldres = s;
   p.out_scale = out_scale; p.tiles_n = gf_cdiv(s, BN);
-  return launch_gemm<1, 256>(ta, ta, tb, p, (cudaStream_t)stream);
+  p.tma_store = (s % 4 == 0) ? 1 : 0;
+  CUtensorMap ty = ta;
+  if (p.tma_store && (rc = make_out_tmap(&ty, sim, s, l, n, s, (int64_t)l * s))) return rc;
+  return launch_gemm<1, 256>(ta, ta, tb, ty, p, (cudaStream_t)stream);
 }

@@ -306,9 +306,10 @@ def geo_module(pw: PackedWeights, x0: torch.Tensor, x1: torch.Tensor, first: dic
     n = x0.shape[0]
     dev = x0.device
     scale = int(hw0_i[0] // hw0_c[0])
-    k0 = first["mkpts0_c"].cpu().numpy()                 # device -> host: RANSAC runs in OpenCV (geo_module.py:48)
-    k1 = first["mkpts1_c"].cpu().numpy()
-    hm, has_h_np, aidx_np, acnt_np = geo_prepare_host(k0, k1, np.asarray(counts), hw0_c, hw1_c, scale, ransac_thr)
+    with ops.PROFILE.region("host:ransac"):
+        k0 = first["mkpts0_c"].cpu().numpy()             # device -> host: RANSAC runs in OpenCV (geo_module.py:48)
+        k1 = first["mkpts1_c"].cpu().numpy()
+        hm, has_h_np, aidx_np, acnt_np = geo_prepare_host(k0, k1, np.asarray(counts), hw0_c, hw1_c, scale, ransac_thr)
     if info is not None:
         info.update(has_h=has_h_np.copy(), anchor_cnt=acnt_np.copy(), hmat=hm.copy())
     hm_d = torch.from_numpy(hm).to(dev, non_blocking=True)

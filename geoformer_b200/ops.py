@@ -79,6 +79,15 @@ class _Profile:
 PROFILE = _Profile()
 
 
+def _call(name: str, *args, tag: str = "") -> None:
+    """Launch through the C ABI, optionally timed as region 'k:<name><tag>'."""
+    if PROFILE.pattern is None:
+        _lib.call(name, *args)
+    else:
+        with PROFILE.region("k:" + name[3:] + tag):
+            _lib.call(name, *args)
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -116,9 +125,9 @@ def linear(a: torch.Tensor, w: torch.Tensor, a2: Optional[torch.Tensor] = None, 
         assert residual.is_contiguous() and residual.shape == (m, n)
     y = out if out is not None else torch.empty((m, n), device=a.device, dtype=torch.float32)
     fn = "gf_linear_tf32" if (impl or _LINEAR_IMPL) == "tf32" else "gf_linear_ref"
-    with PROFILE.region(f"k:linear[{n}x{k1 + k2}]"):
-        _lib.call(fn, a.data_ptr(), _ptr(a2), w.data_ptr(), y.data_ptr(), m, n, k1, k2, epi, act_cols, _ptr(bias),
-                  _ptr(rowbias), rowbias_group, _ptr(gamma), _ptr(beta), _ptr(residual), None, _stream())
+    _call(fn, a.data_ptr(), _ptr(a2), w.data_ptr(), y.data_ptr(), m, n, k1, k2, epi, act_cols, _ptr(bias),
+          _ptr(rowbias), rowbias_group, _ptr(gamma), _ptr(beta), _ptr(residual), None, _stream(),
+          tag=f"[{n}x{k1 + k2}]")
     return y
 
 
@@ -126,7 +135,7 @@ def add_posenc(x: torch.Tensor, pe: torch.Tensor) -> torch.Tensor:
     n, l, c = x.shape
     assert x.is_contiguous() and pe.is_contiguous() and pe.shape == (l, c)
     out = torch.empty_like(x)
-    _lib.call("gf_add_posenc", x.data_ptr(), pe.data_ptr(), out.data_ptr(), n, l, c, _stream())
+    _call("gf_add_posenc", x.data_ptr(), pe.data_ptr(), out.data_ptr(), n, l, c, _stream())
     return out
 
 
@@ -138,10 +147,10 @@ def linattn(q: torch.Tensor, ldq: int, k: torch.Tensor, ldk: int, v: torch.Tenso
     partial = torch.empty(nfl, device=dev, dtype=torch.float32)
     kv = torch.empty((n, heads, dim, dim), device=dev, dtype=torch.float32)
     ksum = torch.empty((n, heads, dim), device=dev, dtype=torch.float32)
-    _lib.call("gf_linattn_reduce", k.data_ptr(), ldk, v.data_ptr(), ldv, n, s, heads, dim, partial.data_ptr(),
+    _call("gf_linattn_reduce", k.data_ptr(), ldk, v.data_ptr(), ldv, n, s, heads, dim, partial.data_ptr(),
               kv.data_ptr(), ksum.data_ptr(), _stream())
     out = torch.empty((n * l, heads * dim), device=dev, dtype=torch.float32)
-    _lib.call("gf_linattn_apply", q.data_ptr(), ldq, kv.data_ptr(), ksum.data_ptr(), out.data_ptr(), n, l, s, heads,
+    _call("gf_linattn_apply", q.data_ptr(), ldq, kv.data_ptr(), ksum.data_ptr(), out.data_ptr(), n, l, s, heads,
               dim, _stream())
     return out
 
@@ -149,7 +158,7 @@ def linattn(q: torch.Tensor, ldq: int, k: torch.Tensor, ldk: int, v: torch.Tenso
 def linattn_window(q: torch.Tensor, ldq: int, k: torch.Tensor, ldk: int, v: torch.Tensor, ldv: int, n_windows: int,
                    tokens: int, heads: int, dim: int) -> torch.Tensor:
     out = torch.empty((n_windows * tokens, heads * dim), device=q.device, dtype=torch.float32)
-    _lib.call("gf_linattn_window", q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, out.data_ptr(),
+    _call("gf_linattn_window", q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, out.data_ptr(),
               n_windows, tokens, heads, dim, _stream())
     return out
 
@@ -166,13 +175,12 @@ def similarity(f0: torch.Tensor, f1: torch.Tensor, temperature: float, impl: Opt
     if (impl or _SIM_IMPL) == "f16x3":
         a3 = torch.empty((n, l, 3 * c), device=f0.device, dtype=torch.float16)
         b3 = torch.empty((n, s, 3 * c), device=f0.device, dtype=torch.float16)
-        _lib.call("gf_pack_split_f16", f0.data_ptr(), a3.data_ptr(), n * l, c, in_scale, 0, _stream())
-        _lib.call("gf_pack_split_f16", f1.data_ptr(), b3.data_ptr(), n * s, c, in_scale, 1, _stream())
-        with PROFILE.region("k:similarity"):
-            _lib.call("gf_similarity_f16x3", a3.data_ptr(), b3.data_ptr(), sim.data_ptr(), n, l, s, 3 * c,
-                      1.0 / temperature, _stream())
+        _call("gf_pack_split_f16", f0.data_ptr(), a3.data_ptr(), n * l, c, in_scale, 0, _stream())
+        _call("gf_pack_split_f16", f1.data_ptr(), b3.data_ptr(), n * s, c, in_scale, 1, _stream())
+        _call("gf_similarity_f16x3", a3.data_ptr(), b3.data_ptr(), sim.data_ptr(), n, l, s, 3 * c,
+              1.0 / temperature, _stream())
     else:
-        _lib.call("gf_similarity_ref", f0.data_ptr(), f1.data_ptr(), sim.data_ptr(), n, l, s, c, in_scale,
+        _call("gf_similarity_ref", f0.data_ptr(), f1.data_ptr(), sim.data_ptr(), n, l, s, c, in_scale,
                   1.0 / temperature, _stream())
     return sim
 
@@ -183,10 +191,10 @@ def dual_softmax_(sim: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.
     dev = sim.device
     rmax = torch.empty((n, l), device=dev); rsum = torch.empty((n, l), device=dev)
     cmax = torch.empty((n, s), device=dev); csum = torch.empty((n, s), device=dev)
-    _lib.call("gf_dual_softmax_stats", sim.data_ptr(), n, l, s, rmax.data_ptr(), rsum.data_ptr(), cmax.data_ptr(),
+    _call("gf_dual_softmax_stats", sim.data_ptr(), n, l, s, rmax.data_ptr(), rsum.data_ptr(), cmax.data_ptr(),
               csum.data_ptr(), _stream())
     crmax = torch.empty((n, l), device=dev); ccmax = torch.empty((n, s), device=dev)
-    _lib.call("gf_dual_softmax_conf", sim.data_ptr(), n, l, s, rmax.data_ptr(), rsum.data_ptr(), cmax.data_ptr(),
+    _call("gf_dual_softmax_conf", sim.data_ptr(), n, l, s, rmax.data_ptr(), rsum.data_ptr(), cmax.data_ptr(),
               csum.data_ptr(), crmax.data_ptr(), ccmax.data_ptr(), _stream())
     return sim, crmax, ccmax
 
@@ -194,7 +202,7 @@ def dual_softmax_(sim: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.
 def conf_row_col_max(conf: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     n, l, s = conf.shape
     crmax = torch.empty((n, l), device=conf.device); ccmax = torch.empty((n, s), device=conf.device)
-    _lib.call("gf_conf_row_col_max", conf.data_ptr(), n, l, s, crmax.data_ptr(), ccmax.data_ptr(), _stream())
+    _call("gf_conf_row_col_max", conf.data_ptr(), n, l, s, crmax.data_ptr(), ccmax.data_ptr(), _stream())
     return crmax, ccmax
 
 
@@ -207,13 +215,13 @@ def mutual_nearest(conf: torch.Tensor, crmax: torch.Tensor, ccmax: torch.Tensor,
     dev = conf.device
     mj = torch.empty((n, l), device=dev, dtype=torch.int32)
     mc = torch.empty((n, l), device=dev, dtype=torch.float32)
-    _lib.call("gf_mnn_select", conf.data_ptr(), n, l, s, float(thr), int(border), hw0c[0], hw0c[1], hw1c[0], hw1c[1],
+    _call("gf_mnn_select", conf.data_ptr(), n, l, s, float(thr), int(border), hw0c[0], hw0c[1], hw1c[0], hw1c[1],
               crmax.data_ptr(), ccmax.data_ptr(), mj.data_ptr(), mc.data_ptr(), _stream())
     cap = n * l
     b_ids = torch.empty(cap, device=dev, dtype=torch.int64); i_ids = torch.empty_like(b_ids); j_ids = torch.empty_like(b_ids)
     mconf = torch.empty(cap, device=dev); k0 = torch.empty((cap, 2), device=dev); k1 = torch.empty((cap, 2), device=dev)
     counts = torch.empty(n + 1, device=dev, dtype=torch.int32)
-    _lib.call("gf_compact_coarse", mj.data_ptr(), mc.data_ptr(), n, l, hw0c[1], hw1c[1], float(scale), b_ids.data_ptr(),
+    _call("gf_compact_coarse", mj.data_ptr(), mc.data_ptr(), n, l, hw0c[1], hw1c[1], float(scale), b_ids.data_ptr(),
               i_ids.data_ptr(), j_ids.data_ptr(), mconf.data_ptr(), k0.data_ptr(), k1.data_ptr(), counts.data_ptr(),
               counts.data_ptr() + 4 * n, cap, _stream())
     counts_h = counts.cpu()
@@ -227,28 +235,28 @@ def geo_window_table(hmat: torch.Tensor, has_h: torch.Tensor, n: int, hw_src_c, 
                      window: int) -> torch.Tensor:
     l = hw_src_c[0] * hw_src_c[1]
     widx = torch.empty((n, l, window * window), device=hmat.device, dtype=torch.int32)
-    _lib.call("gf_geo_window_table", hmat.data_ptr(), has_h.data_ptr(), n, hw_src_c[0], hw_src_c[1], hw_dst_px[0],
+    _call("gf_geo_window_table", hmat.data_ptr(), has_h.data_ptr(), n, hw_src_c[0], hw_src_c[1], hw_dst_px[0],
               hw_dst_px[1], w_dst_c, scale, window, widx.data_ptr(), _stream())
     return widx
 
 
 def geo_self_attention(q, ldq, k, ldk, v, ldv, n, l, heads, dim, anchor_idx, anchor_cnt) -> torch.Tensor:
     out = torch.empty((n * l, heads * dim), device=q.device, dtype=torch.float32)
-    _lib.call("gf_geo_self_attention", q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, out.data_ptr(), n, l,
+    _call("gf_geo_self_attention", q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, out.data_ptr(), n, l,
               heads, dim, anchor_idx.data_ptr(), anchor_cnt.data_ptr(), anchor_idx.shape[1], _stream())
     return out
 
 
 def geo_cross_attention(q, ldq, kp, ldk, vp, ldv, n, l, s, heads, dim, widx) -> torch.Tensor:
     out = torch.empty((n * l, heads * dim), device=q.device, dtype=torch.float32)
-    _lib.call("gf_geo_cross_attention", q.data_ptr(), ldq, kp.data_ptr(), ldk, vp.data_ptr(), ldv, out.data_ptr(), n,
+    _call("gf_geo_cross_attention", q.data_ptr(), ldq, kp.data_ptr(), ldk, vp.data_ptr(), ldv, out.data_ptr(), n,
               l, s, heads, dim, widx.data_ptr(), widx.shape[2], _stream())
     return out
 
 
 def select_rows_(dst: torch.Tensor, src: torch.Tensor, flag: torch.Tensor, n: int, l: int, c: int) -> None:
     """dst[b] = src[b] for samples with flag[b] == 0 (per-sample skipped layers)."""
-    _lib.call("gf_select_rows", dst.data_ptr(), src.data_ptr(), flag.data_ptr(), n, l, c, _stream())
+    _call("gf_select_rows", dst.data_ptr(), src.data_ptr(), flag.data_ptr(), n, l, c, _stream())
 
 
 # ------------------------------------------------------------------ fine level
@@ -259,7 +267,7 @@ def fine_gather(fine_nhwc: torch.Tensor, b_ids, tok_ids, wc: int, stride: int, w
     m = b_ids.shape[0]
     if out is None:
         out = torch.empty((m, window * window, c), device=fine_nhwc.device, dtype=torch.float32)
-    _lib.call("gf_fine_gather", fine_nhwc.data_ptr(), hf, wf, c, b_ids.data_ptr(), tok_ids.data_ptr(), m, wc, stride,
+    _call("gf_fine_gather", fine_nhwc.data_ptr(), hf, wf, c, b_ids.data_ptr(), tok_ids.data_ptr(), m, wc, stride,
               window, out.data_ptr(), _stream())
     return out
 
@@ -270,7 +278,7 @@ def gather_rows(feat: torch.Tensor, b_ids, tok_ids, out: Optional[torch.Tensor] 
     m = b_ids.shape[0]
     if out is None:
         out = torch.empty((m, c), device=feat.device, dtype=torch.float32)
-    _lib.call("gf_gather_rows", feat.data_ptr(), l, c, b_ids.data_ptr(), tok_ids.data_ptr(), m, out.data_ptr(), _stream())
+    _call("gf_gather_rows", feat.data_ptr(), l, c, b_ids.data_ptr(), tok_ids.data_ptr(), m, out.data_ptr(), _stream())
     return out
 
 
@@ -281,11 +289,11 @@ def fine_match(f0: torch.Tensor, f1: torch.Tensor, temperature: float, thr: floa
     sel = torch.empty(m, device=dev, dtype=torch.int32); fi = torch.empty_like(sel); fj = torch.empty_like(sel)
     fconf = torch.empty(m, device=dev)
     fmat = torch.empty((m, ww, ww), device=dev) if want_matrix else None
-    _lib.call("gf_fine_match", f0.data_ptr(), f1.data_ptr(), m, ww, c, float(temperature), float(thr), sel.data_ptr(),
+    _call("gf_fine_match", f0.data_ptr(), f1.data_ptr(), m, ww, c, float(temperature), float(thr), sel.data_ptr(),
               fi.data_ptr(), fj.data_ptr(), fconf.data_ptr(), _ptr(fmat), _stream())
     k0 = torch.empty((m, 2), device=dev); k1 = torch.empty((m, 2), device=dev); mconf = torch.empty(m, device=dev)
     mb = torch.empty(m, device=dev, dtype=torch.int64); total = torch.empty(1, device=dev, dtype=torch.int32)
-    _lib.call("gf_compact_fine", sel.data_ptr(), fi.data_ptr(), fj.data_ptr(), fconf.data_ptr(), mkpts0_c.data_ptr(),
+    _call("gf_compact_fine", sel.data_ptr(), fi.data_ptr(), fj.data_ptr(), fconf.data_ptr(), mkpts0_c.data_ptr(),
               mkpts1_c.data_ptr(), b_ids.data_ptr(), m, window, float(coarse_scale), float(c2f), float(fine_scale),
               k0.data_ptr(), k1.data_ptr(), mconf.data_ptr(), mb.data_ptr(), total.data_ptr(), _stream())
     t = int(total.item())
