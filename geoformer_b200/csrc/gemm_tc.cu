@@ -352,7 +352,7 @@ static int make_tmap(CUtensorMap* m, const void* base, int esize, int64_t k, int
   if (!g_encode) return gf_set_error(GF_ERR_DRIVER, "gf_init() was not called");
   cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, (cuuint64_t)batches};
   cuuint64_t strides[2] = {(cuuint64_t)(row_stride_elems * esize), (cuuint64_t)(batch_stride_elems * esize)};
-  if (batches == 1) strides[1] = strides[0] * (cuuint64_t)rows;
+  if (batches == 1 && batch_stride_elems == 0) strides[1] = strides[0] * (cuuint64_t)rows;
   cuuint32_t box[3] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMapDataType dt = esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -368,7 +368,7 @@ static int make_out_tmap(CUtensorMap* m, float* base, int64_t n, int64_t rows, i
   if (!g_encode) return gf_set_error(GF_ERR_DRIVER, "gf_init() was not called");
   cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)rows, (cuuint64_t)batches};
   cuuint64_t strides[2] = {(cuuint64_t)(ld * 4), (cuuint64_t)(batch_stride * 4)};
-  if (batches == 1) strides[1] = strides[0] * (cuuint64_t)rows;
+  if (batches == 1 && batch_stride == 0) strides[1] = strides[0] * (cuuint64_t)rows;
   cuuint32_t box[3] = {32, 32, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -447,4 +447,26 @@ extern "C" int gf_similarity_f16x3(const void* a3, const void* b3, float* sim, i
   CUtensorMap ty = ta;
   if (p.tma_store && (rc = make_out_tmap(&ty, sim, s, l, n, s, (int64_t)l * s))) return rc;
   return launch_gemm<1, 256>(ta, ta, tb, ty, p, (cudaStream_t)stream);
+}
+
+// Batched K-major GEMM with explicit strides (floats): Y[b] = out_scale * A[b] (M x K) * B[b]^T (N x K).
+// Building block of the geo self-attention (Q K^T and P V per head, geo_attention.py:72-97).
+extern "C" int gf_gemm_tf32_batched(const float* A, int64_t lda, int64_t a_batch_stride, const float* B, int64_t ldb,
+                                    int64_t b_batch_stride, float* Y, int64_t ldy, int64_t y_batch_stride, int M,
+                                    int N, int K, int batches, float out_scale, gf_stream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || batches <= 0 || (K % 32) || (lda % 4) || (ldb % 4) || (ldy % 4) ||
+      (a_batch_stride % 4) || (b_batch_stride % 4) || (y_batch_stride % 4))
+    return gf_set_error(GF_ERR_ARG, "gf_gemm_tf32_batched: K % 32 == 0 and 16-byte aligned strides required");
+  const int BN = (N > 128) ? 256 : 128;
+  CUtensorMap ta, tb, ty;
+  int rc;
+  if ((rc = make_tmap(&ta, A, 4, K, M, batches, lda, batches == 1 ? lda * M : a_batch_stride, kBM))) return rc;
+  if ((rc = make_tmap(&tb, B, 4, K, N, batches, ldb, batches == 1 ? ldb * N : b_batch_stride, BN))) return rc;
+  if ((rc = make_out_tmap(&ty, Y, N, M, batches, ldy, batches == 1 ? ldy * M : y_batch_stride))) return rc;
+  GemmParams p{};
+  p.Y = Y; p.ldy = ldy; p.y_batch_stride = y_batch_stride; p.M = M; p.N = N; p.batches = batches;
+  p.kblocks1 = K / 32; p.kblocks2 = 0; p.epi = 0; p.act_cols = 0; p.rowbias_group = 1; p.ldres = ldy;
+  p.out_scale = out_scale; p.tiles_n = gf_cdiv(N, BN); p.tma_store = 1;
+  if (BN == 256) return launch_gemm<0, 256>(ta, ta, tb, ty, p, (cudaStream_t)stream);
+  return launch_gemm<0, 128>(ta, ta, tb, ty, p, (cudaStream_t)stream);
 }

@@ -227,6 +227,51 @@ __global__ void geo_cross_attention_kernel(const float* __restrict__ q, int ldq,
   *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// tensor-core path of the self attention: anchor K rows gathered per head (K-major for Q K^T) and
+// anchor V rows gathered transposed (K-major for P V), masked row soft-max in between.
+//   kg[h][n][s_pad][dim]   vt[h][n][dim][s_pad]   (zero beyond anchor_cnt[n])
+// ---------------------------------------------------------------------------------------------
+__global__ void gather_anchor_kv_kernel(const float* __restrict__ k, int ldk, const float* __restrict__ v, int ldv,
+                                        int n, int l, int heads, int dim, const int* __restrict__ anchor_idx,
+                                        const int* __restrict__ anchor_cnt, int anchor_cap, int s_pad,
+                                        float* __restrict__ kg, float* __restrict__ vt) {
+  const int c = heads * dim;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // over n * s_pad * c
+  if (idx >= (int64_t)n * s_pad * c) return;
+  const int ch = (int)(idx % c);
+  const int64_t r = idx / c;
+  const int s = (int)(r % s_pad), b = (int)(r / s_pad);
+  const int h = ch / dim, d = ch - h * dim;
+  float kv = 0.f, vv = 0.f;
+  if (s < anchor_cnt[b]) {
+    const int64_t tok = (int64_t)b * l + anchor_idx[(int64_t)b * anchor_cap + s];
+    kv = k[tok * ldk + ch];
+    vv = v[tok * ldv + ch];
+  }
+  kg[(((int64_t)h * n + b) * s_pad + s) * dim + d] = kv;
+  vt[(((int64_t)h * n + b) * dim + d) * s_pad + s] = vv;
+}
+
+// rows of [heads][n][l][s_pad]: p = softmax(x[0:cnt]) (x is already scaled), zeros beyond cnt.  One warp per row.
+__global__ void masked_softmax_rows_kernel(float* __restrict__ x, int64_t rows, int n, int l, int s_pad,
+                                           const int* __restrict__ cnt_per_sample) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int b = (int)((row / l) % n);
+  const int cnt = cnt_per_sample[b];
+  float* p = x + row * s_pad;
+  float m = -INFINITY;
+  for (int j = lane; j < cnt; j += 32) m = fmaxf(m, p[j]);
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int j = lane; j < cnt; j += 32) sum += expf(p[j] - m);
+  sum = warp_sum(sum);
+  const float inv = cnt > 0 ? 1.f / sum : 0.f;
+  for (int j = lane; j < s_pad; j += 32) p[j] = j < cnt ? expf(p[j] - m) * inv : 0.f;
+}
+
 }  // namespace gf
 
 using namespace gf;
@@ -265,6 +310,28 @@ extern "C" int gf_geo_cross_attention(const float* q, int ldq, const float* kpro
     return gf_set_error(GF_ERR_ARG, "gf_geo_cross_attention: needs heads*dim == 256, dim == 64, window <= 25");
   geo_cross_attention_kernel<<<gf_cdiv((int64_t)n * l, 4), 128, 0, STREAM>>>(q, ldq, kproj, ldk, vproj, ldv, out, n, l, s,
                                                                             widx, window2, 1.f / sqrtf((float)dim));
+  g_launches++;
+  GF_CHECK_LAUNCH();
+  return GF_OK;
+}
+
+extern "C" int gf_gather_anchor_kv(const float* k, int ldk, const float* v, int ldv, int n, int l, int heads, int dim,
+                                   const int* anchor_idx, const int* anchor_cnt, int anchor_cap, int s_pad, float* kg,
+                                   float* vt, gf_stream_t stream) {
+  if (n <= 0 || l <= 0 || heads <= 0 || dim <= 0 || s_pad <= 0) return gf_set_error(GF_ERR_ARG, "gf_gather_anchor_kv: bad shape");
+  const int64_t total = (int64_t)n * s_pad * heads * dim;
+  gather_anchor_kv_kernel<<<gf_cdiv(total, 256), 256, 0, STREAM>>>(k, ldk, v, ldv, n, l, heads, dim, anchor_idx, anchor_cnt,
+                                                                   anchor_cap, s_pad, kg, vt);
+  g_launches++;
+  GF_CHECK_LAUNCH();
+  return GF_OK;
+}
+
+extern "C" int gf_masked_softmax_rows(float* x, int heads, int n, int l, int s_pad, const int* cnt_per_sample,
+                                      gf_stream_t stream) {
+  if (heads <= 0 || n <= 0 || l <= 0 || s_pad <= 0) return gf_set_error(GF_ERR_ARG, "gf_masked_softmax_rows: bad shape");
+  const int64_t rows = (int64_t)heads * n * l;
+  masked_softmax_rows_kernel<<<gf_cdiv(rows, 8), 256, 0, STREAM>>>(x, rows, n, l, s_pad, cnt_per_sample);
   g_launches++;
   GF_CHECK_LAUNCH();
   return GF_OK;

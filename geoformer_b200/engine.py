@@ -68,12 +68,31 @@ class PackedWeights:
         self.fp = dict(wd=f32(sd["fine_preprocess.down_proj.weight"]), bd=f32(sd["fine_preprocess.down_proj.bias"]),
                        wa=f32(wm[:, :cf]), wb=f32(wm[:, cf:]), bm=f32(sd["fine_preprocess.merge_feat.bias"]))
 
-        # backbone: BN folded, channels-last, tensor-core dtype (cuDNN through torch)
-        def conv(name, bn=None):
+        # backbone: BN folded, channels-last, tensor-core dtype (cuDNN through torch).  Channel counts that
+        # are not a multiple of `cpad_to` (the 196-wide stage) are zero-padded in the weights: padded output
+        # channels stay exactly 0 through ReLU / residual adds and padded input channels multiply zeros, so the
+        # result is unchanged while cuDNN keeps its aligned tensor-core kernels (no nhwcAddPadding passes).
+        cpad_to = int(os.environ.get("GF_BACKBONE_CPAD", "8"))
+        bsd = {k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")}
+
+        def padc(c):
+            return c if (c % cpad_to == 0 or c == 1) else (c + cpad_to - 1) // cpad_to * cpad_to
+
+        def conv(name, bn=None, pad_out=True):
             w = sd["backbone." + name + ".weight"]
             b = None
             if bn is not None:
-                w, b = _fold_bn(w, {k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")}, bn)
+                w, b = _fold_bn(w, bsd, bn)
+            co, ci = w.shape[:2]
+            cop, cip = (padc(co) if pad_out else co), padc(ci)
+            if (cop, cip) != (co, ci):
+                wp = torch.zeros((cop, cip) + tuple(w.shape[2:]), dtype=w.dtype)
+                wp[:co, :ci] = w
+                w = wp
+                if b is not None:
+                    bp = torch.zeros(cop, dtype=b.dtype)
+                    bp[:co] = b
+                    b = bp
             w = w.detach().to(device=device, dtype=backbone_dtype).contiguous(memory_format=torch.channels_last)
             b = None if b is None else b.to(device=device, dtype=backbone_dtype)
             return w, b
@@ -271,12 +290,14 @@ def geo_prepare_host(k0: np.ndarray, k1: np.ndarray, counts: np.ndarray, hw0_c, 
     return hm, has_h, aidx, acnt
 
 
-def geo_self_layer(lw: dict, x: torch.Tensor, aidx: torch.Tensor, acnt: torch.Tensor, heads: int) -> torch.Tensor:
+def geo_self_layer(lw: dict, x: torch.Tensor, aidx: torch.Tensor, acnt: torch.Tensor, heads: int,
+                   max_cnt: int = 0) -> torch.Tensor:
     """All tokens attend to the anchor tokens of their own image (geo_transformer/transformer.py:111-124)."""
     n, l, c = x.shape
     x2d = x.reshape(n * l, c)
     qkv = ops.linear(x2d, lw["wqkv"])
-    att = ops.geo_self_attention(qkv, 3 * c, qkv[:, c:], 3 * c, qkv[:, 2 * c:], 3 * c, n, l, heads, c // heads, aidx, acnt)
+    att = ops.geo_self_attention(qkv, 3 * c, qkv[:, c:], 3 * c, qkv[:, 2 * c:], 3 * c, n, l, heads, c // heads, aidx, acnt,
+                                 max_cnt)
     y = _post_attention(lw, x2d, att, EPI_TANH)
     ops.select_rows_(y, x2d, acnt, n, l, c)            # samples without anchors keep their features
     return y.view(n, l, c)
@@ -325,9 +346,9 @@ def geo_module(pw: PackedWeights, x0: torch.Tensor, x1: torch.Tensor, first: dic
     for lw, name in zip(pw.geo, names):
         if name == "self":
             if acnt_np[0].any():
-                x0 = geo_self_layer(lw, x0, aidx[0], acnt[0], heads)
+                x0 = geo_self_layer(lw, x0, aidx[0], acnt[0], heads, int(acnt_np[0].max()))
             if acnt_np[1].any():
-                x1 = geo_self_layer(lw, x1, aidx[1], acnt[1], heads)
+                x1 = geo_self_layer(lw, x1, aidx[1], acnt[1], heads, int(acnt_np[1].max()))
         elif any_h:
             x0, x1 = geo_cross_layer(lw, x0, x1, widx_in1, widx_in0, has_h, heads)
     return x0, x1

@@ -17,10 +17,15 @@ EPI_RELU, EPI_TANH, EPI_ELU1, EPI_LN = 1, 2, 4, 8
 # (accuracy mode for parity runs; same ABI contract).  Both are sm_100a CUDA from this library.
 _LINEAR_IMPL = "tf32"
 _SIM_IMPL = "f16x3"
+_ATTN_IMPL = "tf32"
 
 
-def set_precision(linear: Optional[str] = None, similarity: Optional[str] = None) -> None:
-    global _LINEAR_IMPL, _SIM_IMPL
+def set_precision(linear: Optional[str] = None, similarity: Optional[str] = None,
+                  attention: Optional[str] = None) -> None:
+    global _LINEAR_IMPL, _SIM_IMPL, _ATTN_IMPL
+    if attention is not None:
+        assert attention in ("tf32", "ref")
+        _ATTN_IMPL = attention
     if linear is not None:
         assert linear in ("tf32", "ref")
         _LINEAR_IMPL = linear
@@ -240,8 +245,28 @@ def geo_window_table(hmat: torch.Tensor, has_h: torch.Tensor, n: int, hw_src_c, 
     return widx
 
 
-def geo_self_attention(q, ldq, k, ldk, v, ldv, n, l, heads, dim, anchor_idx, anchor_cnt) -> torch.Tensor:
-    out = torch.empty((n * l, heads * dim), device=q.device, dtype=torch.float32)
+def geo_self_attention(q, ldq, k, ldk, v, ldv, n, l, heads, dim, anchor_idx, anchor_cnt, max_cnt: int = 0,
+                       impl: Optional[str] = None) -> torch.Tensor:
+    """Full softmax attention of all l tokens against the anchor tokens of the same image.
+    'tf32': per-head tcgen05 GEMMs over materialised score blocks; 'ref': fp32 flash-style FFMA kernel."""
+    c = heads * dim
+    out = torch.empty((n * l, c), device=q.device, dtype=torch.float32)
+    if (impl or _ATTN_IMPL) == "tf32" and max_cnt > 0:
+        s_pad = (max_cnt + 31) // 32 * 32
+        dev = q.device
+        kg = torch.empty((heads, n, s_pad, dim), device=dev, dtype=torch.float32)
+        vt = torch.empty((heads, n, dim, s_pad), device=dev, dtype=torch.float32)
+        sc = torch.empty((heads, n, l, s_pad), device=dev, dtype=torch.float32)
+        _call("gf_gather_anchor_kv", k.data_ptr(), ldk, v.data_ptr(), ldv, n, l, heads, dim, anchor_idx.data_ptr(),
+              anchor_cnt.data_ptr(), anchor_idx.shape[1], s_pad, kg.data_ptr(), vt.data_ptr(), _stream())
+        for h in range(heads):
+            _call("gf_gemm_tf32_batched", q.data_ptr() + 4 * h * dim, ldq, l * ldq, kg[h].data_ptr(), dim, s_pad * dim,
+                  sc[h].data_ptr(), s_pad, l * s_pad, l, s_pad, dim, n, 1.0 / dim ** 0.5, _stream(), tag="[QK]")
+        _call("gf_masked_softmax_rows", sc.data_ptr(), heads, n, l, s_pad, anchor_cnt.data_ptr(), _stream())
+        for h in range(heads):
+            _call("gf_gemm_tf32_batched", sc[h].data_ptr(), s_pad, l * s_pad, vt[h].data_ptr(), s_pad, dim * s_pad,
+                  out.data_ptr() + 4 * h * dim, c, l * c, l, dim, s_pad, n, 1.0, _stream(), tag="[PV]")
+        return out
     _call("gf_geo_self_attention", q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, out.data_ptr(), n, l,
               heads, dim, anchor_idx.data_ptr(), anchor_cnt.data_ptr(), anchor_idx.shape[1], _stream())
     return out

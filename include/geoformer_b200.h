@@ -135,6 +135,20 @@ int gf_geo_window_table(const float* hmat, const int* has_h, int n, int h_src_c,
 int gf_geo_self_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out,
                           int n, int l, int heads, int dim, const int* anchor_idx, const int* anchor_cnt,
                           int anchor_cap, gf_stream_t stream);
+/* Tensor-core path of the same self attention, as three steps over materialised per-head score blocks:
+ *   gf_gather_anchor_kv   : kg[h][n][s_pad][dim] (K rows) and vt[h][n][dim][s_pad] (V rows, transposed), 0 beyond cnt
+ *   gf_gemm_tf32_batched  : scores[h][n][l][s_pad] = Q_h Kg_h^T / sqrt(dim)   (tcgen05 kind::tf32)
+ *   gf_masked_softmax_rows: row soft-max over the first anchor_cnt[n] entries, zeros beyond
+ *   gf_gemm_tf32_batched  : out[:, h*dim:(h+1)*dim] = P_h Vt_h^T */
+int gf_gather_anchor_kv(const float* k, int ldk, const float* v, int ldv, int n, int l, int heads, int dim,
+                        const int* anchor_idx, const int* anchor_cnt, int anchor_cap, int s_pad, float* kg, float* vt,
+                        gf_stream_t stream);
+int gf_masked_softmax_rows(float* x, int heads, int n, int l, int s_pad, const int* cnt_per_sample, gf_stream_t stream);
+/* Y[b] = out_scale * A[b] (M x K, row stride lda) * B[b]^T (N x K, row stride ldb); strides in floats */
+int gf_gemm_tf32_batched(const float* A, int64_t lda, int64_t a_batch_stride, const float* B, int64_t ldb,
+                         int64_t b_batch_stride, float* Y, int64_t ldy, int64_t y_batch_stride, int M, int N, int K,
+                         int batches, float out_scale, gf_stream_t stream);
+
 /* cross attention: one query token against its 25-token window of the other image (projected K/V rows
  * kproj/vproj [n, s, heads*dim]); masked entries filled with -1e8, all-masked rows give 0. */
 int gf_geo_cross_attention(const float* q, int ldq, const float* kproj, int ldk, const float* vproj, int ldv,

@@ -24,7 +24,7 @@ def build_model(sd, coarse_thr, backbone="fp32", linear="tf32", sim="f16x3"):
     m.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=True)
     m.backbone_precision = backbone
     m = m.eval().to("cuda:0")
-    ops.set_precision(linear=linear, similarity=sim)
+    ops.set_precision(linear=linear, similarity=sim, attention="ref" if linear == "ref" else "tf32")
     m.capture = True
     m.materialize = True
     return m

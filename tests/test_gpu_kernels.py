@@ -234,7 +234,10 @@ def test_geo_window_table(ops):
     assert (none == -1).all()
 
 
-def test_geo_self_attention(ops):
+@pytest.mark.parametrize("impl,tol", [("ref", 2e-5), ("tf32", 5e-3)])
+def test_geo_self_attention(ops, impl, tol):
+    """'ref': fp32 flash-style kernel; 'tf32': per-head tcgen05 GEMMs (Q K^T, P V) + masked row softmax —
+    tf32 operand rounding on the logits gives ~1e-3 abs error on O(1) outputs."""
     n, l, h, d = 3, 200, 4, 64
     c = h * d
     qkv = rnd(n * l, 3 * c, seed=4)
@@ -245,7 +248,7 @@ def test_geo_self_attention(ops):
         aidx[b, :cnt] = torch.sort(torch.randperm(l, generator=g)[:cnt])[0].int()
     dq = dev(qkv)
     got = ops.geo_self_attention(dq, 3 * c, dq[:, c:], 3 * c, dq[:, 2 * c:], 3 * c, n, l, h, d, dev(aidx),
-                                 dev(torch.tensor(cnts, dtype=torch.int32))).cpu().view(n, l, c)
+                                 dev(torch.tensor(cnts, dtype=torch.int32)), max_cnt=max(cnts), impl=impl).cpu().view(n, l, c)
     x = qkv.view(n, l, 3 * c)
     for b, cnt in enumerate(cnts):
         if cnt == 0:
@@ -256,7 +259,7 @@ def test_geo_self_attention(ops):
         k = x[b, sel, c:2 * c].view(1, cnt, h, d)
         v = x[b, sel, 2 * c:].view(1, cnt, h, d)
         want = O.softmax_attention(q, k, v).view(l, c)
-        assert (got[b] - want).abs().max().item() <= 2e-5
+        assert (got[b] - want).abs().max().item() <= tol
 
 
 def test_geo_cross_attention(ops):
