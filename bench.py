@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--regime", default="dense", choices=["dense", "shift"])
     ap.add_argument("--backbone", default=os.environ.get("GF_BACKBONE", "bf16"))
+    ap.add_argument("--depth", type=int, default=2, help="batches in flight (MatchPipeline); 1 = plain serial forward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stage-times", action="store_true", help="print a per-stage CUDA-event breakdown to stderr")
     return ap.parse_args()
@@ -164,16 +165,21 @@ def run_ours(args):
     host = [(a.pin_memory(), b.pin_memory()) for a, b in host]
     dev = [(a.to(device), b.to(device)) for a, b in host]
 
-    def step_resident(i):
-        a, b = dev[i % pool]
-        d = model({"image0": a, "image1": b})
-        return d
+    from geoformer_b200.pipeline import MatchPipeline
+    pipe = MatchPipeline(model, depth=args.depth, device=device)
 
-    def step_e2e(i):
-        a, b = host[i % pool]
-        d = model({"image0": a.to(device, non_blocking=True), "image1": b.to(device, non_blocking=True)})
-        k0, k1, cf = d["mkpts0_f"].cpu(), d["mkpts1_f"].cpu(), d["mconf"].cpu()      # what match_pairs() reads back
-        return d, k0.numel() * 4 + k1.numel() * 4 + cf.numel() * 4
+    def counts_only(d):            # keep only what the report needs (frees the big per-batch tensors early)
+        return {"b_ids": d["b_ids"].shape[0], "mkpts0_f": d["mkpts0_f"].shape[0]}
+
+    def to_host(d):                # what match_pairs() reads back (geoformer.py:53-54,73)
+        k0, k1, cf = d["mkpts0_f"].cpu(), d["mkpts1_f"].cpu(), d["mconf"].cpu()
+        return counts_only(d), k0.numel() * 4 + k1.numel() * 4 + cf.numel() * 4
+
+    def run_resident(steps):
+        return pipe.run(({"image0": dev[i % pool][0], "image1": dev[i % pool][1]} for i in range(steps)), counts_only)
+
+    def run_e2e(steps):
+        return pipe.run(({"image0": host[i % pool][0], "image1": host[i % pool][1]} for i in range(steps)), to_host)
 
     def barrier():
         if world > 1:
@@ -185,7 +191,7 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.launch_count()
         e0.record()
-        outs = [fn(i) for i in range(steps)]
+        outs = fn(steps)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -195,21 +201,23 @@ def run_ours(args):
             ms = float(t.item())
         return ms, outs, _lib.launch_count() - l0
 
-    for i in range(args.warmup):
-        step_resident(i)
-        step_e2e(i)
+    run_resident(args.warmup)
+    run_e2e(args.warmup)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    ms, outs, launches = timed(run_resident, args.steps)
+    ms_e2e, outs_e2e, _ = timed(run_e2e, args.steps)
+    # dominant-kernel timing: the conf-matrix GEMM, CUDA events on its launching stream, live in this run
     ops.PROFILE.enable("similarity_f16x3")
-    ms, outs, launches = timed(step_resident, args.steps)
-    sim_ms = ops.PROFILE.collect("similarity_f16x3")            # per-launch CUDA-event durations of the conf-matrix GEMM
+    for i in range(2):
+        model({"image0": dev[i % pool][0], "image1": dev[i % pool][1]})
+    sim_ms = ops.PROFILE.collect("similarity_f16x3")
     ops.PROFILE.disable()
-    ms_e2e, outs_e2e, _ = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    mc = float(np.mean([o["b_ids"].shape[0] for o in outs])) / args.batch
-    mf = float(np.mean([o["mkpts0_f"].shape[0] for o in outs])) / args.batch
+    mc = float(np.mean([o["b_ids"] for o in outs])) / args.batch
+    mf = float(np.mean([o["mkpts0_f"] for o in outs])) / args.batch
     d2h = int(np.mean([o[1] for o in outs_e2e]))
     if world > 1:
         # the path's only exchange step: gather match counts / lists (here: counts + last step's list sizes) to all ranks
@@ -246,6 +254,7 @@ def run_ours(args):
             "dtype": "tf32/f16x3 (bf16 cuDNN backbone)" if args.backbone == "bf16" else f"tf32/f16x3 ({args.backbone} backbone)",
             "data": "synthetic",
             "config": workload_config(args, {"matches_coarse_per_pair": mc, "matches_fine_per_pair": mf,
+                                             "batches_in_flight": args.depth,
                                              "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective"}),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * args.batch * H * W * 4, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}

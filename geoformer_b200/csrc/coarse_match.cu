@@ -59,13 +59,16 @@ __global__ void row_stats_kernel(const float* __restrict__ sim, int64_t rows, in
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float* p = sim + row * s;
-  float m = -INFINITY;
-  for (int j = lane; j < s; j += 32) m = fmaxf(m, p[j]);
-  m = warp_max(m);
-  float sum = 0.f;
-  for (int j = lane; j < s; j += 32) sum += expf(p[j] - m);
+  // online (max, sum exp) per lane: a single read of the row; lanes are merged afterwards
+  float m = -INFINITY, sum = 0.f;
+  for (int j = lane; j < s; j += 32) {
+    const float v = p[j];
+    if (v > m) { sum = sum * expf(m - v) + 1.f; m = v; } else { sum += expf(v - m); }
+  }
+  const float mm = warp_max(m);
+  sum = (m > -INFINITY) ? sum * expf(m - mm) : 0.f;
   sum = warp_sum(sum);
-  if (lane == 0) { row_max[row] = m; row_sum[row] = sum; }
+  if (lane == 0) { row_max[row] = mm; row_sum[row] = sum; }
 }
 
 // MODE 0: (max, sum exp(x - max)) per column;  MODE 1: max only
@@ -105,27 +108,47 @@ __global__ void col_stats_kernel(const float* __restrict__ mat, int l, int s, fl
   }
 }
 
-// conf = softmax(sim, dim=1) * softmax(sim, dim=2) in place; per-row max of conf.  One warp per row.
-__global__ void conf_kernel(float* __restrict__ sim, int64_t rows, int l, int s, const float* __restrict__ row_max,
-                            const float* __restrict__ row_sum, const float* __restrict__ col_max,
-                            const float* __restrict__ col_sum, float* __restrict__ conf_row_max) {
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// conf = softmax(sim, dim=1) * softmax(sim, dim=2) in place, plus max of conf per row and per column, in ONE
+// sweep.  CTA = 256 columns x 32 rows; thread == column (coalesced), loops the 32 rows.  Row maxima are merged
+// with warp shuffles + shared atomics, column maxima with one global atomicMax per (column, 32-row strip)
+// (conf >= 0, so the float bit pattern orders like an unsigned integer).
+__global__ void __launch_bounds__(256)
+conf_kernel(float* __restrict__ sim, int l, int s, const float* __restrict__ row_max, const float* __restrict__ row_sum,
+            const float* __restrict__ col_max, const float* __restrict__ col_sum, unsigned* __restrict__ conf_row_max,
+            unsigned* __restrict__ conf_col_max) {
+  __shared__ unsigned rbest[32];
+  __shared__ float rm[32], rinv[32];
+  const int n = blockIdx.z;
+  const int r0 = blockIdx.y * 32;
+  const int col = blockIdx.x * 256 + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const int64_t n = row / l;
-  float* p = sim + row * s;
-  const float* cm = col_max + n * s;
-  const float* cs = col_sum + n * s;
-  const float rm = row_max[row], rs = row_sum[row];
-  float best = 0.f;
-  for (int j = lane; j < s; j += 32) {
-    const float v = p[j];
-    const float c = (expf(v - cm[j]) / cs[j]) * (expf(v - rm) / rs);
-    p[j] = c;
-    best = fmaxf(best, c);
+  if (threadIdx.x < 32) {
+    rbest[threadIdx.x] = 0u;
+    const int r = r0 + threadIdx.x;
+    rm[threadIdx.x] = r < l ? row_max[(int64_t)n * l + r] : 0.f;
+    rinv[threadIdx.x] = r < l ? row_sum[(int64_t)n * l + r] : 1.f;
   }
-  best = warp_max(best);
-  if (lane == 0) conf_row_max[row] = best;
+  __syncthreads();
+  const bool ok = col < s;
+  const float cm = ok ? col_max[(int64_t)n * s + col] : 0.f;
+  const float cs = ok ? col_sum[(int64_t)n * s + col] : 1.f;
+  float* p = sim + ((int64_t)n * l + r0) * s + col;
+  const int rows = min(32, l - r0);
+  float cbest = 0.f;
+  for (int r = 0; r < rows; ++r) {
+    float c = 0.f;
+    if (ok) {
+      const float v = p[(int64_t)r * s];
+      c = (expf(v - cm) / cs) * (expf(v - rm[r]) / rinv[r]);
+      p[(int64_t)r * s] = c;
+      cbest = fmaxf(cbest, c);
+    }
+    const float wbest = warp_max(c);
+    if (lane == 0) atomicMax(&rbest[r], __float_as_uint(wbest));
+  }
+  if (ok) atomicMax(&conf_col_max[(int64_t)n * s + col], __float_as_uint(cbest));
+  __syncthreads();
+  if (threadIdx.x < rows) atomicMax(&conf_row_max[(int64_t)n * l + r0 + threadIdx.x], rbest[threadIdx.x]);
 }
 
 __global__ void row_max_kernel(const float* __restrict__ mat, int64_t rows, int s, float* __restrict__ out) {
@@ -287,10 +310,11 @@ extern "C" int gf_dual_softmax_conf(float* sim_conf, int n, int l, int s, const 
                                     const float* col_max, const float* col_sum, float* conf_row_max,
                                     float* conf_col_max, gf_stream_t stream) {
   if (n <= 0 || l <= 0 || s <= 0) return gf_set_error(GF_ERR_ARG, "gf_dual_softmax_conf: bad shape");
-  const int64_t rows = (int64_t)n * l;
-  conf_kernel<<<gf_cdiv(rows, 8), 256, 0, STREAM>>>(sim_conf, rows, l, s, row_max, row_sum, col_max, col_sum, conf_row_max);
-  col_stats_kernel<1><<<dim3(gf_cdiv(s, 32), n), dim3(32, 32), 0, STREAM>>>(sim_conf, l, s, conf_col_max, nullptr);
-  g_launches += 2;
+  cudaMemsetAsync(conf_row_max, 0, sizeof(float) * (size_t)n * l, STREAM);
+  cudaMemsetAsync(conf_col_max, 0, sizeof(float) * (size_t)n * s, STREAM);
+  conf_kernel<<<dim3(gf_cdiv(s, 256), gf_cdiv(l, 32), n), 256, 0, STREAM>>>(
+      sim_conf, l, s, row_max, row_sum, col_max, col_sum, (unsigned*)conf_row_max, (unsigned*)conf_col_max);
+  g_launches += 1;
   GF_CHECK_LAUNCH();
   return GF_OK;
 }

@@ -18,6 +18,14 @@ static inline int gf_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b);
 
 namespace gf {
 
+// TMA descriptor helpers (gemm_tc.cu).  K-major operand map: dims {k, rows, batches}, box {128 B, box_rows, 1},
+// 128B swizzle, OOB -> 0.  Output map: dims {n, rows, batches} fp32, box {32, 32, 1}, 128B swizzle.
+int make_tmap(CUtensorMap* m, const void* base, int esize, int64_t k, int64_t rows, int64_t batches,
+              int64_t row_stride_elems, int64_t batch_stride_elems, int box_rows);
+int make_out_tmap(CUtensorMap* m, float* base, int64_t n, int64_t rows, int64_t batches, int64_t ld,
+                  int64_t batch_stride);
+int num_sms();
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

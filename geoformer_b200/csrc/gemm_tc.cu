@@ -43,9 +43,9 @@ constexpr int kStageABytes = kBM * 128;
 template <int BN> struct GemmCfg {
   static constexpr int kStageBBytes = BN * 128;
   static constexpr int kStageBytes = kStageABytes + kStageBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256) ? 3 : 5;
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kStagingBytes = 4 * 2 * 4096;   // per epilogue warp: 2 x (32 rows x 128 B) output boxes
+  static constexpr int kStagingBytes = 4 * 4 * 4096;   // per epilogue warp: ring of 4 x (32 rows x 128 B) output boxes
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -154,7 +154,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------ epilogue (warps 2..5) ------------------------------
     const int quad = warp & 3;                           // TMEM lane quadrant this warp may access
     int acc = 0; uint32_t acc_phase = 0;
-    uint32_t chunk_ctr = 0;
+    uint32_t grp = 0;          // TMA-store group counter: 2 boxes per fence / commit, ring of 2 groups per warp
+    int pend = 0;
+    int pend_col[2] = {0, 0};
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int n_blk = t % p.tiles_n;
       const int rest = t / p.tiles_n;
@@ -169,7 +171,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const float* rrow = p.residual ? p.residual + (int64_t)row * p.ldres : nullptr;
       const float* rb = p.rowbias ? p.rowbias + (int64_t)(row / p.rowbias_group) * p.N : nullptr;
       const int col0 = n_blk * BN;
-      uint8_t* wstage = staging + (warp - 2) * 8192;     // this warp's two 4 KB boxes
+      uint8_t* wstage = staging + (warp - 2) * 16384;    // this warp's four 4 KB boxes
       // residual tile slice of this lane for one 32x32 chunk: 8 coalesced float4 (4 rows x 128 B per instruction);
       // software-pipelined one chunk ahead so that the global-load latency hides behind the previous chunk
       float4 rnext[8];
@@ -210,11 +212,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int c = 0; c < BN; c += 32) {
         const int gc = col0 + c;
         if (gc >= p.N) break;                              // column tail of the last tile (warp-uniform)
-        uint8_t* box = wstage + (chunk_ctr & 1) * 4096;
-        ++chunk_ctr;
+        uint8_t* box = wstage + ((grp & 1) * 2 + pend) * 4096;
         if (p.tma_store) {
-          if (lane == 0) ptx::bulk_wait_read<1>();         // the store issued 2 chunks ago no longer reads this box
-          __syncwarp();
+          if (pend == 0) {
+            if (lane == 0) ptx::bulk_wait_read<1>();       // the group issued 2 groups ago no longer reads these boxes
+            __syncwarp();
+          }
           if (stage_res) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
@@ -295,11 +298,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.residual) { const float4 r4 = *dst; o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
             *dst = o;
           }
-          ptx::fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            ptx::tma_store_3d(&tmY, box, gc, m_blk * kBM + quad * 32, batch);
-            ptx::bulk_commit();
+          pend_col[pend++] = gc;
+          const bool last = (c + 32 >= BN) || (gc + 32 >= p.N);
+          if (pend == 2 || last) {                         // one proxy fence + commit per two boxes
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              uint8_t* gbase = wstage + (grp & 1) * 8192;
+              for (int i = 0; i < pend; ++i)
+                ptx::tma_store_3d(&tmY, gbase + i * 4096, pend_col[i], m_blk * kBM + quad * 32, batch);
+              ptx::bulk_commit();
+            }
+            pend = 0;
+            ++grp;
           }
         } else if (row_ok) {
           for (int j = 0; j < 32; ++j) if (gc + j < p.N) yrow[gc + j] = v[j];
@@ -347,7 +358,7 @@ int init_driver(int device) {
 int num_sms() { return g_num_sms; }
 
 // 3-D K-major operand map: dims {K, rows, batches}; box {128 bytes of K, box_rows, 1}; 128B swizzle; OOB -> 0
-static int make_tmap(CUtensorMap* m, const void* base, int esize, int64_t k, int64_t rows, int64_t batches,
+int make_tmap(CUtensorMap* m, const void* base, int esize, int64_t k, int64_t rows, int64_t batches,
                      int64_t row_stride_elems, int64_t batch_stride_elems, int box_rows) {
   if (!g_encode) return gf_set_error(GF_ERR_DRIVER, "gf_init() was not called");
   cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, (cuuint64_t)batches};
@@ -363,7 +374,7 @@ static int make_tmap(CUtensorMap* m, const void* base, int esize, int64_t k, int
 }
 
 // output map: dims {N, M, batches} fp32, box {32 cols, 32 rows, 1}, 128B swizzle (matches the epilogue staging)
-static int make_out_tmap(CUtensorMap* m, float* base, int64_t n, int64_t rows, int64_t batches, int64_t ld,
+int make_out_tmap(CUtensorMap* m, float* base, int64_t n, int64_t rows, int64_t batches, int64_t ld,
                          int64_t batch_stride) {
   if (!g_encode) return gf_set_error(GF_ERR_DRIVER, "gf_init() was not called");
   cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)rows, (cuuint64_t)batches};

@@ -254,6 +254,8 @@ __global__ void gather_anchor_kv_kernel(const float* __restrict__ k, int ldk, co
 }
 
 // rows of [heads][n][l][s_pad]: p = softmax(x[0:cnt]) (x is already scaled), zeros beyond cnt.  One warp per row.
+// PER_LANE > 0: the whole row (s_pad <= 32 * PER_LANE) lives in registers -> one read and one write of the block.
+template <int PER_LANE>
 __global__ void masked_softmax_rows_kernel(float* __restrict__ x, int64_t rows, int n, int l, int s_pad,
                                            const int* __restrict__ cnt_per_sample) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -262,14 +264,36 @@ __global__ void masked_softmax_rows_kernel(float* __restrict__ x, int64_t rows, 
   const int b = (int)((row / l) % n);
   const int cnt = cnt_per_sample[b];
   float* p = x + row * s_pad;
-  float m = -INFINITY;
-  for (int j = lane; j < cnt; j += 32) m = fmaxf(m, p[j]);
-  m = warp_max(m);
-  float sum = 0.f;
-  for (int j = lane; j < cnt; j += 32) sum += expf(p[j] - m);
-  sum = warp_sum(sum);
-  const float inv = cnt > 0 ? 1.f / sum : 0.f;
-  for (int j = lane; j < s_pad; j += 32) p[j] = j < cnt ? expf(p[j] - m) * inv : 0.f;
+  if constexpr (PER_LANE > 0) {
+    float v[PER_LANE];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) {
+      const int j = lane + 32 * i;
+      v[i] = j < cnt ? p[j] : -INFINITY;
+      m = fmaxf(m, v[i]);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) { v[i] = (lane + 32 * i < cnt) ? expf(v[i] - m) : 0.f; sum += v[i]; }
+    sum = warp_sum(sum);
+    const float inv = cnt > 0 ? 1.f / sum : 0.f;
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) {
+      const int j = lane + 32 * i;
+      if (j < s_pad) p[j] = v[i] * inv;
+    }
+  } else {
+    float m = -INFINITY;
+    for (int j = lane; j < cnt; j += 32) m = fmaxf(m, p[j]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int j = lane; j < cnt; j += 32) sum += expf(p[j] - m);
+    sum = warp_sum(sum);
+    const float inv = cnt > 0 ? 1.f / sum : 0.f;
+    for (int j = lane; j < s_pad; j += 32) p[j] = j < cnt ? expf(p[j] - m) * inv : 0.f;
+  }
 }
 
 }  // namespace gf
@@ -331,7 +355,10 @@ extern "C" int gf_masked_softmax_rows(float* x, int heads, int n, int l, int s_p
                                       gf_stream_t stream) {
   if (heads <= 0 || n <= 0 || l <= 0 || s_pad <= 0) return gf_set_error(GF_ERR_ARG, "gf_masked_softmax_rows: bad shape");
   const int64_t rows = (int64_t)heads * n * l;
-  masked_softmax_rows_kernel<<<gf_cdiv(rows, 8), 256, 0, STREAM>>>(x, rows, n, l, s_pad, cnt_per_sample);
+  if (s_pad <= 512)       masked_softmax_rows_kernel<16><<<gf_cdiv(rows, 8), 256, 0, STREAM>>>(x, rows, n, l, s_pad, cnt_per_sample);
+  else if (s_pad <= 1024) masked_softmax_rows_kernel<32><<<gf_cdiv(rows, 8), 256, 0, STREAM>>>(x, rows, n, l, s_pad, cnt_per_sample);
+  else if (s_pad <= 2048) masked_softmax_rows_kernel<64><<<gf_cdiv(rows, 8), 256, 0, STREAM>>>(x, rows, n, l, s_pad, cnt_per_sample);
+  else                    masked_softmax_rows_kernel<0><<<gf_cdiv(rows, 8), 256, 0, STREAM>>>(x, rows, n, l, s_pad, cnt_per_sample);
   g_launches++;
   GF_CHECK_LAUNCH();
   return GF_OK;

@@ -9,143 +9,196 @@ extern std::atomic<int64_t> g_launches;
 
 constexpr int kChunk = 256;   // source tokens per partial reduction block
 
-// partial[(n,h,chunk)][D*D + D]: KV block then Ksum
+// ---------------------------------------------------------------------------------------------
+// reduce, stage 1.  One CTA per (256-token chunk, sample); warp w == head w (blockDim = 32 * heads).
+// Lane v owns column v of the head's dim x dim block: acc[d] += K[s,h,d] * V[s,h,v] with K broadcast
+// from shared memory as float4 (dim/4 LDS.128 + 1 LDS per dim FMAs).  dim == 32.
+// partial[(n, chunk, h)][dim*dim + dim]: KV block (row d, col v) then Ksum.
+// ---------------------------------------------------------------------------------------------
+template <int D>
 __global__ void linattn_partial_kernel(const float* __restrict__ K, int ldk, const float* __restrict__ V, int ldv,
-                                       int s, int heads, int dim, float inv_s, float* __restrict__ partial) {
+                                       int s, int heads, float inv_s, float* __restrict__ partial) {
   extern __shared__ float sh[];
-  float* Ks = sh;                    // [64][dim]
-  float* Vs = sh + 64 * dim;         // [64][dim]
-  const int chunk = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+  const int c = heads * D;
+  float* Ks = sh;                 // [32 tokens][c]
+  float* Vs = sh + 32 * c;        // [32 tokens][c]
+  const int chunk = blockIdx.x, n = blockIdx.y;
   const int nchunks = gridDim.x;
-  const int entries = dim * dim;
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s0 = chunk * kChunk, s1 = min(s, s0 + kChunk);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};   // up to 4 entries per thread (dim <= 32 with 256 threads)
+  float acc[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) acc[d] = 0.f;
   float ksum = 0.f;
-  for (int t0 = s0; t0 < s1; t0 += 64) {
-    const int cnt = min(64, s1 - t0);
-    for (int e = threadIdx.x; e < 64 * dim; e += blockDim.x) {
-      const int r = e / dim, d = e - r * dim;
-      float kv = 0.f, vv = 0.f;
+  for (int t0 = s0; t0 < s1; t0 += 32) {
+    const int cnt = min(32, s1 - t0);
+    for (int e = threadIdx.x; e < 32 * (c / 4); e += blockDim.x) {
+      const int r = e / (c / 4), q = e - r * (c / 4);
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
       if (r < cnt) {
         const int64_t tok = (int64_t)n * s + t0 + r;
-        kv = K[tok * ldk + h * dim + d];
-        vv = V[tok * ldv + h * dim + d] * inv_s;   // values / v_length (linear_attention.py:46)
+        kv = *reinterpret_cast<const float4*>(K + tok * ldk + 4 * q);
+        vv = *reinterpret_cast<const float4*>(V + tok * ldv + 4 * q);
+        vv.x *= inv_s; vv.y *= inv_s; vv.z *= inv_s; vv.w *= inv_s;      // values / v_length (linear_attention.py:46)
       }
-      Ks[e] = kv; Vs[e] = vv;
+      *reinterpret_cast<float4*>(Ks + r * c + 4 * q) = kv;
+      *reinterpret_cast<float4*>(Vs + r * c + 4 * q) = vv;
     }
     __syncthreads();
+    if (lane < D) {
+      for (int r = 0; r < cnt; ++r) {
+        const float vv = Vs[r * c + h * D + lane];
+        ksum += Ks[r * c + h * D + lane];
+        const float4* kr = reinterpret_cast<const float4*>(Ks + r * c + h * D);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int e = threadIdx.x + q * blockDim.x;
-      if (e < entries) {
-        const int d = e / dim, v = e - d * dim;
-        float a = acc[q];
-        for (int r = 0; r < cnt; ++r) a = fmaf(Ks[r * dim + d], Vs[r * dim + v], a);
-        acc[q] = a;
+        for (int q = 0; q < D / 4; ++q) {
+          const float4 k4 = kr[q];
+          acc[4 * q] = fmaf(k4.x, vv, acc[4 * q]); acc[4 * q + 1] = fmaf(k4.y, vv, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(k4.z, vv, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(k4.w, vv, acc[4 * q + 3]);
+        }
       }
-    }
-    if (threadIdx.x < dim) {
-      float a = ksum;
-      for (int r = 0; r < cnt; ++r) a += Ks[r * dim + threadIdx.x];
-      ksum = a;
     }
     __syncthreads();
   }
-  float* out = partial + ((int64_t)(n * heads + h) * nchunks + chunk) * (entries + dim);
+  if (lane < D) {
+    float* out = partial + (((int64_t)n * nchunks + chunk) * heads + h) * (D * D + D);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int e = threadIdx.x + q * blockDim.x;
-    if (e < entries) out[e] = acc[q];
+    for (int d = 0; d < D; ++d) out[d * D + lane] = acc[d];
+    out[D * D + lane] = ksum;
   }
-  if (threadIdx.x < dim) out[entries + threadIdx.x] = ksum;
 }
 
-__global__ void linattn_finalize_kernel(const float* __restrict__ partial, int nchunks, int dim, float* __restrict__ KV,
-                                        float* __restrict__ Ksum) {
-  const int nh = blockIdx.x;
+__global__ void linattn_finalize_kernel(const float* __restrict__ partial, int nchunks, int heads, int dim,
+                                        float* __restrict__ KV, float* __restrict__ Ksum) {
+  const int n = blockIdx.x / heads, h = blockIdx.x % heads;
   const int entries = dim * dim;
   for (int e = threadIdx.x; e < entries + dim; e += blockDim.x) {
     float a = 0.f;
-    for (int c = 0; c < nchunks; ++c) a += partial[((int64_t)nh * nchunks + c) * (entries + dim) + e];
-    if (e < entries) KV[(int64_t)nh * entries + e] = a; else Ksum[(int64_t)nh * dim + (e - entries)] = a;
+    for (int c = 0; c < nchunks; ++c) a += partial[(((int64_t)n * nchunks + c) * heads + h) * (entries + dim) + e];
+    if (e < entries) KV[((int64_t)n * heads + h) * entries + e] = a;
+    else Ksum[((int64_t)n * heads + h) * dim + (e - entries)] = a;
   }
 }
 
-// out[n,l,h,v] = (sum_d Q[l,h,d] KV[h,d,v]) * (1 / (Q[l,h,:].Ksum[h,:] + eps)) * S      blockDim = heads*dim
+// ---------------------------------------------------------------------------------------------
+// apply.  out[n,l,h,v] = (sum_d Q[l,h,d] KV[h,d,v]) * (1 / (Q[l,h,:].Ksum[h,:] + eps)) * S
+// blockDim = heads*dim (thread == output channel); the thread keeps its KV column and the head's Ksum in
+// registers; 128 tokens per CTA, Q rows staged in shared memory and read as broadcast float4.
+// ---------------------------------------------------------------------------------------------
+template <int D>
 __global__ void linattn_apply_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ KV,
-                                     const float* __restrict__ Ksum, float* __restrict__ out, int l, int heads, int dim,
+                                     const float* __restrict__ Ksum, float* __restrict__ out, int l, int heads,
                                      float s_len) {
   extern __shared__ float sh[];
-  const int c = heads * dim;
-  float* kv = sh;                       // [heads][dim][dim]
-  float* ks = kv + heads * dim * dim;   // [c]
-  float* qs = ks + c;                   // [32][c]
+  const int c = heads * D;
+  float* qs = sh;                       // [32][c]
   const int n = blockIdx.y;
-  const int l0 = blockIdx.x * 32;
   const int t = threadIdx.x;
-  for (int e = t; e < heads * dim * dim; e += blockDim.x) kv[e] = KV[(int64_t)n * heads * dim * dim + e];
-  ks[t] = Ksum[(int64_t)n * c + t];
-  const int cnt = min(32, l - l0);
-  for (int r = 0; r < cnt; ++r) qs[r * c + t] = Q[((int64_t)n * l + l0 + r) * ldq + t];
-  __syncthreads();
-  const int h = t / dim, v = t - h * dim;
-  const float* kvh = kv + h * dim * dim;
-  for (int r = 0; r < cnt; ++r) {
-    const float* q = qs + r * c + h * dim;
-    float num = 0.f, den = 0.f;
-    for (int d = 0; d < dim; ++d) {
-      const float qd = q[d];
-      num = fmaf(qd, kvh[d * dim + v], num);
-      den = fmaf(qd, ks[h * dim + d], den);
+  const int h = t / D, v = t - h * D;
+  float kvcol[D], ks[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    kvcol[d] = KV[(((int64_t)n * heads + h) * D + d) * D + v];
+    ks[d] = Ksum[((int64_t)n * heads + h) * D + d];
+  }
+  const int l_begin = blockIdx.x * 128, l_end = min(l, l_begin + 128);
+  for (int l0 = l_begin; l0 < l_end; l0 += 32) {
+    const int cnt = min(32, l_end - l0);
+    __syncthreads();
+    for (int e = t; e < 32 * (c / 4); e += blockDim.x) {
+      const int r = e / (c / 4), q = e - r * (c / 4);
+      float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < cnt) qv = *reinterpret_cast<const float4*>(Q + ((int64_t)n * l + l0 + r) * ldq + 4 * q);
+      *reinterpret_cast<float4*>(qs + r * c + 4 * q) = qv;
     }
-    const float z = 1.f / (den + 1e-6f);
-    out[((int64_t)n * l + l0 + r) * c + t] = num * z * s_len;
+    __syncthreads();
+    for (int r = 0; r < cnt; ++r) {
+      const float4* qr = reinterpret_cast<const float4*>(qs + r * c + h * D);
+      float num = 0.f, den = 0.f;
+#pragma unroll
+      for (int q = 0; q < D / 4; ++q) {
+        const float4 q4 = qr[q];
+        num = fmaf(q4.x, kvcol[4 * q], num); den = fmaf(q4.x, ks[4 * q], den);
+        num = fmaf(q4.y, kvcol[4 * q + 1], num); den = fmaf(q4.y, ks[4 * q + 1], den);
+        num = fmaf(q4.z, kvcol[4 * q + 2], num); den = fmaf(q4.z, ks[4 * q + 2], den);
+        num = fmaf(q4.w, kvcol[4 * q + 3], num); den = fmaf(q4.w, ks[4 * q + 3], den);
+      }
+      out[((int64_t)n * l + l0 + r) * c + t] = num * (1.f / (den + 1e-6f)) * s_len;
+    }
   }
 }
 
-// Fine-level: one CTA per 25-token window; blockDim = heads*dim (=128).  Both phases fused.
+// ---------------------------------------------------------------------------------------------
+// Fine level: one CTA per 25-token window; blockDim = heads*dim (=128), dim == 16.  Both phases fused;
+// K / Q rows are read from shared memory as broadcast float4.
+// ---------------------------------------------------------------------------------------------
+template <int D, int TOK>
 __global__ void linattn_window_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ K, int ldk,
-                                      const float* __restrict__ V, int ldv, float* __restrict__ out, int tokens,
-                                      int heads, int dim) {
+                                      const float* __restrict__ V, int ldv, float* __restrict__ out, int tokens_rt,
+                                      int heads) {
+  const int tokens = TOK > 0 ? TOK : tokens_rt;     // compile-time token count -> fully unrolled, 3*TOK loads in flight
   extern __shared__ float sh[];
-  const int c = heads * dim;
+  const int c = heads * D;
   float* qs = sh;                  // [tokens][c]
   float* ks = qs + tokens * c;
   float* vs = ks + tokens * c;
   float* ksum = vs + tokens * c;   // [c]
   const int64_t w = blockIdx.x;
   const int t = threadIdx.x;
-  const float inv_s = 1.f / (float)tokens;
-  for (int r = 0; r < tokens; ++r) {
-    const int64_t row = w * tokens + r;
-    qs[r * c + t] = Q[row * ldq + t];
-    ks[r * c + t] = K[row * ldk + t];
-    vs[r * c + t] = V[row * ldv + t] / (float)tokens;
-  }
-  (void)inv_s;
+  const float ftok = (float)tokens;
   float a = 0.f;
-  for (int r = 0; r < tokens; ++r) a += ks[r * c + t];
+  if constexpr (TOK > 0) {
+    float qr[TOK], kr[TOK], vr[TOK];
+#pragma unroll
+    for (int r = 0; r < TOK; ++r) {
+      const int64_t row = w * TOK + r;
+      qr[r] = __ldg(Q + row * ldq + t); kr[r] = __ldg(K + row * ldk + t); vr[r] = __ldg(V + row * ldv + t);
+    }
+#pragma unroll
+    for (int r = 0; r < TOK; ++r) {
+      qs[r * c + t] = qr[r]; ks[r * c + t] = kr[r]; a += kr[r]; vs[r * c + t] = vr[r] / ftok;
+    }
+  } else {
+    for (int r = 0; r < tokens; ++r) {
+      const int64_t row = w * tokens + r;
+      qs[r * c + t] = Q[row * ldq + t];
+      const float kk = K[row * ldk + t];
+      ks[r * c + t] = kk;
+      a += kk;
+      vs[r * c + t] = V[row * ldv + t] / ftok;
+    }
+  }
   ksum[t] = a;
   __syncthreads();
-  const int h = t / dim, v = t - h * dim;
-  // KV[h, d, v] for this thread's (h, v): dim values kept in registers (dim <= 16 at the fine level)
-  float kvcol[16];
+  const int h = t / D;
+  float kvcol[D];
 #pragma unroll
-  for (int d = 0; d < 16; ++d) kvcol[d] = 0.f;
+  for (int d = 0; d < D; ++d) kvcol[d] = 0.f;
   for (int r = 0; r < tokens; ++r) {
     const float vv = vs[r * c + t];
+    const float4* kr = reinterpret_cast<const float4*>(ks + r * c + h * D);
 #pragma unroll
-    for (int d = 0; d < 16; ++d) if (d < dim) kvcol[d] = fmaf(ks[r * c + h * dim + d], vv, kvcol[d]);
+    for (int q = 0; q < D / 4; ++q) {
+      const float4 k4 = kr[q];
+      kvcol[4 * q] = fmaf(k4.x, vv, kvcol[4 * q]); kvcol[4 * q + 1] = fmaf(k4.y, vv, kvcol[4 * q + 1]);
+      kvcol[4 * q + 2] = fmaf(k4.z, vv, kvcol[4 * q + 2]); kvcol[4 * q + 3] = fmaf(k4.w, vv, kvcol[4 * q + 3]);
+    }
   }
+  float ksr[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) ksr[d] = ksum[h * D + d];
   for (int r = 0; r < tokens; ++r) {
+    const float4* qr = reinterpret_cast<const float4*>(qs + r * c + h * D);
     float num = 0.f, den = 0.f;
 #pragma unroll
-    for (int d = 0; d < 16; ++d) if (d < dim) {
-      const float qd = qs[r * c + h * dim + d];
-      num = fmaf(qd, kvcol[d], num);
-      den = fmaf(qd, ksum[h * dim + d], den);
+    for (int q = 0; q < D / 4; ++q) {
+      const float4 q4 = qr[q];
+      num = fmaf(q4.x, kvcol[4 * q], num); den = fmaf(q4.x, ksr[4 * q], den);
+      num = fmaf(q4.y, kvcol[4 * q + 1], num); den = fmaf(q4.y, ksr[4 * q + 1], den);
+      num = fmaf(q4.z, kvcol[4 * q + 2], num); den = fmaf(q4.z, ksr[4 * q + 2], den);
+      num = fmaf(q4.w, kvcol[4 * q + 3], num); den = fmaf(q4.w, ksr[4 * q + 3], den);
     }
-    out[(w * tokens + r) * c + t] = num * (1.f / (den + 1e-6f)) * (float)tokens;
+    out[(w * tokens + r) * c + t] = num * (1.f / (den + 1e-6f)) * ftok;
   }
 }
 
@@ -186,11 +239,15 @@ extern "C" int64_t gf_linattn_partial_floats(int n, int s, int heads, int dim) {
 
 extern "C" int gf_linattn_reduce(const float* K, int ldk, const float* V, int ldv, int n, int s, int heads, int dim,
                                  float* partial, float* KV, float* Ksum, gf_stream_t stream) {
-  if (n <= 0 || s <= 0 || heads <= 0 || dim <= 0 || dim > 32) return gf_set_error(GF_ERR_ARG, "gf_linattn_reduce: dim must be <= 32");
+  if (n <= 0 || s <= 0 || heads <= 0 || heads > 32 || dim != 32 || (ldk % 4) || (ldv % 4))
+    return gf_set_error(GF_ERR_ARG, "gf_linattn_reduce: dim must be 32, heads <= 32, 16-byte aligned rows");
   const int nchunks = gf_cdiv(s, kChunk);
-  const size_t smem = 2 * 64 * dim * sizeof(float);
-  linattn_partial_kernel<<<dim3(nchunks, heads, n), 256, smem, STREAM>>>(K, ldk, V, ldv, s, heads, dim, 1.f / (float)s, partial);
-  linattn_finalize_kernel<<<n * heads, 256, 0, STREAM>>>(partial, nchunks, dim, KV, Ksum);
+  const size_t smem = (size_t)2 * 32 * heads * dim * sizeof(float);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(linattn_partial_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+  if (smem > 96 * 1024) return gf_set_error(GF_ERR_ARG, "gf_linattn_reduce: shared memory");
+  linattn_partial_kernel<32><<<dim3(nchunks, n), 32 * heads, smem, STREAM>>>(K, ldk, V, ldv, s, heads, 1.f / (float)s, partial);
+  linattn_finalize_kernel<<<n * heads, 256, 0, STREAM>>>(partial, nchunks, heads, dim, KV, Ksum);
   g_launches += 2;
   GF_CHECK_LAUNCH();
   return GF_OK;
@@ -199,12 +256,9 @@ extern "C" int gf_linattn_reduce(const float* K, int ldk, const float* V, int ld
 extern "C" int gf_linattn_apply(const float* Q, int ldq, const float* KV, const float* Ksum, float* out, int n, int l,
                                 int s, int heads, int dim, gf_stream_t stream) {
   const int c = heads * dim;
-  if (n <= 0 || l <= 0 || c > 1024 || (c % 32)) return gf_set_error(GF_ERR_ARG, "gf_linattn_apply: bad shape");
-  const size_t smem = (size_t)(heads * dim * dim + c + 32 * c) * sizeof(float);
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(linattn_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
-  if (smem > 96 * 1024) return gf_set_error(GF_ERR_ARG, "gf_linattn_apply: shared memory");
-  linattn_apply_kernel<<<dim3(gf_cdiv(l, 32), n), c, smem, STREAM>>>(Q, ldq, KV, Ksum, out, l, heads, dim, (float)s);
+  if (n <= 0 || l <= 0 || c > 1024 || dim != 32 || (ldq % 4)) return gf_set_error(GF_ERR_ARG, "gf_linattn_apply: dim must be 32");
+  const size_t smem = (size_t)32 * c * sizeof(float);
+  linattn_apply_kernel<32><<<dim3(gf_cdiv(l, 128), n), c, smem, STREAM>>>(Q, ldq, KV, Ksum, out, l, heads, (float)s);
   g_launches++;
   GF_CHECK_LAUNCH();
   return GF_OK;
@@ -213,14 +267,19 @@ extern "C" int gf_linattn_apply(const float* Q, int ldq, const float* KV, const 
 extern "C" int gf_linattn_window(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, float* out,
                                  int64_t n_windows, int tokens, int heads, int dim, gf_stream_t stream) {
   const int c = heads * dim;
-  if (n_windows < 0 || tokens <= 0 || tokens > 64 || dim > 16 || c > 1024 || (c % 32))
-    return gf_set_error(GF_ERR_ARG, "gf_linattn_window: bad shape");
+  if (n_windows < 0 || tokens <= 0 || tokens > 64 || dim != 16 || c > 1024 || (c % 32))
+    return gf_set_error(GF_ERR_ARG, "gf_linattn_window: dim must be 16");
   if (n_windows == 0) return GF_OK;
   const size_t smem = (size_t)(3 * tokens * c + c) * sizeof(float);
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(linattn_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+  if (!attr) {
+    cudaFuncSetAttribute(linattn_window_kernel<16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(linattn_window_kernel<16, 25>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr = true;
+  }
   if (smem > 96 * 1024) return gf_set_error(GF_ERR_ARG, "gf_linattn_window: shared memory");
-  linattn_window_kernel<<<(unsigned)n_windows, c, smem, STREAM>>>(Q, ldq, K, ldk, V, ldv, out, tokens, heads, dim);
+  if (tokens == 25) linattn_window_kernel<16, 25><<<(unsigned)n_windows, c, smem, STREAM>>>(Q, ldq, K, ldk, V, ldv, out, tokens, heads);
+  else              linattn_window_kernel<16, 0><<<(unsigned)n_windows, c, smem, STREAM>>>(Q, ldq, K, ldk, V, ldv, out, tokens, heads);
   g_launches++;
   GF_CHECK_LAUNCH();
   return GF_OK;

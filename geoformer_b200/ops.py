@@ -24,7 +24,7 @@ def set_precision(linear: Optional[str] = None, similarity: Optional[str] = None
                   attention: Optional[str] = None) -> None:
     global _LINEAR_IMPL, _SIM_IMPL, _ATTN_IMPL
     if attention is not None:
-        assert attention in ("tf32", "ref")
+        assert attention in ("tf32", "tf32_mat", "ref")
         _ATTN_IMPL = attention
     if linear is not None:
         assert linear in ("tf32", "ref")
@@ -251,14 +251,19 @@ def geo_self_attention(q, ldq, k, ldk, v, ldv, n, l, heads, dim, anchor_idx, anc
     'tf32': per-head tcgen05 GEMMs over materialised score blocks; 'ref': fp32 flash-style FFMA kernel."""
     c = heads * dim
     out = torch.empty((n * l, c), device=q.device, dtype=torch.float32)
-    if (impl or _ATTN_IMPL) == "tf32" and max_cnt > 0:
-        s_pad = (max_cnt + 31) // 32 * 32
+    mode = impl or _ATTN_IMPL
+    if mode in ("tf32", "tf32_mat") and max_cnt > 0:
+        s_pad = (max_cnt + 63) // 64 * 64
         dev = q.device
         kg = torch.empty((heads, n, s_pad, dim), device=dev, dtype=torch.float32)
         vt = torch.empty((heads, n, dim, s_pad), device=dev, dtype=torch.float32)
-        sc = torch.empty((heads, n, l, s_pad), device=dev, dtype=torch.float32)
         _call("gf_gather_anchor_kv", k.data_ptr(), ldk, v.data_ptr(), ldv, n, l, heads, dim, anchor_idx.data_ptr(),
               anchor_cnt.data_ptr(), anchor_idx.shape[1], s_pad, kg.data_ptr(), vt.data_ptr(), _stream())
+        if mode == "tf32":           # fused flash-style tcgen05 kernel: scores never leave the SM
+            _call("gf_geo_self_attention_tc", q.data_ptr(), ldq, kg.data_ptr(), vt.data_ptr(), out.data_ptr(), n, l,
+                  heads, dim, s_pad, anchor_cnt.data_ptr(), _stream())
+            return out
+        sc = torch.empty((heads, n, l, s_pad), device=dev, dtype=torch.float32)
         for h in range(heads):
             _call("gf_gemm_tf32_batched", q.data_ptr() + 4 * h * dim, ldq, l * ldq, kg[h].data_ptr(), dim, s_pad * dim,
                   sc[h].data_ptr(), s_pad, l * s_pad, l, s_pad, dim, n, 1.0 / dim ** 0.5, _stream(), tag="[QK]")
