@@ -219,11 +219,18 @@ def run_ours(args):
     mc = float(np.mean([o["b_ids"] for o in outs])) / args.batch
     mf = float(np.mean([o["mkpts0_f"] for o in outs])) / args.batch
     d2h = int(np.mean([o[1] for o in outs_e2e]))
-    if world > 1:
-        # the path's only exchange step: gather match counts / lists (here: counts + last step's list sizes) to all ranks
-        t = torch.tensor([mc, mf], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        mc, mf = (t / world).tolist()
+    # the path's only exchange step (outside the per-step loop): gather one batch's match lists + metric sums
+    from geoformer_b200.dist import gather_match_lists, reduce_sums
+    d = model({"image0": dev[0][0], "image1": dev[0][1]})
+    lists = torch.cat([d["mkpts0_f"], d["mkpts1_f"], d["mconf"][:, None]], 1)
+    pair_ids = d["m_bids"] * world + rank
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    allm, allid = gather_match_lists(lists, pair_ids)
+    mc, mf = [v / world for v in reduce_sums([mc, mf], device)]
+    torch.cuda.synchronize()
+    exchange_ms = 1e3 * (time.perf_counter() - t0)
+    gathered = int(allm.shape[0])
     if args.stage_times and rank == 0:
         stage_breakdown(model, dev[0])
     if rank != 0:
@@ -254,7 +261,8 @@ def run_ours(args):
             "dtype": "tf32/f16x3 (bf16 cuDNN backbone)" if args.backbone == "bf16" else f"tf32/f16x3 ({args.backbone} backbone)",
             "data": "synthetic",
             "config": workload_config(args, {"matches_coarse_per_pair": mc, "matches_fine_per_pair": mf,
-                                             "batches_in_flight": args.depth,
+                                             "batches_in_flight": args.depth, "exchange_ms_per_batch_gather": exchange_ms,
+                                             "gathered_matches": gathered,
                                              "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective"}),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * args.batch * H * W * 4, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
