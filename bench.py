@@ -258,7 +258,8 @@ def run_ours(args):
             "avg_launch_ms": sim_avg_ms, "launches_timed": len(sim_ms), "traffic": None}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32/f16x3 (bf16 cuDNN backbone)" if args.backbone == "bf16" else f"tf32/f16x3 ({args.backbone} backbone)",
+            "dtype": "tf32 projections/attention, split-f16 similarity, bf16 backbone" if args.backbone == "bf16"
+                     else f"tf32 projections/attention, split-f16 similarity, {args.backbone} backbone",
             "data": "synthetic",
             "config": workload_config(args, {"matches_coarse_per_pair": mc, "matches_fine_per_pair": mf,
                                              "batches_in_flight": args.depth, "exchange_ms_per_batch_gather": exchange_ms,

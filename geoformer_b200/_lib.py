@@ -21,6 +21,8 @@ SIGNATURES = {
     "gf_launch_count": (L, []),
     "gf_linear_tf32": (I, [P, P, P, P, L, I, I, I, I, I, P, P, I, P, P, P, P, P]),
     "gf_linear_ref": (I, [P, P, P, P, L, I, I, I, I, I, P, P, I, P, P, P, P, P]),
+    "gf_conv3x3_bf16": (I, [P, P, P, P, P, I, I, I, I, I, I, I, P]),
+    "gf_upsample_add_bf16": (I, [P, P, P, I, I, I, I, I, I, P]),
     "gf_add_posenc": (I, [P, P, P, I, L, I, P]),
     "gf_linattn_partial_floats": (L, [I, I, I, I]),
     "gf_linattn_reduce": (I, [P, I, P, I, I, I, I, I, P, P, P, P]),

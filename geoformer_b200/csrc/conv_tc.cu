@@ -1,0 +1,333 @@
+// 3x3 / stride-1 / pad-1 convolution as a tcgen05 implicit GEMM (backbone: resnet_fpn.py:32-40, 70-82, 100-118;
+// SURVEY.md §8f rank 1).  NHWC bf16 activations, BN folded into weights + bias.
+//
+//   Y[b,y,x,co] = act( bias[co] + sum_{dy,dx,ci} X[b,y+dy-1,x+dx-1,ci] * W[co,dy,dx,ci]  (+ R[b,y,x,co]) )
+//
+// GEMM view: M = 128 output pixels (an 8 x 16 patch), N = all output channels (128 / 208 / 256), K = 9 taps x Cin.
+// The im2col never exists: for tap (dy,dx) and 64-channel block cb the A tile is ONE 4-D TMA box
+// {64 ch, 16 px, 8 rows, 1} at (cb*64, x0+dx-1, y0+dy-1, b); TMA zero-fills the padding halo and the channel tail,
+// and lands the box as 128 rows x 128 B with the 128B swizzle == a K-major UMMA operand.
+// Same warp-specialised persistent structure as gemm_tc.cu (TMA producer / single-thread MMA issuer / 4 epilogue
+// warps, double-buffered TMEM accumulator); epilogue fuses bias, residual add, ReLU / LeakyReLU, bf16 pack and
+// writes 4-D TMA boxes {64 ch, 16 px, 2 rows}.
+#include "common.cuh"
+#include "ptx.cuh"
+
+#include <atomic>
+#include <cuda_bf16.h>
+
+namespace gf {
+extern std::atomic<int64_t> g_launches;
+
+struct ConvParams {
+  const float* bias;                 // [cout_p] fp32
+  const __nv_bfloat16* residual;     // NHWC [b,h,w,cout_p] or null
+  int batch, h, w, cout_p;
+  int kbc;                           // 64-channel k-blocks per tap
+  int tiles_x, tiles_y;
+  int act;                           // 0 none, 1 relu, 2 leaky relu (0.01)
+};
+
+template <int BN> struct ConvCfg {
+  static constexpr int kStageA = 128 * 128;
+  static constexpr int kStageB = BN * 128;
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kStages = (BN <= 128) ? 5 : 3;
+  static constexpr int kAccStride = (BN <= 128) ? 128 : 256;      // TMEM column offset of accumulator 1
+  static constexpr int kTmemCols = (BN <= 128) ? 256 : 512;
+  static constexpr int kStaging = 4 * 2 * 4096;                   // per epilogue warp: 2 boxes of 32 px x 128 B
+  static constexpr int kSmem = kStages * kStage + kStaging + 1024 + 256;
+};
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_addr(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ CUtensorMap tmY, const ConvParams p) {
+  using Cfg = ConvCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + Cfg::kStages * Cfg::kStage;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStaging);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int total_tiles = p.batch * tiles_per_img;
+  const int kblocks = 9 * p.kbc;
+
+  if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmX); ptx::prefetch_tmap(&tmW); ptx::prefetch_tmap(&tmY); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < Cfg::kStages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+      for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], 4); }
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int b = t / tiles_per_img, r = t - b * tiles_per_img;
+        const int y0 = (r / p.tiles_x) * 8, x0 = (r % p.tiles_x) * 16;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const int tap = kb / p.kbc, cb = kb - tap * p.kbc;
+          const int dy = tap / 3, dx = tap - dy * 3;
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStage;
+          ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStage);
+          ptx::tma_load_4d(sa, &tmX, &full_bar[stage], cb * 64, x0 + dx - 1, y0 + dy - 1, b);
+          ptx::tma_load_3d(sa + Cfg::kStageA, &tmW, &full_bar[stage], kb * 64, 0, 0);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc(1 /*bf16*/, 128, BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_addr(smem + stage * Cfg::kStage);
+          const uint64_t adesc = ptx::umma_desc_sw128(sa);
+          const uint64_t bdesc = ptx::umma_desc_sw128(sa + Cfg::kStageA);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ptx::umma<1>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    uint8_t* wstage = staging + (warp - 2) * 8192;
+    int acc = 0; uint32_t acc_phase = 0;
+    uint32_t box_ctr = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int b = t / tiles_per_img, r = t - b * tiles_per_img;
+      const int y0 = (r / p.tiles_x) * 8, x0 = (r % p.tiles_x) * 16;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * Cfg::kAccStride;
+      for (int c0 = 0; c0 < BN; c0 += 64) {
+        if (c0 >= p.cout_p) break;
+        uint8_t* box = wstage + (box_ctr & 1) * 4096;
+        ++box_ctr;
+        if (lane == 0) ptx::bulk_wait_read<1>();
+        __syncwarp();
+        if (p.residual) {
+          // coalesced: 4 pixels x 128 B per instruction (pixel = it*4 + lane/8, 16-byte chunk = lane%8)
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int px = it * 4 + (lane >> 3), ch = lane & 7;
+            const int y = y0 + quad * 2 + (px >> 4), x = x0 + (px & 15);
+            uint4 val = make_uint4(0u, 0u, 0u, 0u);
+            if (y < p.h && x < p.w && c0 + ch * 8 < p.cout_p)
+              val = __ldg(reinterpret_cast<const uint4*>(p.residual + (((int64_t)b * p.h + y) * p.w + x) * p.cout_p + c0 + ch * 8));
+            *reinterpret_cast<uint4*>(box + px * 128 + ((ch ^ (px & 7)) << 4)) = val;
+          }
+          __syncwarp();
+        }
+        float v[64];
+        ptx::tmem_ld_32x32(t_row + c0, v);
+        ptx::tmem_ld_32x32(t_row + c0 + 32, v + 32);
+        ptx::tmem_ld_wait();
+        if (c0 + 64 <= p.cout_p) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + j);
+            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+          }
+        } else {
+          for (int j = 0; j < 64; ++j) if (c0 + j < p.cout_p) v[j] += __ldg(p.bias + c0 + j);
+        }
+        uint8_t* myrow = box + lane * 128;
+        if (p.residual) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 r4 = *reinterpret_cast<const uint4*>(myrow + ((j ^ (lane & 7)) << 4));
+            const uint32_t w4[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[q]);
+              v[8 * j + 2 * q] += __low2float(h2);
+              v[8 * j + 2 * q + 1] += __high2float(h2);
+            }
+          }
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (p.act == 2) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = v[j] > 0.f ? v[j] : 0.01f * v[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 o;
+          o.x = pack_bf16(v[8 * j], v[8 * j + 1]); o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+          o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+          *reinterpret_cast<uint4*>(myrow + ((j ^ (lane & 7)) << 4)) = o;
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&tmY, box, c0, x0, y0 + quad * 2, b);
+          ptx::bulk_commit();
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) ptx::bulk_wait<0>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// out = lateral + bilinear_upsample(src -> (h, w), align_corners=True)   (FPN top-down merge, resnet_fpn.py:108-115)
+// NHWC bf16; one thread per 8 channels (16 B).
+__global__ void upsample_add_bf16_kernel(const uint4* __restrict__ lateral, const uint4* __restrict__ src,
+                                         uint4* __restrict__ out, int b, int h, int w, int hs, int ws, int c8,
+                                         float ry, float rx) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)b * h * w * c8;
+  if (idx >= total) return;
+  const int ch = (int)(idx % c8);
+  int64_t r = idx / c8;
+  const int x = (int)(r % w); r /= w;
+  const int y = (int)(r % h);
+  const int n = (int)(r / h);
+  const float fy = ry * y, fx = rx * x;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = min(y0 + 1, hs - 1), x1 = min(x0 + 1, ws - 1);
+  const float ly = fy - y0, lx = fx - x0;
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const uint4* s = src + (int64_t)n * hs * ws * c8;
+  const uint4 a = __ldg(s + ((int64_t)y0 * ws + x0) * c8 + ch), bq = __ldg(s + ((int64_t)y0 * ws + x1) * c8 + ch);
+  const uint4 cq = __ldg(s + ((int64_t)y1 * ws + x0) * c8 + ch), d = __ldg(s + ((int64_t)y1 * ws + x1) * c8 + ch);
+  const uint4 l = __ldg(lateral + idx);
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {bq.x, bq.y, bq.z, bq.w}, cw[4] = {cq.x, cq.y, cq.z, cq.w},
+                 dw[4] = {d.x, d.y, d.z, d.w}, lw[4] = {l.x, l.y, l.z, l.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(&aw[q]), b2 = *reinterpret_cast<const __nv_bfloat162*>(&bw[q]);
+    const __nv_bfloat162 c2 = *reinterpret_cast<const __nv_bfloat162*>(&cw[q]), d2 = *reinterpret_cast<const __nv_bfloat162*>(&dw[q]);
+    const __nv_bfloat162 l2 = *reinterpret_cast<const __nv_bfloat162*>(&lw[q]);
+    const float lo = __low2float(l2) + w00 * __low2float(a2) + w01 * __low2float(b2) + w10 * __low2float(c2) + w11 * __low2float(d2);
+    const float hi = __high2float(l2) + w00 * __high2float(a2) + w01 * __high2float(b2) + w10 * __high2float(c2) + w11 * __high2float(d2);
+    o[q] = pack_bf16(lo, hi);
+  }
+  out[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn();
+
+// NHWC bf16 map: dims {C, W, H, B}; box {64, box_w, box_h, 1}; 128B swizzle; OOB -> 0 on load, clipped on store
+static int make_nhwc_tmap(CUtensorMap* m, const void* base, int c, int w, int h, int b, int box_w, int box_h) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return gf_set_error(GF_ERR_DRIVER, "gf_init() was not called");
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)b};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)c * 2 * w, (cuuint64_t)c * 2 * w * h};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return gf_set_error(GF_ERR_DRIVER, "cuTensorMapEncodeTiled(nhwc) failed");
+  return GF_OK;
+}
+
+template <int BN>
+static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const ConvParams& p,
+                       cudaStream_t stream) {
+  using Cfg = ConvCfg<BN>;
+  static bool attr = false;
+  auto kern = conv3x3_tc_kernel<BN>;
+  if (!attr) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem) != cudaSuccess)
+      return gf_set_error(GF_ERR_LAUNCH, "cudaFuncSetAttribute(conv smem) failed");
+    attr = true;
+  }
+  const int tiles = p.batch * p.tiles_x * p.tiles_y;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, 192, Cfg::kSmem, stream>>>(tx, tw, ty, p);
+  g_launches++;
+  GF_CHECK_LAUNCH();
+  return GF_OK;
+}
+
+}  // namespace gf
+
+using namespace gf;
+
+// x NHWC bf16 [b,h,w,cin_p]; wt bf16 [cout_p][9][cin_k] (cin_k = cin_p rounded up to 64, zero padded);
+// bias fp32 [cout_p]; residual / y NHWC bf16 [b,h,w,cout_p].  cin_p, cout_p multiples of 8; cout_p <= 256.
+extern "C" int gf_conv3x3_bf16(const void* x, const void* wt, const float* bias, const void* residual, void* y,
+                               int batch, int h, int w, int cin_p, int cout_p, int cin_k, int act, gf_stream_t stream) {
+  if (batch <= 0 || h <= 0 || w <= 0 || (cin_p % 8) || (cout_p % 8) || cout_p > 256 || (cin_k % 64) || cin_k < cin_p)
+    return gf_set_error(GF_ERR_ARG, "gf_conv3x3_bf16: channels must be multiples of 8, cout <= 256, cin_k % 64 == 0");
+  const int BN = cout_p <= 128 ? 128 : (cout_p <= 208 ? 208 : 256);
+  CUtensorMap tx, tw, ty;
+  int rc;
+  if ((rc = make_nhwc_tmap(&tx, x, cin_p, w, h, batch, 16, 8))) return rc;
+  if ((rc = make_nhwc_tmap(&ty, y, cout_p, w, h, batch, 16, 2))) return rc;
+  if ((rc = make_tmap(&tw, wt, 2, 9 * (int64_t)cin_k, cout_p, 1, 9 * (int64_t)cin_k, 0, BN))) return rc;
+  ConvParams p{};
+  p.bias = bias; p.residual = (const __nv_bfloat16*)residual; p.batch = batch; p.h = h; p.w = w; p.cout_p = cout_p;
+  p.kbc = cin_k / 64; p.tiles_x = gf_cdiv(w, 16); p.tiles_y = gf_cdiv(h, 8); p.act = act;
+  if (BN == 128) return launch_conv<128>(tx, tw, ty, p, (cudaStream_t)stream);
+  if (BN == 208) return launch_conv<208>(tx, tw, ty, p, (cudaStream_t)stream);
+  return launch_conv<256>(tx, tw, ty, p, (cudaStream_t)stream);
+}
+
+extern "C" int gf_upsample_add_bf16(const void* lateral, const void* src, void* out, int batch, int h, int w, int hs,
+                                    int ws, int c, gf_stream_t stream) {
+  if (batch <= 0 || h <= 1 || w <= 1 || hs <= 0 || ws <= 0 || (c % 8)) return gf_set_error(GF_ERR_ARG, "gf_upsample_add_bf16: bad shape");
+  const int64_t total = (int64_t)batch * h * w * (c / 8);
+  const float ry = (float)(hs - 1) / (float)(h - 1), rx = (float)(ws - 1) / (float)(w - 1);
+  upsample_add_bf16_kernel<<<gf_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)lateral, (const uint4*)src, (uint4*)out, batch, h, w, hs, ws, c / 8, ry, rx);
+  g_launches++;
+  GF_CHECK_LAUNCH();
+  return GF_OK;
+}

@@ -356,6 +356,7 @@ int init_driver(int device) {
   return GF_OK;
 }
 int num_sms() { return g_num_sms; }
+EncodeTiledFn encode_fn() { return g_encode; }
 
 // 3-D K-major operand map: dims {K, rows, batches}; box {128 bytes of K, box_rows, 1}; 128B swizzle; OOB -> 0
 int make_tmap(CUtensorMap* m, const void* base, int esize, int64_t k, int64_t rows, int64_t batches,

@@ -40,6 +40,19 @@ def _fold_bn(w: torch.Tensor, sd: Dict[str, torch.Tensor], bn: str, eps: float =
     return wf, bf
 
 
+def pack_conv3x3(w: torch.Tensor, b: Optional[torch.Tensor], cin_p: int, cout_p: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[Cout,Cin,3,3] fp32 (+bias) -> tap-major K-major bf16 [cout_p, 9, cin_k] and fp32 bias [cout_p] for
+    gf_conv3x3_bf16 (cin_k = cin_p rounded up to a multiple of 64; all padding is zero)."""
+    co, ci = w.shape[:2]
+    cin_k = (cin_p + 63) // 64 * 64
+    wt = torch.zeros((cout_p, 9, cin_k), dtype=torch.float32)
+    wt[:co, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, 9, ci)
+    bias = torch.zeros(cout_p, dtype=torch.float32)
+    if b is not None:
+        bias[:co] = b
+    return wt.to(device=device, dtype=torch.bfloat16).contiguous(), bias.to(device)
+
+
 class PackedWeights:
     """Device-resident, kernel-ready weights derived from a reference-schema state dict."""
 
@@ -113,6 +126,27 @@ class PackedWeights:
         bb["layer1_outconv2.0"] = conv("layer1_outconv2.0", "layer1_outconv2.1")
         bb["layer1_outconv2.3"] = conv("layer1_outconv2.3")
         self.bb = bb
+        # tcgen05 implicit-GEMM path (bf16 only): tap-major packed weights for every 3x3 / stride-1 conv
+        self.bb_tc = None
+        if backbone_dtype == torch.bfloat16 and os.environ.get("GF_CONV", "tc") == "tc":
+            def tc(name, bn=None):
+                w = sd["backbone." + name + ".weight"]
+                b = None
+                if bn is not None:
+                    w, b = _fold_bn(w, bsd, bn)
+                return pack_conv3x3(w.float(), b, padc(w.shape[1]), padc(w.shape[0]), device)
+            t = {}
+            for li in (1, 2, 3):
+                for bi in (0, 1):
+                    p = f"layer{li}.{bi}"
+                    if not (li > 1 and bi == 0):
+                        t[p + ".conv1"] = tc(p + ".conv1", p + ".bn1")
+                    t[p + ".conv2"] = tc(p + ".conv2", p + ".bn2")
+            t["layer2_outconv2.0"] = tc("layer2_outconv2.0", "layer2_outconv2.1")
+            t["layer2_outconv2.3"] = tc("layer2_outconv2.3")
+            t["layer1_outconv2.0"] = tc("layer1_outconv2.0", "layer1_outconv2.1")
+            t["layer1_outconv2.3"] = tc("layer1_outconv2.3")
+            self.bb_tc = t
         self._pe: Dict[Tuple[int, int, int], torch.Tensor] = {}
 
     def pos_table(self, c: int, h: int, w: int) -> torch.Tensor:
@@ -135,6 +169,8 @@ class PackedWeights:
 # --------------------------------------------------------------------------------------------
 def backbone_forward(pw: PackedWeights, img: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """[B,1,H,W] fp32 -> coarse NHWC [B,H/8,W/8,256] fp32, fine NHWC [B,H/2,W/2,128] fp32 (both contiguous)."""
+    if pw.bb_tc is not None:
+        return backbone_forward_tc(pw, img)
     bb = pw.bb
     x = img.to(pw.backbone_dtype).contiguous(memory_format=torch.channels_last)
 
@@ -163,6 +199,43 @@ def backbone_forward(pw: PackedWeights, img: torch.Tensor) -> Tuple[torch.Tensor
     coarse = x3o.permute(0, 2, 3, 1).float().contiguous()
     fine = x1o.permute(0, 2, 3, 1).float().contiguous()
     return coarse, fine
+
+
+def backbone_forward_tc(pw: PackedWeights, img: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Same network; every 3x3 / stride-1 convolution (95 % of the backbone FLOPs) runs in the tcgen05
+    implicit-GEMM kernel with BN, residual add and activation fused into its epilogue.  The 7x7 stem, the three
+    stride-2 convolutions and the 1x1 laterals stay on cuDNN; the FPN upsample+add is one fused kernel."""
+    bb, tc = pw.bb, pw.bb_tc
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous()   # channels-last NCHW -> NHWC (no copy when already channels-last)
+    nchw = lambda t: t.permute(0, 3, 1, 2)
+
+    def cudnn(name, t, stride=1, pad=1):
+        w, b = bb[name]
+        return F.conv2d(t, w, b, stride, pad)
+
+    def conv(name, t, act, residual=None):
+        wt, b = tc[name]
+        return ops.conv3x3(t, wt, b, residual, act)
+
+    def block(p, a):                                  # a: NHWC
+        if (p + ".down") in bb:                       # stride-2 entry block
+            y = nhwc(F.relu_(cudnn(p + ".conv1", nchw(a), 2)))
+            a = nhwc(cudnn(p + ".down", nchw(a), 2, 0))
+        else:
+            y = conv(p + ".conv1", a, 1)
+        return conv(p + ".conv2", y, 1, residual=a)
+
+    x = img.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    x0 = nhwc(F.relu_(cudnn("conv1", x, 2, 3)))
+    x1 = block("layer1.1", block("layer1.0", x0))
+    x2 = block("layer2.1", block("layer2.0", x1))
+    x3 = block("layer3.1", block("layer3.0", x2))
+    x3o = nhwc(cudnn("layer3_outconv", nchw(x3), 1, 0))
+    x2o = ops.upsample_add(nhwc(cudnn("layer2_outconv", nchw(x2), 1, 0)), x3o)
+    x2o = conv("layer2_outconv2.3", conv("layer2_outconv2.0", x2o, 2), 0)
+    x1o = ops.upsample_add(nhwc(cudnn("layer1_outconv", nchw(x1), 1, 0)), x2o)
+    x1o = conv("layer1_outconv2.3", conv("layer1_outconv2.0", x1o, 2), 0)
+    return x3o.float().contiguous(), x1o.float().contiguous()
 
 
 # --------------------------------------------------------------------------------------------

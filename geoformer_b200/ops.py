@@ -136,6 +136,31 @@ def linear(a: torch.Tensor, w: torch.Tensor, a2: Optional[torch.Tensor] = None, 
     return y
 
 
+def conv3x3(x: torch.Tensor, wt: torch.Tensor, bias: torch.Tensor, residual: Optional[torch.Tensor] = None,
+            act: int = 0) -> torch.Tensor:
+    """3x3/s1/p1 conv + folded BN (+ residual) + activation on NHWC bf16 (tcgen05 implicit GEMM).
+    x [b,h,w,cin_p]; wt [cout_p, 9, cin_k]; bias fp32 [cout_p]; returns [b,h,w,cout_p] bf16."""
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and wt.dtype == torch.bfloat16 and wt.is_contiguous()
+    b, h, w, cin_p = x.shape
+    cout_p, _, cin_k = wt.shape
+    y = torch.empty((b, h, w, cout_p), device=x.device, dtype=torch.bfloat16)
+    if residual is not None:
+        assert residual.shape == y.shape and residual.is_contiguous() and residual.dtype == torch.bfloat16
+    _call("gf_conv3x3_bf16", x.data_ptr(), wt.data_ptr(), bias.data_ptr(), _ptr(residual), y.data_ptr(), b, h, w, cin_p,
+          cout_p, cin_k, act, _stream(), tag=f"[{cin_p}->{cout_p}@{h}x{w}]")
+    return y
+
+
+def upsample_add(lateral: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+    """lateral [b,h,w,c] + bilinear_upsample(src [b,hs,ws,c]) (align_corners=True), NHWC bf16."""
+    assert lateral.is_contiguous() and src.is_contiguous() and lateral.dtype == src.dtype == torch.bfloat16
+    b, h, w, c = lateral.shape
+    out = torch.empty_like(lateral)
+    _call("gf_upsample_add_bf16", lateral.data_ptr(), src.data_ptr(), out.data_ptr(), b, h, w, src.shape[1], src.shape[2],
+          c, _stream())
+    return out
+
+
 def add_posenc(x: torch.Tensor, pe: torch.Tensor) -> torch.Tensor:
     n, l, c = x.shape
     assert x.is_contiguous() and pe.is_contiguous() and pe.shape == (l, c)

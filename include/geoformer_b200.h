@@ -64,6 +64,17 @@ int gf_linear_ref(const float* A, const float* A2, const float* W, float* Y, int
                   const float* gamma, const float* beta, const float* residual, const int* m_dev,
                   gf_stream_t stream);
 
+/* Backbone 3x3 / stride 1 / pad 1 convolution with folded BatchNorm (resnet_fpn.py:32-40,70-82) as a tcgen05
+ * implicit GEMM over NHWC bf16:  y = act(conv(x, wt) + bias (+ residual)).
+ *   x [b,h,w,cin_p] bf16; wt [cout_p][9][cin_k] bf16 (tap-major, cin_k = cin_p rounded up to 64, zero padded);
+ *   bias fp32 [cout_p]; residual (optional) and y [b,h,w,cout_p] bf16.  act: 0 none, 1 ReLU, 2 LeakyReLU(0.01). */
+int gf_conv3x3_bf16(const void* x, const void* wt, const float* bias, const void* residual, void* y, int batch, int h,
+                    int w, int cin_p, int cout_p, int cin_k, int act, gf_stream_t stream);
+
+/* FPN top-down merge (resnet_fpn.py:108-115): out = lateral + bilinear(src -> h x w, align_corners=True); NHWC bf16 */
+int gf_upsample_add_bf16(const void* lateral, const void* src, void* out, int batch, int h, int w, int hs, int ws,
+                         int c, gf_stream_t stream);
+
 /* out[n,l,c] = x[n,l,c] + pe[l,c]  (position_encoding.py:42 on the NHWC-flattened coarse map) */
 int gf_add_posenc(const float* x, const float* pe, float* out, int n, int64_t l, int c, gf_stream_t stream);
 

@@ -142,3 +142,26 @@ def test_full_size_dense_pair_corner_error(golden_dir):
     e_ref = corner_err(g["mkpts0_f"].astype(np.float32), g["mkpts1_f"].astype(np.float32))
     e_gpu = corner_err(k0, k1)
     assert abs(e_gpu - e_ref) <= 0.1, (e_gpu, e_ref)
+
+
+def test_backbone_tcgen05_vs_cudnn_and_fp32():
+    """The tcgen05 implicit-GEMM backbone (bf16) against cuDNN bf16 and cuDNN fp32 on the same folded weights:
+    bf16 storage of 20 chained conv layers gives ~1e-2 relative differences; both bf16 paths must sit at the same
+    distance from the fp32 result."""
+    from geoformer_b200 import engine, ops
+    dev = torch.device("cuda:0")
+    ops.ensure_init(dev)
+    sd = synth.make_state_dict(7, True)
+    img = torch.cat(synth.make_pairs(2, 96, 128, "dense", 3), 0).to(dev)
+    torch.backends.cudnn.allow_tf32 = False
+    ref_c, ref_f = engine.backbone_forward(engine.PackedWeights(sd, dev, torch.float32), img)
+    os.environ["GF_CONV"] = "cudnn"
+    cd_c, cd_f = engine.backbone_forward(engine.PackedWeights(sd, dev, torch.bfloat16), img)
+    os.environ["GF_CONV"] = "tc"
+    pw = engine.PackedWeights(sd, dev, torch.bfloat16)
+    assert pw.bb_tc is not None
+    tc_c, tc_f = engine.backbone_forward(pw, img)
+    rel = lambda a, b: ((a - b).abs().max() / b.abs().max()).item()
+    assert tc_c.shape == ref_c.shape and tc_f.shape == ref_f.shape
+    e_tc, e_cd = max(rel(tc_c, ref_c), rel(tc_f, ref_f)), max(rel(cd_c, ref_c), rel(cd_f, ref_f))
+    assert e_tc <= 3e-2 and e_tc <= 2.0 * e_cd + 5e-3, (e_tc, e_cd)

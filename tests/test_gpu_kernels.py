@@ -323,3 +323,34 @@ def test_fine_match_threshold_and_random(ops):
     assert 0 < want["mkpts0_f"].shape[0] < m              # the threshold bites
     assert torch.equal(out["mkpts0_f"].cpu(), want["mkpts0_f"]) and torch.equal(out["mkpts1_f"].cpu(), want["mkpts1_f"])
     assert (out["mkpts0_f"].cpu() % 2 == 0).all()
+
+
+# ------------------------------------------------------------------------------------------- backbone conv
+@pytest.mark.parametrize("cin,cout,cin_p,cout_p,res,act", [
+    (128, 128, 128, 128, False, 1), (128, 128, 128, 128, True, 1), (196, 196, 200, 200, True, 1),
+    (256, 196, 256, 200, False, 0), (196, 128, 200, 128, False, 0), (256, 256, 256, 256, False, 2),
+])
+def test_conv3x3_tcgen05(ops, cin, cout, cin_p, cout_p, res, act):
+    """tcgen05 implicit-GEMM 3x3 conv (NHWC bf16, zero-padded channels, partial 8x16 tiles at the borders) vs
+    F.conv2d in fp32 on the same bf16-rounded operands.  Tolerance: bf16 output rounding (2^-8) on top of
+    fp32 accumulation -> 1e-2 of the output range."""
+    from geoformer_b200.engine import pack_conv3x3
+    b, h, w = 2, 20, 40
+    x = rnd(b, cin, h, w, seed=1).bfloat16()
+    wgt = (rnd(cout, cin, 3, 3, seed=2) * (cin * 9) ** -0.5).bfloat16()
+    bias = rnd(cout, seed=3) * 0.1
+    r = rnd(b, cout, h, w, seed=4).bfloat16() if res else None
+    want = F.conv2d(x.float(), wgt.float(), bias, 1, 1)
+    if res:
+        want = want + r.float()
+    want = F.relu(want) if act == 1 else (F.leaky_relu(want, 0.01) if act == 2 else want)
+    xp = torch.zeros(b, h, w, cin_p, dtype=torch.bfloat16); xp[..., :cin] = x.permute(0, 2, 3, 1)
+    rp = None
+    if res:
+        rp = torch.zeros(b, h, w, cout_p, dtype=torch.bfloat16); rp[..., :cout] = r.permute(0, 2, 3, 1)
+    wt, bp = pack_conv3x3(wgt.float(), bias, cin_p, cout_p, "cuda")
+    y = ops.conv3x3(dev(xp), wt, bp, None if rp is None else dev(rp), act).cpu().float()
+    got = y[..., :cout].permute(0, 3, 1, 2)
+    assert (y[..., cout:] == 0).all()                       # padded channels stay exactly zero
+    err = (got - want).abs().max().item()
+    assert err <= 1e-2 * want.abs().max().item(), err
