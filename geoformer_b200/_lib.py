@@ -22,6 +22,7 @@ SIGNATURES = {
     "gf_linear_tf32": (I, [P, P, P, P, L, I, I, I, I, I, P, P, I, P, P, P, P, P]),
     "gf_linear_ref": (I, [P, P, P, P, L, I, I, I, I, I, P, P, I, P, P, P, P, P]),
     "gf_conv3x3_bf16": (I, [P, P, P, P, P, I, I, I, I, I, I, I, P]),
+    "gf_stem_conv7x7_bf16": (I, [P, P, P, P, I, I, I, P]),
     "gf_upsample_add_bf16": (I, [P, P, P, I, I, I, I, I, I, P]),
     "gf_add_posenc": (I, [P, P, P, I, L, I, P]),
     "gf_linattn_partial_floats": (L, [I, I, I, I]),
@@ -31,7 +32,8 @@ SIGNATURES = {
     "gf_pack_split_f16": (I, [P, P, L, I, F, I, P]),
     "gf_similarity_f16x3": (I, [P, P, P, I, I, I, I, F, P]),
     "gf_similarity_ref": (I, [P, P, P, I, I, I, I, F, F, P]),
-    "gf_dual_softmax_stats": (I, [P, I, I, I, P, P, P, P, P]),
+    "gf_dual_softmax_workspace_floats": (L, [I, I, I]),
+    "gf_dual_softmax_stats": (I, [P, I, I, I, P, P, P, P, P, P]),
     "gf_dual_softmax_conf": (I, [P, I, I, I, P, P, P, P, P, P, P]),
     "gf_conf_row_col_max": (I, [P, I, I, I, P, P, P]),
     "gf_mnn_select": (I, [P, I, I, I, F, I, I, I, I, I, P, P, P, P, P]),
@@ -45,6 +47,7 @@ SIGNATURES = {
     "gf_geo_cross_attention": (I, [P, I, P, I, P, I, P, I, I, I, I, I, P, I, P]),
     "gf_select_rows": (I, [P, P, P, I, L, I, P]),
     "gf_fine_gather": (I, [P, I, I, I, P, P, L, I, I, I, P, P]),
+    "gf_fine_gather_bf16": (I, [P, I, I, I, P, P, L, I, I, I, P, P]),
     "gf_gather_rows": (I, [P, L, I, P, P, L, P, P]),
     "gf_fine_match": (I, [P, P, L, I, I, F, F, P, P, P, P, P, P]),
     "gf_compact_fine": (I, [P, P, P, P, P, P, P, L, I, F, F, F, P, P, P, P, P, P]),

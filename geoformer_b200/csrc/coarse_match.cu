@@ -108,47 +108,128 @@ __global__ void col_stats_kernel(const float* __restrict__ mat, int l, int s, fl
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused statistics: ONE read of sim produces row and column (max, sum exp) partials.
+// CTA = 128 rows x 256 columns; thread == column (coalesced 1 KB row segments).  Column statistics are an
+// online (max, sum) in the thread's registers; row statistics are reduced across the CTA's 256 columns with
+// warp shuffles + shared memory.  Partials: rowp[n][l][cblocks] and colp[n][rblocks][s] as float2 (max, sum).
+// ---------------------------------------------------------------------------------------------
+constexpr int kStatRows = 128;
+constexpr int kStatSub = 32;       // rows staged per shared-memory sub-tile
+__global__ void __launch_bounds__(256)
+fused_stats_kernel(const float* __restrict__ sim, int l, int s, float2* __restrict__ rowp, float2* __restrict__ colp) {
+  __shared__ float tile[kStatSub][256 + 4];
+  const int n = blockIdx.z, rb = blockIdx.y, cb = blockIdx.x;
+  const int col = cb * 256 + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r0 = rb * kStatRows;
+  const int rows = min(kStatRows, l - r0);
+  const bool ok = col < s;
+  const float* p = sim + ((int64_t)n * l + r0) * s + col;
+  float cm = -INFINITY, cs = 0.f;
+  for (int rs = 0; rs < rows; rs += kStatSub) {
+    const int sub = min(kStatSub, rows - rs);
+    // column pass: thread == column, online (max, sum); the values are parked in shared memory for the row pass
+    float v[kStatSub];
+#pragma unroll
+    for (int r = 0; r < kStatSub; ++r) v[r] = (ok && r < sub) ? p[(int64_t)(rs + r) * s] : -INFINITY;   // 32 loads in flight
+#pragma unroll
+    for (int r = 0; r < kStatSub; ++r) {
+      tile[r][threadIdx.x] = v[r];
+      if (v[r] > cm) { cs = cs * __expf(cm - v[r]) + 1.f; cm = v[r]; } else if (v[r] > -INFINITY) { cs += __expf(v[r] - cm); }
+    }
+    __syncthreads();
+    // row pass: each warp owns 4 of the 32 rows; lane reads 8 values, then one shuffle tree per row
+#pragma unroll
+    for (int q = 0; q < kStatSub / 8; ++q) {
+      const int r = warp * (kStatSub / 8) + q;
+      float x[8];
+      float m = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { x[k] = tile[r][lane + 32 * k]; m = fmaxf(m, x[k]); }
+      m = warp_max(m);
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum += (x[k] > -INFINITY) ? __expf(x[k] - m) : 0.f;
+      sum = warp_sum(sum);
+      if (lane == 0 && r < sub) rowp[((int64_t)n * l + r0 + rs + r) * gridDim.x + cb] = make_float2(m, sum);
+    }
+    __syncthreads();
+  }
+  if (ok) colp[((int64_t)n * gridDim.y + rb) * s + col] = make_float2(cm, cs);
+}
+
+// merge `parts` (max, sum) partials per output element; partial k of element e is at in[e*estride + k*kstride]
+__global__ void merge_stats_kernel(const float2* __restrict__ in, int64_t elems, int parts, int64_t estride,
+                                   int64_t kstride, int64_t group, int64_t gstride, float* __restrict__ out_max,
+                                   float* __restrict__ out_sum) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= elems) return;
+  // element e = (g, i) with i < group: base = g*gstride + i*estride
+  const int64_t g = e / group, i = e - g * group;
+  const float2* p = in + g * gstride + i * estride;
+  float m = -INFINITY;
+  for (int k = 0; k < parts; ++k) m = fmaxf(m, p[k * kstride].x);
+  float sum = 0.f;
+  for (int k = 0; k < parts; ++k) { const float2 v = p[k * kstride]; sum += v.y * __expf(v.x - m); }
+  out_max[e] = m;
+  out_sum[e] = sum;
+}
+
 // conf = softmax(sim, dim=1) * softmax(sim, dim=2) in place, plus max of conf per row and per column, in ONE
 // sweep.  CTA = 256 columns x 32 rows; thread == column (coalesced), loops the 32 rows.  Row maxima are merged
 // with warp shuffles + shared atomics, column maxima with one global atomicMax per (column, 32-row strip)
 // (conf >= 0, so the float bit pattern orders like an unsigned integer).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 conf_kernel(float* __restrict__ sim, int l, int s, const float* __restrict__ row_max, const float* __restrict__ row_sum,
             const float* __restrict__ col_max, const float* __restrict__ col_sum, unsigned* __restrict__ conf_row_max,
             unsigned* __restrict__ conf_col_max) {
-  __shared__ unsigned rbest[32];
-  __shared__ float rm[32], rinv[32];
+  __shared__ float tile[32][256 + 4];
+  __shared__ float rm[32], rs[32];
   const int n = blockIdx.z;
   const int r0 = blockIdx.y * 32;
   const int col = blockIdx.x * 256 + threadIdx.x;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rows = min(32, l - r0);
   if (threadIdx.x < 32) {
-    rbest[threadIdx.x] = 0u;
     const int r = r0 + threadIdx.x;
     rm[threadIdx.x] = r < l ? row_max[(int64_t)n * l + r] : 0.f;
-    rinv[threadIdx.x] = r < l ? row_sum[(int64_t)n * l + r] : 1.f;
+    rs[threadIdx.x] = r < l ? 1.f / row_sum[(int64_t)n * l + r] : 1.f;      // reciprocal row sum
   }
   __syncthreads();
   const bool ok = col < s;
   const float cm = ok ? col_max[(int64_t)n * s + col] : 0.f;
-  const float cs = ok ? col_sum[(int64_t)n * s + col] : 1.f;
+  const float ics = ok ? 1.f / col_sum[(int64_t)n * s + col] : 1.f;
   float* p = sim + ((int64_t)n * l + r0) * s + col;
-  const int rows = min(32, l - r0);
   float cbest = 0.f;
-  for (int r = 0; r < rows; ++r) {
-    float c = 0.f;
-    if (ok) {
-      const float v = p[(int64_t)r * s];
-      c = (expf(v - cm) / cs) * (expf(v - rm[r]) / rinv[r]);
-      p[(int64_t)r * s] = c;
-      cbest = fmaxf(cbest, c);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    float v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = (ok && half * 16 + r < rows) ? p[(int64_t)(half * 16 + r) * s] : -INFINITY;   // 16 loads in flight
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int rr = half * 16 + r;
+      float c = 0.f;
+      if (ok && rr < rows) {
+        c = (__expf(v[r] - cm) * ics) * (__expf(v[r] - rm[rr]) * rs[rr]);
+        p[(int64_t)rr * s] = c;
+        cbest = fmaxf(cbest, c);
+      }
+      tile[rr][threadIdx.x] = c;
     }
-    const float wbest = warp_max(c);
-    if (lane == 0) atomicMax(&rbest[r], __float_as_uint(wbest));
   }
   if (ok) atomicMax(&conf_col_max[(int64_t)n * s + col], __float_as_uint(cbest));
   __syncthreads();
-  if (threadIdx.x < rows) atomicMax(&conf_row_max[(int64_t)n * l + r0 + threadIdx.x], rbest[threadIdx.x]);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {                       // warp w reduces rows 4w .. 4w+3 over the CTA's 256 columns
+    const int r = warp * 4 + q;
+    float m = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m = fmaxf(m, tile[r][lane + 32 * k]);
+    m = warp_max(m);
+    if (lane == 0 && r < rows) atomicMax(&conf_row_max[(int64_t)n * l + r0 + r], __float_as_uint(m));
+  }
 }
 
 __global__ void row_max_kernel(const float* __restrict__ mat, int64_t rows, int s, float* __restrict__ out) {
@@ -295,13 +376,30 @@ extern "C" int gf_similarity_ref(const float* f0, const float* f1, float* sim, i
   return GF_OK;
 }
 
+extern "C" int64_t gf_dual_softmax_workspace_floats(int n, int l, int s) {
+  return 2 * ((int64_t)n * l * gf_cdiv(s, 256) + (int64_t)n * gf_cdiv(l, kStatRows) * s);
+}
+
 extern "C" int gf_dual_softmax_stats(const float* sim, int n, int l, int s, float* row_max, float* row_sum,
-                                     float* col_max, float* col_sum, gf_stream_t stream) {
+                                     float* col_max, float* col_sum, float* workspace, gf_stream_t stream) {
   if (n <= 0 || l <= 0 || s <= 0) return gf_set_error(GF_ERR_ARG, "gf_dual_softmax_stats: bad shape");
   const int64_t rows = (int64_t)n * l;
-  row_stats_kernel<<<gf_cdiv(rows, 8), 256, 0, STREAM>>>(sim, rows, s, row_max, row_sum);
-  col_stats_kernel<0><<<dim3(gf_cdiv(s, 32), n), dim3(32, 32), 0, STREAM>>>(sim, l, s, col_max, col_sum);
-  g_launches += 2;
+  if (workspace == nullptr) {       // two-sweep fallback (no workspace supplied)
+    row_stats_kernel<<<gf_cdiv(rows, 8), 256, 0, STREAM>>>(sim, rows, s, row_max, row_sum);
+    col_stats_kernel<0><<<dim3(gf_cdiv(s, 32), n), dim3(32, 32), 0, STREAM>>>(sim, l, s, col_max, col_sum);
+    g_launches += 2;
+  } else {
+    const int cblocks = gf_cdiv(s, 256), rblocks = gf_cdiv(l, kStatRows);
+    float2* rowp = reinterpret_cast<float2*>(workspace);
+    float2* colp = rowp + (int64_t)n * l * cblocks;
+    fused_stats_kernel<<<dim3(cblocks, rblocks, n), 256, 0, STREAM>>>(sim, l, s, rowp, colp);
+    // rows: element (g = 0, i = row): partials contiguous (estride = cblocks, kstride = 1)
+    merge_stats_kernel<<<gf_cdiv(rows, 256), 256, 0, STREAM>>>(rowp, rows, cblocks, cblocks, 1, rows, 0, row_max, row_sum);
+    // columns: element (g = sample, i = col): partials strided by s (kstride = s), sample stride rblocks*s
+    merge_stats_kernel<<<gf_cdiv((int64_t)n * s, 256), 256, 0, STREAM>>>(colp, (int64_t)n * s, rblocks, 1, s, s,
+                                                                        (int64_t)rblocks * s, col_max, col_sum);
+    g_launches += 3;
+  }
   GF_CHECK_LAUNCH();
   return GF_OK;
 }

@@ -257,6 +257,76 @@ __global__ void upsample_add_bf16_kernel(const uint4* __restrict__ lateral, cons
   out[idx] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stem: 7x7 / stride 2 / pad 3 convolution of the 1-channel image + folded BN + ReLU (resnet_fpn.py:58-60,102),
+// fp32 image in, NHWC bf16 out.  C_in = 1 makes this a 49-tap FFMA kernel (no tensor-core shape): CTA = 8 x 32
+// output pixels x 128 channels, thread = 8 consecutive pixels x 16 channels (128 accumulators), input patch and
+// weights in shared memory; per kernel row 21 input LDS + 28 weight LDS.128 feed 896 FFMA.
+// Weight layout in smem/global: [49 taps][4 j][8 cg][4 e]  <->  channel = j*32 + cg*4 + e.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+stem_conv7x7_kernel(const float* __restrict__ img, const float* __restrict__ wperm, const float* __restrict__ bias,
+                    __nv_bfloat16* __restrict__ out, int h, int w, int ho, int wo) {
+  __shared__ float patch[21][72];
+  __shared__ __align__(16) float ws[49 * 128];
+  const int b = blockIdx.z;
+  const int oy0 = blockIdx.y * 8, ox0 = blockIdx.x * 32;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < 49 * 128; e += 256) ws[e] = wperm[e];
+  const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+  const float* im = img + (int64_t)b * h * w;
+  for (int e = tid; e < 21 * 69; e += 256) {
+    const int r = e / 69, c = e - r * 69;
+    const int y = iy0 + r, x = ix0 + c;
+    patch[r][c] = (y >= 0 && y < h && x >= 0 && x < w) ? im[(int64_t)y * w + x] : 0.f;
+  }
+  __syncthreads();
+  const int cg = tid & 7, pg = tid >> 3;
+  const int prow = pg >> 2, pcol = (pg & 3) * 8;           // 8 pixels: row prow, columns pcol .. pcol+7 of the tile
+  float acc[8][16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+#pragma unroll 1
+  for (int ky = 0; ky < 7; ++ky) {
+    float in[21];
+#pragma unroll
+    for (int i = 0; i < 21; ++i) in[i] = patch[prow * 2 + ky][pcol * 2 + i];
+#pragma unroll
+    for (int kx = 0; kx < 7; ++kx) {
+      const float4* wp = reinterpret_cast<const float4*>(ws + (ky * 7 + kx) * 128) + cg;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 w4 = wp[j * 8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float x = in[2 * i + kx];
+          acc[i][4 * j] = fmaf(x, w4.x, acc[i][4 * j]); acc[i][4 * j + 1] = fmaf(x, w4.y, acc[i][4 * j + 1]);
+          acc[i][4 * j + 2] = fmaf(x, w4.z, acc[i][4 * j + 2]); acc[i][4 * j + 3] = fmaf(x, w4.w, acc[i][4 * j + 3]);
+        }
+      }
+    }
+  }
+  const int oy = oy0 + prow;
+  if (oy < ho) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + j * 32 + cg * 4));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int ox = ox0 + pcol + i;
+        if (ox < wo) {
+          uint2 o;
+          o.x = pack_bf16(fmaxf(acc[i][4 * j] + b4.x, 0.f), fmaxf(acc[i][4 * j + 1] + b4.y, 0.f));
+          o.y = pack_bf16(fmaxf(acc[i][4 * j + 2] + b4.z, 0.f), fmaxf(acc[i][4 * j + 3] + b4.w, 0.f));
+          *reinterpret_cast<uint2*>(out + (((int64_t)b * ho + oy) * wo + ox) * 128 + j * 32 + cg * 4) = o;
+        }
+      }
+    }
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -327,6 +397,19 @@ extern "C" int gf_upsample_add_bf16(const void* lateral, const void* src, void* 
   const float ry = (float)(hs - 1) / (float)(h - 1), rx = (float)(ws - 1) / (float)(w - 1);
   upsample_add_bf16_kernel<<<gf_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const uint4*)lateral, (const uint4*)src, (uint4*)out, batch, h, w, hs, ws, c / 8, ry, rx);
+  g_launches++;
+  GF_CHECK_LAUNCH();
+  return GF_OK;
+}
+
+// img fp32 [b,1,h,w]; wperm fp32 [49][128] in the permuted channel order of the kernel (see pack in engine.py);
+// bias fp32 [128] (natural channel order); out NHWC bf16 [b, h/2, w/2, 128] (natural channel order).
+extern "C" int gf_stem_conv7x7_bf16(const float* img, const float* wperm, const float* bias, void* out, int batch, int h,
+                                    int w, gf_stream_t stream) {
+  if (batch <= 0 || h <= 0 || w <= 0) return gf_set_error(GF_ERR_ARG, "gf_stem_conv7x7_bf16: bad shape");
+  const int ho = (h + 6 - 7) / 2 + 1, wo = (w + 6 - 7) / 2 + 1;
+  stem_conv7x7_kernel<<<dim3(gf_cdiv(wo, 32), gf_cdiv(ho, 8), batch), 256, 0, (cudaStream_t)stream>>>(
+      img, wperm, bias, (__nv_bfloat16*)out, h, w, ho, wo);
   g_launches++;
   GF_CHECK_LAUNCH();
   return GF_OK;

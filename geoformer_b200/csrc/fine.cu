@@ -2,9 +2,35 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <cuda_bf16.h>
 
 namespace gf {
 extern std::atomic<int64_t> g_launches;
+
+// same gather from a bf16 NHWC fine map (the tcgen05 backbone's native output): 8-byte loads, fp32 windows out
+__global__ void fine_gather_bf16_kernel(const __nv_bfloat16* __restrict__ fine, int hf, int wf, int c,
+                                        const int64_t* __restrict__ b_ids, const int64_t* __restrict__ tok_ids, int wc,
+                                        int stride, int window, float* __restrict__ out) {
+  const int64_t m = blockIdx.x;
+  const int b = (int)b_ids[m];
+  const int tok = (int)tok_ids[m];
+  const int cy = (tok / wc) * stride, cx = (tok % wc) * stride;
+  const int half = window / 2;
+  const int c4 = c >> 2;
+  float4* o = reinterpret_cast<float4*>(out + m * window * window * c);
+  for (int e = threadIdx.x; e < window * window * c4; e += blockDim.x) {
+    const int slot = e / c4, q = e - slot * c4;
+    const int py = cy + slot / window - half, px = cx + slot % window - half;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (py >= 0 && py < hf && px >= 0 && px < wf) {
+      const uint2 raw = __ldg(reinterpret_cast<const uint2*>(fine + (((int64_t)b * hf + py) * wf + px) * c) + q);
+      const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+      const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+      v = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+    }
+    o[e] = v;
+  }
+}
 
 // 5x5 stride-4 pad-2 window of the NHWC fine map around coarse token (row r, col c): pixels
 // (stride*r + ky - half, stride*c + kx - half); slot = ky*window + kx; zero outside (F.unfold padding).
@@ -35,7 +61,7 @@ __global__ void __launch_bounds__(128)
 fine_match_kernel(const float* __restrict__ f0, const float* __restrict__ f1, int ww, int c, float temperature, float thr,
                   int* __restrict__ sel, int* __restrict__ fi, int* __restrict__ fj, float* __restrict__ fconf,
                   float* __restrict__ fine_matrix) {
-  __shared__ float a[25][129], b[25][129];
+  __shared__ __align__(16) float a[25][132], b[25][132];     // stride 132: 16-byte aligned rows, conflict-free LDS.128
   __shared__ float S[25][26];
   __shared__ float rmax[25], rsum[25], cmax[25], csum[25];
   __shared__ float best_v[4];
@@ -52,7 +78,14 @@ fine_match_kernel(const float* __restrict__ f0, const float* __restrict__ f1, in
   for (int e = tid; e < ww * ww; e += 128) {
     const int i = e / ww, j = e - i * ww;
     float acc = 0.f;
-    for (int k = 0; k < c; ++k) acc = fmaf(a[i][k], b[j][k], acc);
+    const float4* ar = reinterpret_cast<const float4*>(&a[i][0]);
+    const float4* br = reinterpret_cast<const float4*>(&b[j][0]);
+#pragma unroll 8
+    for (int k = 0; k < c / 4; ++k) {
+      const float4 x = ar[k], y = br[k];
+      acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+    }
+    for (int k = c & ~3; k < c; ++k) acc = fmaf(a[i][k], b[j][k], acc);
     S[i][j] = acc / temperature;
   }
   __syncthreads();
@@ -147,6 +180,18 @@ extern "C" int gf_fine_gather(const float* fine_nhwc, int hf, int wf, int c, con
   if (m < 0 || c <= 0 || (c % 4) || window <= 0) return gf_set_error(GF_ERR_ARG, "gf_fine_gather: bad shape");
   if (m == 0) return GF_OK;
   fine_gather_kernel<<<(unsigned)m, 128, 0, STREAM>>>(fine_nhwc, hf, wf, c, b_ids, tok_ids, wc, stride, window, out);
+  g_launches++;
+  GF_CHECK_LAUNCH();
+  return GF_OK;
+}
+
+extern "C" int gf_fine_gather_bf16(const void* fine_nhwc, int hf, int wf, int c, const int64_t* b_ids,
+                                   const int64_t* tok_ids, int64_t m, int wc, int stride, int window, float* out,
+                                   gf_stream_t stream) {
+  if (m < 0 || c <= 0 || (c % 4) || window <= 0) return gf_set_error(GF_ERR_ARG, "gf_fine_gather_bf16: bad shape");
+  if (m == 0) return GF_OK;
+  fine_gather_bf16_kernel<<<(unsigned)m, 128, 0, STREAM>>>((const __nv_bfloat16*)fine_nhwc, hf, wf, c, b_ids, tok_ids, wc,
+                                                          stride, window, out);
   g_launches++;
   GF_CHECK_LAUNCH();
   return GF_OK;

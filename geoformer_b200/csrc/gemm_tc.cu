@@ -56,7 +56,9 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return copysignf(t, x);
 }
 
-template <int KIND, int BN>
+// FULL = false: lean epilogue (scale, bias, activation) with the TMEM loads software-pipelined one chunk ahead;
+// FULL = true : + row-group bias, LayerNorm, residual (staged through shared memory).
+template <int KIND, int BN, bool FULL>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY, const GemmParams p) {
@@ -185,52 +187,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             dst[it] = __ldg(reinterpret_cast<const float4*>(p.residual + (int64_t)grow * p.ldres + gcol + ch * 4));
         }
       };
-      const bool stage_res = p.tma_store && p.residual != nullptr;
-      if (stage_res) fetch_residual(col0, rnext);
+      const bool stage_res = FULL && p.tma_store && p.residual != nullptr;
+      if constexpr (FULL) { if (stage_res) fetch_residual(col0, rnext); }
       float mean = 0.f, rstd = 1.f;
-      if (p.epi & GF_EPI_LN) {
-        // LayerNorm over the full row (BN == N): two extra sweeps over TMEM (mean, then centred variance)
-        float s = 0.f;
-        for (int c = 0; c < BN; c += 32) {
-          float v[32];
-          ptx::tmem_ld_32x32(t_row + c, v);
-          ptx::tmem_ld_wait();
+      if constexpr (FULL) {
+        if (p.epi & GF_EPI_LN) {
+          // LayerNorm over the full row (BN == N): two extra sweeps over TMEM (mean, then centred variance)
+          float s = 0.f;
+          for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            ptx::tmem_ld_32x32(t_row + c, v);
+            ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) s += v[j] * p.out_scale;
-        }
-        mean = s * (1.f / BN);
-        float q = 0.f;
-        for (int c = 0; c < BN; c += 32) {
-          float v[32];
-          ptx::tmem_ld_32x32(t_row + c, v);
-          ptx::tmem_ld_wait();
+            for (int j = 0; j < 32; ++j) s += v[j] * p.out_scale;
+          }
+          mean = s * (1.f / BN);
+          float q = 0.f;
+          for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            ptx::tmem_ld_32x32(t_row + c, v);
+            ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { const float d = v[j] * p.out_scale - mean; q += d * d; }
+            for (int j = 0; j < 32; ++j) { const float d = v[j] * p.out_scale - mean; q += d * d; }
+          }
+          rstd = rsqrtf(q * (1.f / BN) + 1e-5f);
         }
-        rstd = rsqrtf(q * (1.f / BN) + 1e-5f);
       }
-      for (int c = 0; c < BN; c += 32) {
+      // one 32-column chunk: math on v[] (thread == row), swizzled smem box, grouped TMA store
+      auto emit_chunk = [&](float (&v)[32], int c, bool prefetch_next) {
         const int gc = col0 + c;
-        if (gc >= p.N) break;                              // column tail of the last tile (warp-uniform)
         uint8_t* box = wstage + ((grp & 1) * 2 + pend) * 4096;
         if (p.tma_store) {
           if (pend == 0) {
             if (lane == 0) ptx::bulk_wait_read<1>();       // the group issued 2 groups ago no longer reads these boxes
             __syncwarp();
           }
-          if (stage_res) {
+          if constexpr (FULL) {
+            if (stage_res) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + (lane >> 3), ch = lane & 7;
-              *reinterpret_cast<float4*>(box + rr * 128 + ((ch ^ (rr & 7)) << 4)) = rnext[it];
+              for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + (lane >> 3), ch = lane & 7;
+                *reinterpret_cast<float4*>(box + rr * 128 + ((ch ^ (rr & 7)) << 4)) = rnext[it];
+              }
+              if (c + 32 < BN && gc + 32 < p.N) fetch_residual(gc + 32, rnext);
+              __syncwarp();
             }
-            if (c + 32 < BN && gc + 32 < p.N) fetch_residual(gc + 32, rnext);
-            __syncwarp();
           }
         }
-        float v[32];
-        ptx::tmem_ld_32x32(t_row + c, v);
-        ptx::tmem_ld_wait();
         // Epilogue math as warp-uniform branches around whole 32-element loops: only the taken
         // variant issues instructions (a predicated all-in-one body cost ~280 issue slots per element).
         const bool full = gc + 32 <= p.N;
@@ -249,15 +252,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) if (gc + j < p.N) v[j] += __ldg(p.bias + gc + j);
           }
         }
-        if (rb && row_ok) {
-          if (full) {
+        if constexpr (FULL) {
+          if (rb && row_ok) {
+            if (full) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(rb + gc) + j);
-              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(rb + gc) + j);
+                v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j) if (gc + j < p.N) v[j] += __ldg(rb + gc + j);
             }
-          } else {
-            for (int j = 0; j < 32; ++j) if (gc + j < p.N) v[j] += __ldg(rb + gc + j);
           }
         }
         if (p.epi & GF_EPI_RELU) {
@@ -275,19 +280,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) if (gc + j < p.act_cols) v[j] = v[j] > 0.f ? v[j] + 1.f : __expf(v[j]);
           }
         }
-        if (p.epi & GF_EPI_LN) {                            // BN == N: chunks are always full
+        if constexpr (FULL) {
+          if (p.epi & GF_EPI_LN) {                            // BN == N: chunks are always full
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + gc) + j);
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta + gc) + j);
-            v[4 * j] = (v[4 * j] - mean) * rstd * g4.x + b4.x;
-            v[4 * j + 1] = (v[4 * j + 1] - mean) * rstd * g4.y + b4.y;
-            v[4 * j + 2] = (v[4 * j + 2] - mean) * rstd * g4.z + b4.z;
-            v[4 * j + 3] = (v[4 * j + 3] - mean) * rstd * g4.w + b4.w;
+            for (int j = 0; j < 8; ++j) {
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + gc) + j);
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta + gc) + j);
+              v[4 * j] = (v[4 * j] - mean) * rstd * g4.x + b4.x;
+              v[4 * j + 1] = (v[4 * j + 1] - mean) * rstd * g4.y + b4.y;
+              v[4 * j + 2] = (v[4 * j + 2] - mean) * rstd * g4.z + b4.z;
+              v[4 * j + 3] = (v[4 * j + 3] - mean) * rstd * g4.w + b4.w;
+            }
           }
-        }
-        if (rrow && row_ok && !p.tma_store) {
-          for (int j = 0; j < 32; ++j) if (gc + j < p.N) v[j] += __ldg(rrow + gc + j);
+          if (rrow && row_ok && !p.tma_store) {
+            for (int j = 0; j < 32; ++j) if (gc + j < p.N) v[j] += __ldg(rrow + gc + j);
+          }
         }
         if (p.tma_store) {
           uint8_t* myrow = box + lane * 128;
@@ -295,9 +302,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 8; ++j) {
             float4* dst = reinterpret_cast<float4*>(myrow + ((j ^ (lane & 7)) << 4));
             float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            if (p.residual) { const float4 r4 = *dst; o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
+            if constexpr (FULL) {
+              if (stage_res) { const float4 r4 = *dst; o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
+            }
             *dst = o;
           }
+          // v[] is consumed: start the TMEM load of the next chunk so that its latency hides behind the
+          // proxy fence / TMA store issue below
+          if (prefetch_next) ptx::tmem_ld_32x32(t_row + c + 32, v);
           pend_col[pend++] = gc;
           const bool last = (c + 32 >= BN) || (gc + 32 >= p.N);
           if (pend == 2 || last) {                         // one proxy fence + commit per two boxes
@@ -312,8 +324,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             pend = 0;
             ++grp;
           }
-        } else if (row_ok) {
-          for (int j = 0; j < 32; ++j) if (gc + j < p.N) yrow[gc + j] = v[j];
+        } else {
+          if (row_ok) {
+            for (int j = 0; j < 32; ++j) if (gc + j < p.N) yrow[gc + j] = v[j];
+          }
+          if (prefetch_next) ptx::tmem_ld_32x32(t_row + c + 32, v);
+        }
+      };
+      const int nch = min(BN / 32, (p.N - col0 + 31) / 32);    // live 32-column chunks of this tile (warp-uniform)
+      {
+        float v[32];
+        ptx::tmem_ld_32x32(t_row, v);
+#pragma unroll 1
+        for (int ci = 0; ci < nch; ++ci) {
+          ptx::tmem_ld_wait();
+          emit_chunk(v, ci * 32, ci + 1 < nch);
         }
       }
       ptx::tc_fence_before();
@@ -389,12 +414,12 @@ int make_out_tmap(CUtensorMap* m, float* base, int64_t n, int64_t rows, int64_t 
   return GF_OK;
 }
 
-template <int KIND, int BN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& ty,
+template <int KIND, int BN, bool FULL>
+static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& ty,
                        const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<KIND, BN>;
+  auto kern = gemm_tc_kernel<KIND, BN, FULL>;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
       return gf_set_error(GF_ERR_LAUNCH, "cudaFuncSetAttribute(smem) failed");
@@ -407,6 +432,14 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta2, const CUte
   g_launches++;
   GF_CHECK_LAUNCH();
   return GF_OK;
+}
+
+template <int KIND, int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& ty,
+                       const GemmParams& p, cudaStream_t stream) {
+  const bool full = (p.epi & GF_EPI_LN) || p.residual != nullptr || p.rowbias != nullptr || !p.tma_store;
+  if (full) return launch_gemm_t<KIND, BN, true>(ta, ta2, tb, ty, p, stream);
+  return launch_gemm_t<KIND, BN, false>(ta, ta2, tb, ty, p, stream);
 }
 
 }  // namespace gf

@@ -146,6 +146,12 @@ class PackedWeights:
             t["layer2_outconv2.3"] = tc("layer2_outconv2.3")
             t["layer1_outconv2.0"] = tc("layer1_outconv2.0", "layer1_outconv2.1")
             t["layer1_outconv2.3"] = tc("layer1_outconv2.3")
+            # stem: BN-folded 7x7 weights, [49 taps][128] with the kernel's channel permutation
+            w7, b7 = _fold_bn(sd["backbone.conv1.weight"], bsd, "bn1")
+            assert w7.shape == (128, 1, 7, 7)
+            wt7 = w7.reshape(128, 49).t().contiguous()                                # [49, 128] natural channel order
+            perm = torch.tensor([j * 32 + cg * 4 + e for j in range(4) for cg in range(8) for e in range(4)])
+            t["stem"] = (wt7[:, perm].contiguous().to(device), b7.float().to(device))
             self.bb_tc = t
         self._pe: Dict[Tuple[int, int, int], torch.Tensor] = {}
 
@@ -225,8 +231,7 @@ def backbone_forward_tc(pw: PackedWeights, img: torch.Tensor) -> Tuple[torch.Ten
             y = conv(p + ".conv1", a, 1)
         return conv(p + ".conv2", y, 1, residual=a)
 
-    x = img.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-    x0 = nhwc(F.relu_(cudnn("conv1", x, 2, 3)))
+    x0 = ops.stem_conv(img.contiguous(), *tc["stem"])
     x1 = block("layer1.1", block("layer1.0", x0))
     x2 = block("layer2.1", block("layer2.0", x1))
     x3 = block("layer3.1", block("layer3.0", x2))
@@ -235,7 +240,7 @@ def backbone_forward_tc(pw: PackedWeights, img: torch.Tensor) -> Tuple[torch.Ten
     x2o = conv("layer2_outconv2.3", conv("layer2_outconv2.0", x2o, 2), 0)
     x1o = ops.upsample_add(nhwc(cudnn("layer1_outconv", nchw(x1), 1, 0)), x2o)
     x1o = conv("layer1_outconv2.3", conv("layer1_outconv2.0", x1o, 2), 0)
-    return x3o.float().contiguous(), x1o.float().contiguous()
+    return x3o.float().contiguous(), x1o          # the fine map stays bf16 NHWC: fine_gather reads it directly
 
 
 # --------------------------------------------------------------------------------------------
@@ -440,7 +445,7 @@ def fine_stage(pw: PackedWeights, fine0: torch.Tensor, fine1: torch.Tensor, g0: 
     cf = fine0.shape[-1]
     stride = hw0_f[0] // hw0_c[0]
     # fine_preprocess.py:41-72.  merge_feat(cat[win, ctx]) = win Wa^T + (ctx Wb^T + b)
-    win = torch.empty((2 * m, ww, cf), device=dev)
+    win = torch.empty((2 * m, ww, cf), device=dev, dtype=torch.float32)
     ops.fine_gather(fine0, b_ids, i_ids, hw0_c[1], stride, window, out=win[:m])
     ops.fine_gather(fine1, b_ids, j_ids, hw1_c[1], stride, window, out=win[m:])
     ctx = torch.empty((2 * m, g0.shape[-1]), device=dev)

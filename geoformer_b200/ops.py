@@ -151,6 +151,15 @@ def conv3x3(x: torch.Tensor, wt: torch.Tensor, bias: torch.Tensor, residual: Opt
     return y
 
 
+def stem_conv(img: torch.Tensor, wperm: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """7x7/s2 stem + folded BN + ReLU: fp32 [b,1,h,w] -> NHWC bf16 [b,h/2,w/2,128]."""
+    assert img.dtype == torch.float32 and img.is_contiguous() and img.shape[1] == 1
+    b, _, h, w = img.shape
+    out = torch.empty((b, (h - 1) // 2 + 1, (w - 1) // 2 + 1, 128), device=img.device, dtype=torch.bfloat16)
+    _call("gf_stem_conv7x7_bf16", img.data_ptr(), wperm.data_ptr(), bias.data_ptr(), out.data_ptr(), b, h, w, _stream())
+    return out
+
+
 def upsample_add(lateral: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
     """lateral [b,h,w,c] + bilinear_upsample(src [b,hs,ws,c]) (align_corners=True), NHWC bf16."""
     assert lateral.is_contiguous() and src.is_contiguous() and lateral.dtype == src.dtype == torch.bfloat16
@@ -221,8 +230,9 @@ def dual_softmax_(sim: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.
     dev = sim.device
     rmax = torch.empty((n, l), device=dev); rsum = torch.empty((n, l), device=dev)
     cmax = torch.empty((n, s), device=dev); csum = torch.empty((n, s), device=dev)
+    ws = torch.empty(_lib.load().gf_dual_softmax_workspace_floats(n, l, s), device=dev, dtype=torch.float32)
     _call("gf_dual_softmax_stats", sim.data_ptr(), n, l, s, rmax.data_ptr(), rsum.data_ptr(), cmax.data_ptr(),
-              csum.data_ptr(), _stream())
+              csum.data_ptr(), ws.data_ptr(), _stream())
     crmax = torch.empty((n, l), device=dev); ccmax = torch.empty((n, s), device=dev)
     _call("gf_dual_softmax_conf", sim.data_ptr(), n, l, s, rmax.data_ptr(), rsum.data_ptr(), cmax.data_ptr(),
               csum.data_ptr(), crmax.data_ptr(), ccmax.data_ptr(), _stream())
@@ -322,7 +332,8 @@ def fine_gather(fine_nhwc: torch.Tensor, b_ids, tok_ids, wc: int, stride: int, w
     m = b_ids.shape[0]
     if out is None:
         out = torch.empty((m, window * window, c), device=fine_nhwc.device, dtype=torch.float32)
-    _call("gf_fine_gather", fine_nhwc.data_ptr(), hf, wf, c, b_ids.data_ptr(), tok_ids.data_ptr(), m, wc, stride,
+    fn = "gf_fine_gather_bf16" if fine_nhwc.dtype == torch.bfloat16 else "gf_fine_gather"
+    _call(fn, fine_nhwc.data_ptr(), hf, wf, c, b_ids.data_ptr(), tok_ids.data_ptr(), m, wc, stride,
               window, out.data_ptr(), _stream())
     return out
 

@@ -71,6 +71,11 @@ int gf_linear_ref(const float* A, const float* A2, const float* W, float* Y, int
 int gf_conv3x3_bf16(const void* x, const void* wt, const float* bias, const void* residual, void* y, int batch, int h,
                     int w, int cin_p, int cout_p, int cin_k, int act, gf_stream_t stream);
 
+/* Backbone stem (resnet_fpn.py:58-60,102): 7x7 / stride 2 / pad 3 conv of the 1-channel fp32 image + folded BN +
+ * ReLU -> NHWC bf16 [b, h/2, w/2, 128].  wperm [49][128] holds, for tap t, channel (j*32 + cg*4 + e) at
+ * position ((j*8 + cg)*4 + e). */
+int gf_stem_conv7x7_bf16(const float* img, const float* wperm, const float* bias, void* out, int batch, int h, int w,
+                         gf_stream_t stream);
 /* FPN top-down merge (resnet_fpn.py:108-115): out = lateral + bilinear(src -> h x w, align_corners=True); NHWC bf16 */
 int gf_upsample_add_bf16(const void* lateral, const void* src, void* out, int batch, int h, int w, int hs, int ws,
                          int c, gf_stream_t stream);
@@ -109,9 +114,12 @@ int gf_similarity_f16x3(const void* a3, const void* b3, float* sim, int n, int l
 /* sim from fp32 features with plain FFMA (accuracy reference) */
 int gf_similarity_ref(const float* f0, const float* f1, float* sim, int n, int l, int s, int c, float in_scale,
                       float out_scale, gf_stream_t stream);
-/* row (dim=2) and column (dim=1) soft-max statistics of sim: max and sum(exp(x-max)) */
+/* row (dim=2) and column (dim=1) soft-max statistics of sim: max and sum(exp(x-max)).  With a workspace of
+ * gf_dual_softmax_workspace_floats() floats both are produced from ONE read of sim (tile partials + merge);
+ * workspace == NULL selects the two-sweep kernels. */
+int64_t gf_dual_softmax_workspace_floats(int n, int l, int s);
 int gf_dual_softmax_stats(const float* sim, int n, int l, int s, float* row_max, float* row_sum, float* col_max,
-                          float* col_sum, gf_stream_t stream);
+                          float* col_sum, float* workspace, gf_stream_t stream);
 /* conf = softmax(sim,1)*softmax(sim,2), written in place over sim; also emits per-row / per-column max of conf */
 int gf_dual_softmax_conf(float* sim_conf, int n, int l, int s, const float* row_max, const float* row_sum,
                          const float* col_max, const float* col_sum, float* conf_row_max, float* conf_col_max,
@@ -180,6 +188,9 @@ int gf_select_rows(float* dst, const float* src, const int* flag, int n, int64_t
 /* 5x5 (stride 4, pad 2) windows of the NHWC fine map around coarse tokens: out[m, w*w, c] */
 int gf_fine_gather(const float* fine_nhwc, int hf, int wf, int c, const int64_t* b_ids, const int64_t* tok_ids,
                    int64_t m, int wc, int stride, int window, float* out, gf_stream_t stream);
+/* same, reading a bf16 NHWC fine map (native output of the tcgen05 backbone) */
+int gf_fine_gather_bf16(const void* fine_nhwc, int hf, int wf, int c, const int64_t* b_ids, const int64_t* tok_ids,
+                        int64_t m, int wc, int stride, int window, float* out, gf_stream_t stream);
 /* rows out[m,:] = feat[b_ids[m], tok_ids[m], :] */
 int gf_gather_rows(const float* feat, int64_t l, int c, const int64_t* b_ids, const int64_t* tok_ids, int64_t m,
                    float* out, gf_stream_t stream);

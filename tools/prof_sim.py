@@ -1,0 +1,19 @@
+"""Micro-driver for the ncu --set full capture of the headline kernels at bench size (16 pairs)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from geoformer_b200 import ops
+from geoformer_b200.engine import pack_conv3x3
+dev = torch.device("cuda:0"); ops.ensure_init(dev)
+g = torch.Generator(device="cuda").manual_seed(0)
+f0 = torch.randn(16, 4800, 256, device=dev, generator=g) * 3 + 1.5
+f1 = torch.randn(16, 4800, 256, device=dev, generator=g) * 3 + 1.5
+x = torch.randn(32, 240, 320, 128, device=dev, generator=g).bfloat16()
+wt, bias = pack_conv3x3(torch.randn(128, 128, 3, 3) * 0.03, torch.zeros(128), 128, 128, dev)
+a = torch.randn(153600, 256, device=dev, generator=g)
+w = torch.randn(512, 512, device=dev, generator=g) / 22
+for _ in range(3):
+    sim = ops.similarity(f0, f1, 0.1)
+    y = ops.conv3x3(x, wt, bias, None, 1)
+    h = ops.linear(a, w, a2=a, epi=ops.EPI_RELU)
+torch.cuda.synchronize()
