@@ -255,7 +255,10 @@ def run_ours(args):
             "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
             "algorithmic_flops_per_launch": flops, "issued_flops_per_launch": 3 * flops,
-            "avg_launch_ms": sim_avg_ms, "launches_timed": len(sim_ms), "traffic": None}
+            "avg_launch_ms": sim_avg_ms, "launches_timed": len(sim_ms),
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this size, ncu --set full
+            # (profiles/r01_ncu_headline_raw.txt); algorithmic bytes = packed operands 0.236 GB + fp32 sim 1.475 GB
+            "traffic": 1.653e9 * args.batch / 16, "tensor_pipe_active_pct_ncu": 58.2}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "tf32 projections/attention, split-f16 similarity, bf16 backbone" if args.backbone == "bf16"

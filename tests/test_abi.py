@@ -1,0 +1,78 @@
+"""CPU-side checks of the drop-in boundary: the shared library builds/loads without a GPU and exports exactly the
+symbols that include/geoformer_b200.h declares; the ctypes table mirrors the header; the Python surface keeps the
+reference's module paths, config keys and checkpoint schema; the product has no CPU fallback."""
+import copy
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "geoformer_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from geoformer_b200 import _lib, build
+    build.build()
+    lib = _lib.load()                      # dlopen + bind; no compute call (no GPU here)
+    declared = _header_functions()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert sorted(_lib.SIGNATURES) == declared, set(_lib.SIGNATURES) ^ set(declared)
+    assert lib.gf_abi_version() == 1
+    assert lib.gf_linattn_partial_floats(2, 4800, 8, 32) == 2 * 8 * 19 * (32 * 32 + 32)
+
+
+def test_header_argument_counts_match_ctypes_table():
+    from geoformer_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "geoformer_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    for name, (_, args) in _lib.SIGNATURES.items():
+        m = re.search(r"\b%s\s*\(([^;]*?)\)\s*;" % name, src, flags=re.S)
+        assert m, name
+        params = [p for p in m.group(1).split(",") if p.strip() and p.strip() != "void"]
+        assert len(params) == len(args), (name, len(params), len(args))
+
+
+def test_python_surface_matches_reference():
+    from geoformer_b200.model.full_model import GeoFormer
+    from geoformer_b200.model.geo_config import default_cfg as geo_cfg
+    from geoformer_b200.model.loftr_src.loftr.utils.cvpr_ds_config import default_cfg
+    assert set(geo_cfg) == {"layer_names", "nhead", "coarse_thr", "fine_temperature", "fine_thr", "window_size", "topk"}
+    assert geo_cfg["coarse_thr"] == 0.2 and geo_cfg["nhead"] == 4 and geo_cfg["layer_names"] == ["self", "cross"] * 2
+    assert default_cfg["coarse"]["layer_names"] == ["self", "cross"] * 4 and default_cfg["match_coarse"]["border_rm"] == 2
+    conf = copy.deepcopy(default_cfg)
+    g = dict(geo_cfg); g["coarse_thr"] = 0.33
+    m = GeoFormer(conf, g)
+    assert conf["match_coarse"]["thr"] == 0.33                     # full_model.py:31 writes the threshold through
+    sd = m.state_dict()
+    assert len(sd) == 253
+    # wrapper-style load: 'matcher.' prefix, strict=False (geoformer.py:27-30)
+    res = m.load_state_dict({"matcher." + k: v.clone() for k, v in sd.items()}, strict=False)
+    assert not res.missing_keys and not res.unexpected_keys
+
+
+def test_no_cpu_fallback():
+    from geoformer_b200 import ops
+    from geoformer_b200._lib import GeoFormerLibError
+    from geoformer_b200.model.full_model import GeoFormer
+    from geoformer_b200.model.loftr_src.loftr.utils.cvpr_ds_config import default_cfg
+    m = GeoFormer(copy.deepcopy(default_cfg)).eval()
+    with pytest.raises(RuntimeError):
+        m({"image0": torch.zeros(1, 1, 64, 64), "image1": torch.zeros(1, 1, 64, 64)})
+    with pytest.raises((GeoFormerLibError, AssertionError)):
+        ops.similarity(torch.zeros(1, 8, 256), torch.zeros(1, 8, 256), 0.1)
+
+
+def test_product_does_not_import_oracle():
+    import subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); import geoformer_b200.model.full_model, geoformer_b200.pipeline, "
+            "geoformer_b200.dist; assert not any(m.startswith('oracle') for m in sys.modules), 'oracle imported'") % ROOT
+    subprocess.run([sys.executable, "-c", code], check=True)
