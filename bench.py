@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--regime", default="dense", choices=["dense", "shift"])
     ap.add_argument("--backbone", default=os.environ.get("GF_BACKBONE", "bf16"))
     ap.add_argument("--depth", type=int, default=2, help="batches in flight (MatchPipeline); 1 = plain serial forward")
+    ap.add_argument("--hw", default=None, help="HxW override for informational runs of the other BASELINE configs (e.g. 768x768)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stage-times", action="store_true", help="print a per-stage CUDA-event breakdown to stderr")
     return ap.parse_args()
@@ -298,6 +299,9 @@ def stage_breakdown(model, batch):
 
 if __name__ == "__main__":
     a = parse()
+    if a.hw:
+        H, W = [int(v) for v in a.hw.lower().split("x")]
+        METRIC = f"pairs_per_sec_{W}x{H}"
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -165,3 +165,25 @@ def test_backbone_tcgen05_vs_cudnn_and_fp32():
     assert tc_c.shape == ref_c.shape and tc_f.shape == ref_f.shape
     e_tc, e_cd = max(rel(tc_c, ref_c), rel(tc_f, ref_f)), max(rel(cd_c, ref_c), rel(cd_f, ref_f))
     assert e_tc <= 3e-2 and e_tc <= 2.0 * e_cd + 5e-3, (e_tc, e_cd)
+
+
+@pytest.mark.parametrize("hw", [(768, 768), (840, 840)])
+def test_fire_and_megadepth_shapes(hw):
+    """BASELINE configs 4/5: FIRE-shaped 768x768 (L = 9216) and MegaDepth-shaped 840x840 (L = 11025, odd: exercises
+    the non-TMA store path of the similarity GEMM and partial conv tiles).  Accurate mode vs the CPU oracle:
+    >= 99 % of the final matches identical."""
+    sd = synth.make_state_dict(0)
+    model = build_model(sd, 0.0, backbone="fp32", linear="ref", sim="ref")
+    model.materialize = False
+    im0, im1 = synth.make_pairs(1, hw[0], hw[1], "shift", 5)
+    data = model({"image0": im0.cuda(), "image1": im1.cuda()})
+    with torch.no_grad():
+        want = O.forward(sd, im0, im1, dict(coarse_thr=0.0))
+    got, ref = _match_set(data), _match_set(want)
+    assert len(ref) > 50
+    assert len(got & ref) >= 0.99 * len(ref), (len(got), len(ref), len(got & ref))
+    # product precision on the same input: runs, finite, similar match count
+    model2 = build_model(sd, 0.0, backbone="bf16", linear="tf32", sim="f16x3")
+    model2.materialize = False
+    d2 = model2({"image0": im0.cuda(), "image1": im1.cuda()})
+    assert torch.isfinite(d2["mconf"]).all() and abs(d2["mkpts0_f"].shape[0] - len(ref)) <= 0.5 * len(ref) + 20
