@@ -14,6 +14,7 @@
 #include "ptx.cuh"
 
 #include <atomic>
+#include <cstdlib>
 
 namespace gf {
 
@@ -34,6 +35,7 @@ struct GemmParams {
   float out_scale;
   const int* m_dev;
   int tiles_n;
+  int cluster;     // 1 or 2 CTAs per cluster (2: B operand multicast between vertically adjacent M tiles)
   int tma_store;   // 1: epilogue stages 32x32 boxes in swizzled smem and TMA-stores them (needs ldy % 4 == 0)
 };
 
@@ -58,7 +60,11 @@ __device__ __forceinline__ float fast_tanh(float x) {
 
 // FULL = false: lean epilogue (scale, bias, activation) with the TMEM loads software-pipelined one chunk ahead;
 // FULL = true : + row-group bias, LayerNorm, residual (staged through shared memory).
-template <int KIND, int BN, bool FULL>
+// CL = 2 (opt-in, env GF_CLUSTER2): two CTAs of a cluster work on vertically adjacent M tiles of the same N tile and
+// share the B operand: each CTA TMA-loads half of every B box and multicasts it into both shared memories, cutting
+// the per-SM L2 -> smem operand traffic from (A + B) to (A + B/2) per k-block.  Measured on B200: no gain (the
+// short-K GEMMs of this model are bound by their HBM output stream, not by the operand feed), so CL = 1 is default.
+template <int KIND, int BN, bool FULL, int CL>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY, const GemmParams p) {
@@ -78,8 +84,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   int m_live = p.M;
   if (p.m_dev != nullptr) m_live = min(p.M, max(0, *p.m_dev));
-  const int tiles_m = (m_live + kBM - 1) / kBM;
+  const int cta_rank = (CL == 2) ? (int)ptx::cluster_ctarank() : 0;
+  const int tiles_m = ((m_live + kBM - 1) / kBM + CL - 1) / CL;          // M-tile groups (pairs when CL == 2)
   const int total_tiles = p.batches * tiles_m * p.tiles_n;
+  const int t_first = blockIdx.x / CL, t_step = gridDim.x / CL;
   const int kblocks = p.kblocks1 + p.kblocks2;
 
   if (warp == 0 && lane == 0) {
@@ -90,7 +98,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < Cfg::kStages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+      for (int i = 0; i < Cfg::kStages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], CL); }
       for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], 4); }
       ptx::fence_barrier_init();
     }
@@ -98,7 +106,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CL == 2) ptx::cluster_sync(); else __syncthreads();   // peers must see initialised barriers
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -106,10 +114,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = t_first; t < total_tiles; t += t_step) {
         const int n_blk = t % p.tiles_n;
         const int rest = t / p.tiles_n;
-        const int m_blk = rest % tiles_m;
+        const int m_blk = (rest % tiles_m) * CL + cta_rank;
         const int batch = rest / tiles_m;
         for (int kb = 0; kb < kblocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -118,7 +126,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           if (kb < p.kblocks1) ptx::tma_load_3d(sa, &tmA, &full_bar[stage], kb * BKE, m_blk * kBM, batch);
           else                 ptx::tma_load_3d(sa, &tmA2, &full_bar[stage], (kb - p.kblocks1) * BKE, m_blk * kBM, batch);
-          ptx::tma_load_3d(sb, &tmB, &full_bar[stage], kb * BKE, n_blk * BN, batch);
+          if constexpr (CL == 2) {
+            ptx::tma_load_3d_mcast(sb + cta_rank * (BN / 2) * 128, &tmB, &full_bar[stage], kb * BKE,
+                                   n_blk * BN + cta_rank * (BN / 2), batch, (uint16_t)0x3);
+          } else {
+            ptx::tma_load_3d(sb, &tmB, &full_bar[stage], kb * BKE, n_blk * BN, batch);
+          }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -129,7 +142,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t idesc = ptx::umma_idesc(KIND == 0 ? 2 : 0, kBM, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = t_first; t < total_tiles; t += t_step) {
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -145,7 +158,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // advance 32 bytes of K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
             ptx::umma<KIND>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
           }
-          ptx::umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+          if constexpr (CL == 2) ptx::umma_commit_mcast(&empty_bar[stage], (uint16_t)0x3);   // frees the slot in both CTAs
+          else ptx::umma_commit(&empty_bar[stage]);     // frees the smem slot when these MMAs retire
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
         ptx::umma_commit(&tmem_full[acc]);              // accumulator complete -> epilogue
@@ -159,10 +173,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t grp = 0;          // TMA-store group counter: 2 boxes per fence / commit, ring of 2 groups per warp
     int pend = 0;
     int pend_col[2] = {0, 0};
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = t_first; t < total_tiles; t += t_step) {
       const int n_blk = t % p.tiles_n;
       const int rest = t / p.tiles_n;
-      const int m_blk = rest % tiles_m;
+      const int m_blk = (rest % tiles_m) * CL + cta_rank;
       const int batch = rest / tiles_m;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
@@ -350,7 +364,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CL == 2) ptx::cluster_sync(); else __syncthreads();   // no CTA leaves while its peer may still multicast into it
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -414,21 +428,31 @@ int make_out_tmap(CUtensorMap* m, float* base, int64_t n, int64_t rows, int64_t 
   return GF_OK;
 }
 
-template <int KIND, int BN, bool FULL>
+template <int KIND, int BN, bool FULL, int CL>
 static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& ty,
-                       const GemmParams& p, cudaStream_t stream) {
+                         const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<KIND, BN, FULL>;
+  auto kern = gemm_tc_kernel<KIND, BN, FULL, CL>;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
       return gf_set_error(GF_ERR_LAUNCH, "cudaFuncSetAttribute(smem) failed");
     attr_set = true;
   }
-  const int64_t tiles = (int64_t)p.batches * gf_cdiv(p.M, kBM) * p.tiles_n;
-  if (tiles == 0) return GF_OK;
-  const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
-  kern<<<grid, 192, Cfg::kSmemBytes, stream>>>(ta, ta2, tb, ty, p);
+  const int64_t groups = (int64_t)p.batches * gf_cdiv(gf_cdiv(p.M, kBM), CL) * p.tiles_n;
+  if (groups == 0) return GF_OK;
+  const int64_t max_groups = g_num_sms / CL;
+  const int grid = (int)(groups < max_groups ? groups : max_groups) * CL;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, kern, ta, ta2, tb, ty, p) != cudaSuccess) {
+    cudaError_t e = cudaGetLastError();
+    return gf_set_error(GF_ERR_LAUNCH, cudaGetErrorString(e));
+  }
   g_launches++;
   GF_CHECK_LAUNCH();
   return GF_OK;
@@ -438,8 +462,12 @@ template <int KIND, int BN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& ty,
                        const GemmParams& p, cudaStream_t stream) {
   const bool full = (p.epi & GF_EPI_LN) || p.residual != nullptr || p.rowbias != nullptr || !p.tma_store;
-  if (full) return launch_gemm_t<KIND, BN, true>(ta, ta2, tb, ty, p, stream);
-  return launch_gemm_t<KIND, BN, false>(ta, ta2, tb, ty, p, stream);
+  if (p.cluster == 2) {
+    if (full) return launch_gemm_t<KIND, BN, true, 2>(ta, ta2, tb, ty, p, stream);
+    return launch_gemm_t<KIND, BN, false, 2>(ta, ta2, tb, ty, p, stream);
+  }
+  if (full) return launch_gemm_t<KIND, BN, true, 1>(ta, ta2, tb, ty, p, stream);
+  return launch_gemm_t<KIND, BN, false, 1>(ta, ta2, tb, ty, p, stream);
 }
 
 }  // namespace gf
@@ -462,13 +490,15 @@ extern "C" int gf_linear_tf32(const float* A, const float* A2, const float* W, f
   int rc;
   if ((rc = make_tmap(&ta, A, 4, K1, M, 1, K1, 0, kBM))) return rc;
   if (K2 > 0) { if ((rc = make_tmap(&ta2, A2, 4, K2, M, 1, K2, 0, kBM))) return rc; } else ta2 = ta;
-  if ((rc = make_tmap(&tb, W, 4, K1 + K2, N, 1, K1 + K2, 0, BN))) return rc;
+  const int cl = (M > kBM && getenv("GF_CLUSTER2") != nullptr) ? 2 : 1;
+  if ((rc = make_tmap(&tb, W, 4, K1 + K2, N, 1, K1 + K2, 0, BN / cl))) return rc;
   GemmParams p{};
   p.Y = Y; p.ldy = N; p.y_batch_stride = 0; p.M = (int)M; p.N = N; p.batches = 1;
   p.kblocks1 = K1 / 32; p.kblocks2 = K2 / 32; p.epi = epi; p.act_cols = act_cols;
   p.bias = bias; p.rowbias = rowbias; p.rowbias_group = rowbias_group > 0 ? rowbias_group : 1;
   p.gamma = gamma; p.beta = beta; p.residual = residual; p.ldres = N; p.out_scale = 1.f; p.m_dev = m_dev;
   p.tiles_n = N / BN;
+  p.cluster = cl;
   p.tma_store = 1;
   CUtensorMap ty;
   if ((rc = make_out_tmap(&ty, Y, N, M, 1, N, 0))) return rc;
@@ -483,11 +513,13 @@ extern "C" int gf_similarity_f16x3(const void* a3, const void* b3, float* sim, i
   int rc;
   constexpr int BN = 256;
   if ((rc = make_tmap(&ta, a3, 2, c3, l, n, c3, (int64_t)l * c3, kBM))) return rc;
-  if ((rc = make_tmap(&tb, b3, 2, c3, s, n, c3, (int64_t)s * c3, BN))) return rc;
+  const int cl = (l > kBM && getenv("GF_CLUSTER2") != nullptr) ? 2 : 1;
+  if ((rc = make_tmap(&tb, b3, 2, c3, s, n, c3, (int64_t)s * c3, BN / cl))) return rc;
   GemmParams p{};
   p.Y = sim; p.ldy = s; p.y_batch_stride = (int64_t)l * s; p.M = l; p.N = s; p.batches = n;
   p.kblocks1 = c3 / 64; p.kblocks2 = 0; p.epi = 0; p.act_cols = 0; p.rowbias_group = 1; p.ldres = s;
   p.out_scale = out_scale; p.tiles_n = gf_cdiv(s, BN);
+  p.cluster = cl;
   p.tma_store = (s % 4 == 0) ? 1 : 0;
   CUtensorMap ty = ta;
   if (p.tma_store && (rc = make_out_tmap(&ty, sim, s, l, n, s, (int64_t)l * s))) return rc;
@@ -506,12 +538,13 @@ extern "C" int gf_gemm_tf32_batched(const float* A, int64_t lda, int64_t a_batch
   CUtensorMap ta, tb, ty;
   int rc;
   if ((rc = make_tmap(&ta, A, 4, K, M, batches, lda, batches == 1 ? lda * M : a_batch_stride, kBM))) return rc;
-  if ((rc = make_tmap(&tb, B, 4, K, N, batches, ldb, batches == 1 ? ldb * N : b_batch_stride, BN))) return rc;
+  const int cl = (M > kBM && getenv("GF_CLUSTER2") != nullptr) ? 2 : 1;
+  if ((rc = make_tmap(&tb, B, 4, K, N, batches, ldb, batches == 1 ? ldb * N : b_batch_stride, BN / cl))) return rc;
   if ((rc = make_out_tmap(&ty, Y, N, M, batches, ldy, batches == 1 ? ldy * M : y_batch_stride))) return rc;
   GemmParams p{};
   p.Y = Y; p.ldy = ldy; p.y_batch_stride = y_batch_stride; p.M = M; p.N = N; p.batches = batches;
   p.kblocks1 = K / 32; p.kblocks2 = 0; p.epi = 0; p.act_cols = 0; p.rowbias_group = 1; p.ldres = ldy;
-  p.out_scale = out_scale; p.tiles_n = gf_cdiv(N, BN); p.tma_store = 1;
+  p.out_scale = out_scale; p.tiles_n = gf_cdiv(N, BN); p.tma_store = 1; p.cluster = cl;
   if (BN == 256) return launch_gemm<0, 256>(ta, ta, tb, ty, p, (cudaStream_t)stream);
   return launch_gemm<0, 128>(ta, ta, tb, ty, p, (cudaStream_t)stream);
 }
