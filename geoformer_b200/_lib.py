@@ -37,6 +37,9 @@ SIGNATURES = {
     "gf_dual_softmax_conf": (I, [P, I, I, I, P, P, P, P, P, P, P]),
     "gf_conf_row_col_max": (I, [P, I, I, I, P, P, P]),
     "gf_mnn_select": (I, [P, I, I, I, F, I, I, I, I, I, P, P, P, P, P]),
+    "gf_coarse_match_fused_workspace_bytes": (L, [I, I, I]),
+    "gf_coarse_match_fused": (I, [P, P, I, I, I, I, F, F, I, I, I, I, I, P, P, P, P]),
+    "gf_coarse_match_fused_pass": (I, [P, P, I, I, I, I, F, P, I, P]),
     "gf_compact_coarse": (I, [P, P, I, I, I, I, F, P, P, P, P, P, P, P, P, L, P]),
     "gf_geo_window_table": (I, [P, P, I, I, I, I, I, I, I, I, P, P]),
     "gf_geo_self_attention": (I, [P, I, P, I, P, I, P, I, I, I, I, P, P, I, P]),

@@ -1,0 +1,354 @@
+// Fused dual-softmax coarse matching (utils/coarse_matching.py:110-125, 161-188) without materialising the
+// L x S similarity / confidence matrix.  Two tcgen05 passes over the same split-fp16 operands (K = 3C):
+//
+//   pass 0 (stats): S tile in TMEM -> per-row online (max, sum 2^x) kept in the epilogue thread (thread == row) and
+//                   per-column (max, sum) of each warp's 32 x 32 sub-block via a swizzled smem transpose;
+//                   partials rowp[n][l][tiles_n], colp[n][tiles_m*4][s]  (log2 domain)
+//   pass 1 (conf):  S tile recomputed (bit-identical) -> conf = 2^(2x - rmax_i - cmax_j) * rinv_i * cinv_j (ONE exp per
+//                   element) -> per-row best (conf, first j) merged with a 64-bit atomicMax, per-column best conf with
+//                   a 32-bit atomicMax.
+//   then mnn_from_best_kernel applies threshold / border / mutual check on vectors.
+// Nothing of size L x S touches HBM: per call the kernels read the packed operands (2 x n*L*3C fp16) and write
+// O(n*(L+S)*tiles) partials, so the similarity contraction is tensor-bound instead of bound by a 1.5 GB fp32 store.
+// Tie caveat (documented in DESIGN.md): among exactly equal row maxima the smallest j is taken BEFORE the column check,
+// whereas the reference takes the first j that also passes it; the materialised path (gf_mnn_select) keeps the
+// reference order bit-exactly and is what the parity tests of the MNN semantics use.
+#include "common.cuh"
+#include "ptx.cuh"
+
+#include <atomic>
+
+namespace gf {
+extern std::atomic<int64_t> g_launches;
+
+namespace sf {
+constexpr int kBM = 128, kBN = 256, kStages = 4;
+constexpr int kStageA = kBM * 128, kStageB = kBN * 128, kStage = kStageA + kStageB;
+constexpr int kEpiWarps = 8;            // two epilogue warps per TMEM lane quadrant (each takes 128 of the 256 columns):
+                                        // with one warp per scheduler every dependency stall of the softmax math was exposed
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kStaging = kEpiWarps * 4096;
+constexpr int kSmem = kStages * kStage + kStaging + 1024 + 256;
+constexpr int kTmemCols = 512;
+}  // namespace sf
+
+struct SimFusedParams {
+  int n, l, s, kblocks, tiles_m, tiles_n;
+  float scale2;                 // out_scale * log2(e): logits in the log2 domain
+  float2* rowp; float2* colp;   // pass 0 outputs
+  const float* row_m2; const float* row_inv; const float* col_m2; const float* col_inv;   // pass 1 inputs
+  unsigned long long* row_best; unsigned* col_best;                                        // pass 1 outputs
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(sf::kThreads, 1)
+sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SimFusedParams p) {
+  using namespace sf;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + kStages * kStage;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStaging);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.n * p.tiles_m * p.tiles_n;
+
+  if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmB); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < kStages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+      for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], kEpiWarps); }
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n_blk = t % p.tiles_n, rest = t / p.tiles_n;
+        const int m_blk = rest % p.tiles_m, batch = rest / p.tiles_m;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStage;
+          ptx::mbar_expect_tx(&full_bar[stage], kStage);
+          ptx::tma_load_3d(sa, &tmA, &full_bar[stage], kb * 64, m_blk * kBM, batch);
+          ptx::tma_load_3d(sa + kStageA, &tmB, &full_bar[stage], kb * 64, n_blk * kBN, batch);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc(0 /*f16*/, kBM, kBN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kBN;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_addr(smem + stage * kStage);
+          const uint64_t adesc = ptx::umma_desc_sw128(sa), bdesc = ptx::umma_desc_sw128(sa + kStageA);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ptx::umma<1>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int quad = warp & 3;                           // TMEM lane quadrant (hardware: warp id % 4)
+    const int half = (warp - 2) >> 2;                    // which 128-column half of the tile this warp handles
+    uint8_t* box = staging + (warp - 2) * 4096;          // this warp's 32 x 32 fp32 transpose box (128B-swizzled rows)
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int n_blk = t % p.tiles_n, rest = t / p.tiles_n;
+      const int m_blk = rest % p.tiles_m, batch = rest / p.tiles_m;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const int row = m_blk * kBM + quad * 32 + lane;
+      const bool row_ok = row < p.l;
+      const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * kBN + half * (kBN / 2);
+      const int col0 = n_blk * kBN + half * (kBN / 2);
+      const int nch = max(0, min(kBN / 64, (p.s - col0 + 31) / 32));
+      float rm = -INFINITY, rsum = 0.f;                  // MODE 0: running row (max, sum)
+      float r_m2 = 0.f, r_inv = 0.f;                     // MODE 1: final row stats
+      float best = 0.f; int best_j = 0;
+      if constexpr (MODE == 1) {
+        if (row_ok) { r_m2 = p.row_m2[(int64_t)batch * p.l + row]; r_inv = p.row_inv[(int64_t)batch * p.l + row]; }
+      }
+      float v[32];
+      if (nch > 0) ptx::tmem_ld_32x32(t_row, v);
+#pragma unroll 1
+      for (int ci = 0; ci < nch; ++ci) {
+        ptx::tmem_ld_wait();
+        const int gc = col0 + ci * 32;
+        const bool full = gc + 32 <= p.s;
+        float c_m2 = 0.f, c_inv = 0.f;                   // MODE 1: stats of column gc + lane
+        if constexpr (MODE == 1) {
+          if (gc + lane < p.s) { c_m2 = p.col_m2[(int64_t)batch * p.s + gc + lane]; c_inv = p.col_inv[(int64_t)batch * p.s + gc + lane]; }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= p.scale2;
+        if (!full) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (gc + j >= p.s) v[j] = -INFINITY;
+        }
+        if constexpr (MODE == 0) {
+          // ---- row (max, sum): thread-local online update over this chunk
+          float cm = v[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) cm = fmaxf(cm, v[j]);
+          const float nm = fmaxf(rm, cm);
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            a0 += ex2f(v[j] - nm); a1 += ex2f(v[j + 1] - nm); a2 += ex2f(v[j + 2] - nm); a3 += ex2f(v[j + 3] - nm);
+          }
+          rsum = rsum * ex2f(rm - nm) + (a0 + a1) + (a2 + a3);
+          rm = nm;
+          if (!row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = -INFINITY;      // rows beyond L must not enter the column statistics
+          }
+        } else {
+          // ---- conf = softmax_row * softmax_col with one exponential: 2^(2x - rmax - cmax_j) * rinv * cinv_j
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float cmj = __shfl_sync(0xffffffffu, c_m2, j), cij = __shfl_sync(0xffffffffu, c_inv, j);
+            const float cf = row_ok ? ex2f(fmaf(2.f, v[j], -r_m2 - cmj)) * (r_inv * cij) : 0.f;   // -inf logits -> 0
+            v[j] = cf;
+            if (cf > best) { best = cf; best_j = gc + j; }     // strict >: the first j wins inside this row
+          }
+        }
+        // ---- transpose through the swizzled box: lane <- column (gc + lane) over the warp's 32 rows
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(box + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        float x[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) x[r] = *reinterpret_cast<const float*>(box + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+        __syncwarp();
+        if (ci + 1 < nch) ptx::tmem_ld_32x32(t_row + (ci + 1) * 32, v);     // v is free: prefetch the next chunk
+        float m0 = x[0], m1 = x[1], m2 = x[2], m3 = x[3];
+#pragma unroll
+        for (int r = 4; r < 32; r += 4) { m0 = fmaxf(m0, x[r]); m1 = fmaxf(m1, x[r + 1]); m2 = fmaxf(m2, x[r + 2]); m3 = fmaxf(m3, x[r + 3]); }
+        const float cmx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        if constexpr (MODE == 0) {
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+          if (cmx > -INFINITY) {
+#pragma unroll
+            for (int r = 0; r < 32; r += 4) {
+              a0 += ex2f(x[r] - cmx); a1 += ex2f(x[r + 1] - cmx); a2 += ex2f(x[r + 2] - cmx); a3 += ex2f(x[r + 3] - cmx);
+            }
+          }
+          if (gc + lane < p.s)
+            p.colp[((int64_t)batch * p.tiles_m * 4 + m_blk * 4 + quad) * p.s + gc + lane] = make_float2(cmx, (a0 + a1) + (a2 + a3));   // columns are disjoint between the two halves
+        } else {
+          if (gc + lane < p.s && cmx > 0.f) atomicMax(&p.col_best[(int64_t)batch * p.s + gc + lane], __float_as_uint(cmx));
+        }
+      }
+      if (row_ok) {
+        if constexpr (MODE == 0) {
+          p.rowp[((int64_t)batch * p.l + row) * (p.tiles_n * 2) + n_blk * 2 + half] = make_float2(rm, rsum);
+        } else if (best > 0.f) {
+          const unsigned long long key = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)best_j);
+          atomicMax(&p.row_best[(int64_t)batch * p.l + row], key);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, sf::kTmemCols);
+  }
+}
+
+// merge `parts` log2-domain (max, sum) partials -> final max and reciprocal sum (layout arguments as merge_stats_kernel)
+__global__ void merge_stats2_kernel(const float2* __restrict__ in, int64_t elems, int parts, int64_t estride, int64_t kstride,
+                                    int64_t group, int64_t gstride, float* __restrict__ out_m2, float* __restrict__ out_inv) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= elems) return;
+  const int64_t g = e / group, i = e - g * group;
+  const float2* q = in + g * gstride + i * estride;
+  float m = -INFINITY;
+  for (int k = 0; k < parts; ++k) m = fmaxf(m, q[k * kstride].x);
+  float sum = 0.f;
+  for (int k = 0; k < parts; ++k) { const float2 v = q[k * kstride]; if (v.x > -INFINITY) sum += v.y * exp2f(v.x - m); }
+  out_m2[e] = m;
+  out_inv[e] = 1.f / sum;
+}
+
+// threshold + border + mutual check on the per-row / per-column bests (coarse_matching.py:161-188)
+__global__ void mnn_from_best_kernel(const unsigned long long* __restrict__ row_best, const unsigned* __restrict__ col_best,
+                                     int n, int l, int s, float thr, int border, int h0c, int w0c, int h1c, int w1c,
+                                     int* __restrict__ match_j, float* __restrict__ match_conf) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n * l) return;
+  const int b = (int)(idx / l), i = (int)(idx - (int64_t)b * l);
+  const unsigned long long key = row_best[idx];
+  const unsigned cbits = (unsigned)(key >> 32);
+  const int j = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+  const float conf = __uint_as_float(cbits);
+  bool ok = key != 0ull && conf > thr && j >= 0 && j < s && col_best[(int64_t)b * s + j] == cbits;
+  if (ok && border > 0) {
+    const int r0 = i / w0c, c0 = i % w0c, r1 = j / w1c, c1 = j % w1c;
+    ok = r0 >= border && r0 < h0c - border && c0 >= border && c0 < w0c - border &&
+         r1 >= border && r1 < h1c - border && c1 >= border && c1 < w1c - border;
+  }
+  match_j[idx] = ok ? j : -1;
+  match_conf[idx] = ok ? conf : 0.f;
+}
+
+}  // namespace gf
+
+using namespace gf;
+
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int64_t gf_coarse_match_fused_workspace_bytes(int n, int l, int s) {
+  const int64_t tiles_m = gf_cdiv(l, sf::kBM), tiles_n = gf_cdiv(s, sf::kBN);
+  int64_t b = 0;
+  b += align_up((int64_t)n * l * tiles_n * 2 * 8, 256);        // rowp (two column halves per tile)
+  b += align_up((int64_t)n * tiles_m * 4 * s * 8, 256);        // colp
+  b += 2 * align_up((int64_t)n * l * 4, 256) + 2 * align_up((int64_t)n * s * 4, 256);   // row/col m2 + inv
+  b += align_up((int64_t)n * l * 8, 256) + align_up((int64_t)n * s * 4, 256);           // row_best, col_best
+  return b;
+}
+
+// a3 [n,l,c3] / b3 [n,s,c3]: split-fp16 packed operands (gf_pack_split_f16).  Outputs match_j / match_conf [n*l]
+// (feed gf_compact_coarse).  out_scale = 1 / temperature.
+static int coarse_match_fused_impl(const void* a3, const void* b3, int n, int l, int s, int c3, float out_scale,
+                                   float thr, int border, int h0c, int w0c, int h1c, int w1c, void* workspace,
+                                   int* match_j, float* match_conf, gf_stream_t stream, int only_pass);
+
+extern "C" int gf_coarse_match_fused(const void* a3, const void* b3, int n, int l, int s, int c3, float out_scale,
+                                     float thr, int border, int h0c, int w0c, int h1c, int w1c, void* workspace,
+                                     int* match_j, float* match_conf, gf_stream_t stream) {
+  return coarse_match_fused_impl(a3, b3, n, l, s, c3, out_scale, thr, border, h0c, w0c, h1c, w1c, workspace, match_j,
+                                 match_conf, stream, -1);
+}
+
+// profiling hook: launch only the tensor pass `pass` (0 = statistics, 1 = confidences) on an already used workspace
+extern "C" int gf_coarse_match_fused_pass(const void* a3, const void* b3, int n, int l, int s, int c3, float out_scale,
+                                          void* workspace, int pass, gf_stream_t stream) {
+  if (pass != 0 && pass != 1) return gf_set_error(GF_ERR_ARG, "gf_coarse_match_fused_pass: pass must be 0 or 1");
+  return coarse_match_fused_impl(a3, b3, n, l, s, c3, out_scale, 0.f, 0, 1, l, 1, s, workspace, nullptr, nullptr, stream, pass);
+}
+
+static int coarse_match_fused_impl(const void* a3, const void* b3, int n, int l, int s, int c3, float out_scale,
+                                   float thr, int border, int h0c, int w0c, int h1c, int w1c, void* workspace,
+                                   int* match_j, float* match_conf, gf_stream_t stream, int only_pass) {
+  if (n <= 0 || l <= 0 || s <= 0 || c3 <= 0 || (c3 % 64) || h0c * w0c != l || h1c * w1c != s || workspace == nullptr)
+    return gf_set_error(GF_ERR_ARG, "gf_coarse_match_fused: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tiles_m = gf_cdiv(l, sf::kBM), tiles_n = gf_cdiv(s, sf::kBN);
+  uint8_t* w = (uint8_t*)workspace;
+  float2* rowp = (float2*)w; w += align_up((int64_t)n * l * tiles_n * 2 * 8, 256);
+  float2* colp = (float2*)w; w += align_up((int64_t)n * tiles_m * 4 * s * 8, 256);
+  float* row_m2 = (float*)w; w += align_up((int64_t)n * l * 4, 256);
+  float* row_inv = (float*)w; w += align_up((int64_t)n * l * 4, 256);
+  float* col_m2 = (float*)w; w += align_up((int64_t)n * s * 4, 256);
+  float* col_inv = (float*)w; w += align_up((int64_t)n * s * 4, 256);
+  unsigned long long* row_best = (unsigned long long*)w; w += align_up((int64_t)n * l * 8, 256);
+  unsigned* col_best = (unsigned*)w;
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = make_tmap(&ta, a3, 2, c3, l, n, c3, (int64_t)l * c3, sf::kBM))) return rc;
+  if ((rc = make_tmap(&tb, b3, 2, c3, s, n, c3, (int64_t)s * c3, sf::kBN))) return rc;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(sim_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sf::kSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(sim_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sf::kSmem) != cudaSuccess)
+      return gf_set_error(GF_ERR_LAUNCH, "cudaFuncSetAttribute(sim_fused smem) failed");
+    attr = true;
+  }
+  SimFusedParams p{};
+  p.n = n; p.l = l; p.s = s; p.kblocks = c3 / 64; p.tiles_m = tiles_m; p.tiles_n = tiles_n;
+  p.scale2 = out_scale * 1.4426950408889634f;
+  p.rowp = rowp; p.colp = colp; p.row_m2 = row_m2; p.row_inv = row_inv; p.col_m2 = col_m2; p.col_inv = col_inv;
+  p.row_best = row_best; p.col_best = col_best;
+  const int64_t tiles = (int64_t)n * tiles_m * tiles_n;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  if (only_pass == 0) { sim_fused_kernel<0><<<grid, sf::kThreads, sf::kSmem, st>>>(ta, tb, p); g_launches++; GF_CHECK_LAUNCH(); return GF_OK; }
+  if (only_pass == 1) { sim_fused_kernel<1><<<grid, sf::kThreads, sf::kSmem, st>>>(ta, tb, p); g_launches++; GF_CHECK_LAUNCH(); return GF_OK; }
+  sim_fused_kernel<0><<<grid, sf::kThreads, sf::kSmem, st>>>(ta, tb, p);
+  merge_stats2_kernel<<<gf_cdiv((int64_t)n * l, 256), 256, 0, st>>>(rowp, (int64_t)n * l, tiles_n * 2, tiles_n * 2, 1, (int64_t)n * l, 0,
+                                                                   row_m2, row_inv);
+  merge_stats2_kernel<<<gf_cdiv((int64_t)n * s, 256), 256, 0, st>>>(colp, (int64_t)n * s, tiles_m * 4, 1, s, s,
+                                                                   (int64_t)tiles_m * 4 * s, col_m2, col_inv);
+  cudaMemsetAsync(row_best, 0, (size_t)n * l * 8, st);
+  cudaMemsetAsync(col_best, 0, (size_t)n * s * 4, st);
+  sim_fused_kernel<1><<<grid, sf::kThreads, sf::kSmem, st>>>(ta, tb, p);
+  mnn_from_best_kernel<<<gf_cdiv((int64_t)n * l, 256), 256, 0, st>>>(row_best, col_best, n, l, s, thr, border, h0c, w0c, h1c, w1c,
+                                                                    match_j, match_conf);
+  g_launches += 5;
+  GF_CHECK_LAUNCH();
+  return GF_OK;
+}

@@ -20,6 +20,9 @@ from . import ops
 from .ops import EPI_ELU1, EPI_LN, EPI_RELU, EPI_TANH
 
 _POOL: Optional[ThreadPoolExecutor] = None
+# inference default: coarse matching without materialising the L x S matrix (conf_matrix is only produced when
+# model.materialize is set); GF_FUSED_MATCHING=0 selects the materialised kernels
+FUSED_MATCHING = os.environ.get("GF_FUSED_MATCHING", "1") != "0"
 
 
 def _pool() -> ThreadPoolExecutor:
@@ -317,9 +320,12 @@ def fine_layer(lw: dict, x: torch.Tensor, src: torch.Tensor, heads: int) -> torc
 # --------------------------------------------------------------------------------------------
 def coarse_matching(f0: torch.Tensor, f1: torch.Tensor, thr: float, temperature: float, border: int,
                     hw0_i, hw0_c, hw1_c, keep_conf: bool):
+    scale = hw0_i[0] / hw0_c[0]
+    if not keep_conf and ops._SIM_IMPL == "f16x3" and FUSED_MATCHING:
+        matches, counts = ops.coarse_match_fused(f0, f1, temperature, thr, border, hw0_c, hw1_c, scale)
+        return matches, counts, None
     sim = ops.similarity(f0, f1, temperature)
     conf, crmax, ccmax = ops.dual_softmax_(sim)
-    scale = hw0_i[0] / hw0_c[0]
     matches, counts = ops.mutual_nearest(conf, crmax, ccmax, thr, border, hw0_c, hw1_c, scale)
     return matches, counts, (conf if keep_conf else None)
 

@@ -246,6 +246,40 @@ def conf_row_col_max(conf: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     return crmax, ccmax
 
 
+def _compact(mj, mc, n, l, hw0c, hw1c, scale, dev):
+    cap = n * l
+    b_ids = torch.empty(cap, device=dev, dtype=torch.int64); i_ids = torch.empty_like(b_ids); j_ids = torch.empty_like(b_ids)
+    mconf = torch.empty(cap, device=dev); k0 = torch.empty((cap, 2), device=dev); k1 = torch.empty((cap, 2), device=dev)
+    counts = torch.empty(n + 1, device=dev, dtype=torch.int32)
+    _call("gf_compact_coarse", mj.data_ptr(), mc.data_ptr(), n, l, hw0c[1], hw1c[1], float(scale), b_ids.data_ptr(),
+          i_ids.data_ptr(), j_ids.data_ptr(), mconf.data_ptr(), k0.data_ptr(), k1.data_ptr(), counts.data_ptr(),
+          counts.data_ptr() + 4 * n, cap, _stream())
+    counts_h = counts.cpu()
+    total = int(counts_h[n])
+    return dict(b_ids=b_ids[:total], i_ids=i_ids[:total], j_ids=j_ids[:total], m_bids=b_ids[:total],
+                mconf=mconf[:total], mkpts0_c=k0[:total], mkpts1_c=k1[:total]), counts_h[:n]
+
+
+def coarse_match_fused(f0: torch.Tensor, f1: torch.Tensor, temperature: float, thr: float, border: int,
+                       hw0c: Tuple[int, int], hw1c: Tuple[int, int], scale: float):
+    """Whole coarse-matching stage without materialising the L x S matrix (two tcgen05 passes + vector MNN)."""
+    _chk(f0); _chk(f1)
+    n, l, c = f0.shape
+    s = f1.shape[1]
+    dev = f0.device
+    a3 = torch.empty((n, l, 3 * c), device=dev, dtype=torch.float16)
+    b3 = torch.empty((n, s, 3 * c), device=dev, dtype=torch.float16)
+    in_scale = 1.0 / c ** 0.5
+    _call("gf_pack_split_f16", f0.data_ptr(), a3.data_ptr(), n * l, c, in_scale, 0, _stream())
+    _call("gf_pack_split_f16", f1.data_ptr(), b3.data_ptr(), n * s, c, in_scale, 1, _stream())
+    ws = torch.empty(_lib.load().gf_coarse_match_fused_workspace_bytes(n, l, s), device=dev, dtype=torch.uint8)
+    mj = torch.empty((n, l), device=dev, dtype=torch.int32)
+    mc = torch.empty((n, l), device=dev, dtype=torch.float32)
+    _call("gf_coarse_match_fused", a3.data_ptr(), b3.data_ptr(), n, l, s, 3 * c, 1.0 / temperature, float(thr), int(border),
+          hw0c[0], hw0c[1], hw1c[0], hw1c[1], ws.data_ptr(), mj.data_ptr(), mc.data_ptr(), _stream())
+    return _compact(mj, mc, n, l, hw0c, hw1c, scale, dev)
+
+
 def mutual_nearest(conf: torch.Tensor, crmax: torch.Tensor, ccmax: torch.Tensor, thr: float, border: int,
                    hw0c: Tuple[int, int], hw1c: Tuple[int, int], scale: float):
     """MNN + threshold + border + ordered compaction.  Returns dict of exact-size tensors and per-sample counts.

@@ -132,6 +132,18 @@ int gf_conf_row_col_max(const float* conf, int n, int l, int s, float* conf_row_
 int gf_mnn_select(const float* conf, int n, int l, int s, float thr, int border, int h0c, int w0c, int h1c, int w1c,
                   const float* conf_row_max, const float* conf_col_max, int* match_j, float* match_conf,
                   gf_stream_t stream);
+/* Fused inference path of the whole coarse-matching stage: two tcgen05 passes over the packed operands (statistics,
+ * then confidences + per-row / per-column bests), never materialising the L x S matrix; then the mutual / threshold /
+ * border test on vectors.  Fills match_j / match_conf [n*l] exactly like gf_mnn_select (feed gf_compact_coarse).
+ * Exact ties between row maxima resolve to the smallest j before the column test (see sim_fused.cu). */
+int64_t gf_coarse_match_fused_workspace_bytes(int n, int l, int s);
+int gf_coarse_match_fused(const void* a3, const void* b3, int n, int l, int s, int c3, float out_scale, float thr,
+                          int border, int h0c, int w0c, int h1c, int w1c, void* workspace, int* match_j,
+                          float* match_conf, gf_stream_t stream);
+/* profiling hook: launch only tensor pass 0 (statistics) or 1 (confidences) of the fused path on a workspace that a
+ * full gf_coarse_match_fused call has already populated */
+int gf_coarse_match_fused_pass(const void* a3, const void* b3, int n, int l, int s, int c3, float out_scale,
+                               void* workspace, int pass, gf_stream_t stream);
 /* ordered compaction (row-major (b,i), as torch.where) into the reference's output tensors
  * (coarse_matching.py:186-210).  counts[n] per sample, total[1]; capacity = max rows of the outputs. */
 int gf_compact_coarse(const int* match_j, const float* match_conf, int n, int l, int w0c, int w1c, float scale,

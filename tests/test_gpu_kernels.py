@@ -354,3 +354,36 @@ def test_conv3x3_tcgen05(ops, cin, cout, cin_p, cout_p, res, act):
     assert (y[..., cout:] == 0).all()                       # padded channels stay exactly zero
     err = (got - want).abs().max().item()
     assert err <= 1e-2 * want.abs().max().item(), err
+
+
+# ------------------------------------------------------------------------------------------- fused coarse matching
+def _match_lists(d):
+    return torch.stack([d["b_ids"].cpu(), d["i_ids"].cpu(), d["j_ids"].cpu()], 1)
+
+
+@pytest.mark.parametrize("shape,thr", [((2, 192, 192), 0.0), ((2, 300, 333), 0.0), ((1, 4800, 4800), 0.0), ((2, 192, 192), 0.2), ((2, 300, 333), 1e-4)])
+def test_fused_coarse_matching_equals_materialised(ops, golden_dir, shape, thr):
+    """The non-materialising two-pass tcgen05 path must select the same matches as the materialised kernels
+    (same split-fp16 logits) and as the CPU oracle; confidences within 1e-4 relative."""
+    n, l, s = shape
+    if l == 192:
+        z = np.load(os.path.join(golden_dir, "small_dense.npz"))
+        f0, f1 = torch.from_numpy(z["geo0"]), torch.from_numpy(z["geo1"])
+        hw0, hw1 = (12, 16), (12, 16)
+    else:
+        f0, f1 = _feat(n, l, 256, 31, rms=1.0, offset=0.3), _feat(n, s, 256, 32, rms=1.0, offset=0.3)
+        hw0, hw1 = ((60, 80), (60, 80)) if l == 4800 else ((15, 20), (9, 37))
+    fused, counts = ops.coarse_match_fused(dev(f0), dev(f1), 0.1, thr, 0, hw0, hw1, 8.0)
+    sim = ops.similarity(dev(f0), dev(f1), 0.1)
+    conf, crmax, ccmax = ops.dual_softmax_(sim)
+    mat, counts2 = ops.mutual_nearest(conf, crmax, ccmax, thr, 0, hw0, hw1, 8.0)
+    a, b = _match_lists(fused), _match_lists(mat)
+    assert a.shape[0] > 0 or thr > 0
+    assert torch.equal(a, b)
+    assert counts.tolist() == counts2.tolist()
+    if a.shape[0]:
+        rel = ((fused["mconf"] - mat["mconf"]).abs() / mat["mconf"].abs().clamp(min=1e-30)).max().item()
+        assert rel <= 1e-4, rel
+    if l <= 333:
+        want = O.coarse_match(O.dual_softmax_conf(f0, f1, 0.1), thr, (hw0[0] * 8, hw0[1] * 8), hw0, hw1, 0)
+        assert torch.equal(a, torch.stack([want["b_ids"], want["i_ids"], want["j_ids"]], 1))

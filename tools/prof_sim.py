@@ -14,6 +14,7 @@ a = torch.randn(153600, 256, device=dev, generator=g)
 w = torch.randn(512, 512, device=dev, generator=g) / 22
 for _ in range(3):
     sim = ops.similarity(f0, f1, 0.1)
+    m, cnt = ops.coarse_match_fused(f0, f1, 0.1, 0.0, 0, (60, 80), (60, 80), 8.0)
     y = ops.conv3x3(x, wt, bias, None, 1)
     h = ops.linear(a, w, a2=a, epi=ops.EPI_RELU)
 torch.cuda.synchronize()
