@@ -51,6 +51,12 @@ template <int BN> struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+__device__ __forceinline__ float ex2_ftz(float x) {      // one MUFU.EX2; elu(x)+1 = e^x for x <= 0 needs no denormal care
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // tanh(x) = sign(x) * (1 - 2 / (exp(2|x|) + 1)); abs error ~1e-7 (well below the tf32 operand rounding)
 __device__ __forceinline__ float fast_tanh(float x) {
   const float e = __expf(2.f * fabsf(x));
@@ -289,9 +295,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if ((p.epi & GF_EPI_ELU1) && gc < p.act_cols) {
           if (gc + 32 <= p.act_cols) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] + 1.f : __expf(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] + 1.f : ex2_ftz(v[j] * 1.4426950408889634f);
           } else {
-            for (int j = 0; j < 32; ++j) if (gc + j < p.act_cols) v[j] = v[j] > 0.f ? v[j] + 1.f : __expf(v[j]);
+            for (int j = 0; j < 32; ++j) if (gc + j < p.act_cols) v[j] = v[j] > 0.f ? v[j] + 1.f : ex2_ftz(v[j] * 1.4426950408889634f);
           }
         }
         if constexpr (FULL) {

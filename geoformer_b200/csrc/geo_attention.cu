@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <cuda_fp16.h>
 
 namespace gf {
 extern std::atomic<int64_t> g_launches;
@@ -253,6 +254,35 @@ __global__ void gather_anchor_kv_kernel(const float* __restrict__ k, int ldk, co
   vt[(((int64_t)h * n + b) * dim + d) * s_pad + s] = vv;
 }
 
+// fp16 variant for the fused flash kernel; the same launch also converts the query rows: q16[n*l][c]
+__global__ void gather_anchor_kv_f16_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
+                                            const float* __restrict__ v, int ldv, int n, int l, int heads, int dim,
+                                            const int* __restrict__ anchor_idx, const int* __restrict__ anchor_cnt,
+                                            int anchor_cap, int s_pad, __half* __restrict__ q16, __half* __restrict__ kg,
+                                            __half* __restrict__ vt) {
+  const int c = heads * dim;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n_kv = (int64_t)n * s_pad * c, n_q = (int64_t)n * l * c;
+  if (idx < n_kv) {
+    const int ch = (int)(idx % c);
+    const int64_t r = idx / c;
+    const int s = (int)(r % s_pad), b = (int)(r / s_pad);
+    const int h = ch / dim, d = ch - h * dim;
+    float kv = 0.f, vv = 0.f;
+    if (s < anchor_cnt[b]) {
+      const int64_t tok = (int64_t)b * l + anchor_idx[(int64_t)b * anchor_cap + s];
+      kv = k[tok * ldk + ch];
+      vv = v[tok * ldv + ch];
+    }
+    kg[(((int64_t)h * n + b) * s_pad + s) * dim + d] = __float2half_rn(kv);
+    vt[(((int64_t)h * n + b) * dim + d) * s_pad + s] = __float2half_rn(vv);
+  } else if (idx < n_kv + n_q) {
+    const int64_t e = idx - n_kv;
+    const int64_t row = e / c;
+    q16[e] = __float2half_rn(q[row * ldq + (e - row * c)]);
+  }
+}
+
 // rows of [heads][n][l][s_pad]: p = softmax(x[0:cnt]) (x is already scaled), zeros beyond cnt.  One warp per row.
 // PER_LANE > 0: the whole row (s_pad <= 32 * PER_LANE) lives in registers -> one read and one write of the block.
 template <int PER_LANE>
@@ -346,6 +376,19 @@ extern "C" int gf_gather_anchor_kv(const float* k, int ldk, const float* v, int 
   const int64_t total = (int64_t)n * s_pad * heads * dim;
   gather_anchor_kv_kernel<<<gf_cdiv(total, 256), 256, 0, STREAM>>>(k, ldk, v, ldv, n, l, heads, dim, anchor_idx, anchor_cnt,
                                                                    anchor_cap, s_pad, kg, vt);
+  g_launches++;
+  GF_CHECK_LAUNCH();
+  return GF_OK;
+}
+
+extern "C" int gf_gather_anchor_kv_f16(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int n,
+                                       int l, int heads, int dim, const int* anchor_idx, const int* anchor_cnt,
+                                       int anchor_cap, int s_pad, void* q16, void* kg, void* vt, gf_stream_t stream) {
+  if (n <= 0 || l <= 0 || heads <= 0 || dim <= 0 || s_pad <= 0) return gf_set_error(GF_ERR_ARG, "gf_gather_anchor_kv_f16: bad shape");
+  const int64_t total = (int64_t)n * (s_pad + l) * heads * dim;
+  gather_anchor_kv_f16_kernel<<<gf_cdiv(total, 256), 256, 0, STREAM>>>(q, ldq, k, ldk, v, ldv, n, l, heads, dim, anchor_idx,
+                                                                       anchor_cnt, anchor_cap, s_pad, (__half*)q16, (__half*)kg,
+                                                                       (__half*)vt);
   g_launches++;
   GF_CHECK_LAUNCH();
   return GF_OK;

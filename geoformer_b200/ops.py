@@ -324,14 +324,20 @@ def geo_self_attention(q, ldq, k, ldk, v, ldv, n, l, heads, dim, anchor_idx, anc
     if mode in ("tf32", "tf32_mat") and max_cnt > 0:
         s_pad = (max_cnt + 63) // 64 * 64
         dev = q.device
+        if mode == "tf32":           # fused flash-style tcgen05 kernel (fp16 operands): scores never leave the SM
+            q16 = torch.empty((n * l, c), device=dev, dtype=torch.float16)
+            kg = torch.empty((heads, n, s_pad, dim), device=dev, dtype=torch.float16)
+            vt = torch.empty((heads, n, dim, s_pad), device=dev, dtype=torch.float16)
+            _call("gf_gather_anchor_kv_f16", q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, n, l, heads, dim,
+                  anchor_idx.data_ptr(), anchor_cnt.data_ptr(), anchor_idx.shape[1], s_pad, q16.data_ptr(),
+                  kg.data_ptr(), vt.data_ptr(), _stream())
+            _call("gf_geo_self_attention_tc", q16.data_ptr(), kg.data_ptr(), vt.data_ptr(), out.data_ptr(), n, l,
+                  heads, dim, s_pad, anchor_cnt.data_ptr(), _stream())
+            return out
         kg = torch.empty((heads, n, s_pad, dim), device=dev, dtype=torch.float32)
         vt = torch.empty((heads, n, dim, s_pad), device=dev, dtype=torch.float32)
         _call("gf_gather_anchor_kv", k.data_ptr(), ldk, v.data_ptr(), ldv, n, l, heads, dim, anchor_idx.data_ptr(),
               anchor_cnt.data_ptr(), anchor_idx.shape[1], s_pad, kg.data_ptr(), vt.data_ptr(), _stream())
-        if mode == "tf32":           # fused flash-style tcgen05 kernel: scores never leave the SM
-            _call("gf_geo_self_attention_tc", q.data_ptr(), ldq, kg.data_ptr(), vt.data_ptr(), out.data_ptr(), n, l,
-                  heads, dim, s_pad, anchor_cnt.data_ptr(), _stream())
-            return out
         sc = torch.empty((heads, n, l, s_pad), device=dev, dtype=torch.float32)
         for h in range(heads):
             _call("gf_gemm_tf32_batched", q.data_ptr() + 4 * h * dim, ldq, l * ldq, kg[h].data_ptr(), dim, s_pad * dim,

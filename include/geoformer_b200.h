@@ -176,11 +176,14 @@ int gf_gather_anchor_kv(const float* k, int ldk, const float* v, int ldv, int n,
                         gf_stream_t stream);
 int gf_masked_softmax_rows(float* x, int heads, int n, int l, int s_pad, const int* cnt_per_sample, gf_stream_t stream);
 /* Fused version of the three steps above: one tcgen05 kernel per call, 128 queries of one (sample, head) per CTA,
- * two passes over 64-key tiles (row maxima, then exp / P V), scores stay in TMEM / shared memory.
- * q = fused projection rows (stride ldq floats, head h at columns [h*dim, (h+1)*dim)); kg / vt from
- * gf_gather_anchor_kv with the same s_pad. */
-int gf_geo_self_attention_tc(const float* q, int ldq, const float* kg, const float* vt, float* out, int n, int l,
-                             int heads, int dim, int s_pad, const int* anchor_cnt, gf_stream_t stream);
+ * two passes over 64-key tiles (row maxima, then exp / P V), scores stay in TMEM / shared memory.  Operands are
+ * fp16 (kind::f16, fp32 accumulate) prepared by gf_gather_anchor_kv_f16: q16 [n*l, heads*dim] (converted query rows),
+ * kg [heads][n][s_pad][dim], vt [heads][n][dim][s_pad] (zero beyond anchor_cnt[n]); s_pad % 64 == 0. */
+int gf_gather_anchor_kv_f16(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int n, int l,
+                            int heads, int dim, const int* anchor_idx, const int* anchor_cnt, int anchor_cap, int s_pad,
+                            void* q16, void* kg, void* vt, gf_stream_t stream);
+int gf_geo_self_attention_tc(const void* q16, const void* kg, const void* vt, float* out, int n, int l, int heads,
+                             int dim, int s_pad, const int* anchor_cnt, gf_stream_t stream);
 /* Y[b] = out_scale * A[b] (M x K, row stride lda) * B[b]^T (N x K, row stride ldb); strides in floats */
 int gf_gemm_tf32_batched(const float* A, int64_t lda, int64_t a_batch_stride, const float* B, int64_t ldb,
                          int64_t b_batch_stride, float* Y, int64_t ldy, int64_t y_batch_stride, int M, int N, int K,
