@@ -130,7 +130,7 @@ def run_reference(args):
                              "sample": f"{steps} single-pair 640x480 forwards of the CPU oracle port after {warmup} warm-up "
                                        f"(the reference is pure PyTorch; /root/reference is absent on the GPU box)"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------- our arm
@@ -298,7 +298,7 @@ def run_ours(args):
                                           f"({spp:.2f} s/pair)"}
     else:
         line["cpu_baseline"] = None
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -316,6 +316,15 @@ def stage_breakdown(model, batch):
         sys.stderr.write(f"  {k:36s} x{cnt:4d}  {ms:9.3f} ms  {100 * ms / tot:5.1f}%\n")
     sys.stderr.write(f"  {'sum of stages':36s}        {tot:9.3f} ms\n")
 
+
+def _emit(line: dict) -> None:
+    """Exactly ONE JSON line on the real stdout (fd 1 was pointed at stderr while the run was in progress so that
+    library chatter such as NCCL's version banner cannot pollute it)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 if __name__ == "__main__":
     a = parse()
