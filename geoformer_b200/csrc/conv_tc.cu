@@ -262,7 +262,8 @@ __global__ void upsample_add_bf16_kernel(const uint4* __restrict__ lateral, cons
 // fp32 image in, NHWC bf16 out.  C_in = 1 makes this a 49-tap FFMA kernel (no tensor-core shape): CTA = 8 x 32
 // output pixels x 128 channels, thread = 8 consecutive pixels x 16 channels (128 accumulators), input patch and
 // weights in shared memory; per kernel row 21 input LDS + 28 weight LDS.128 feed 896 FFMA.
-// Weight layout in smem/global: [49 taps][4 j][8 cg][4 e]  <->  channel = j*32 + cg*4 + e.
+// Weights: [49 taps][128 channels] fp32 (natural channel order); thread (cg, j) reads the float4 of channels
+// j*32 + cg*4 .. +3, so the 8 channel groups of a quarter-warp cover 128 contiguous bytes (conflict-free).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 stem_conv7x7_kernel(const float* __restrict__ img, const float* __restrict__ wperm, const float* __restrict__ bias,
@@ -402,8 +403,7 @@ extern "C" int gf_upsample_add_bf16(const void* lateral, const void* src, void* 
   return GF_OK;
 }
 
-// img fp32 [b,1,h,w]; wperm fp32 [49][128] in the permuted channel order of the kernel (see pack in engine.py);
-// bias fp32 [128] (natural channel order); out NHWC bf16 [b, h/2, w/2, 128] (natural channel order).
+// img fp32 [b,1,h,w]; wperm fp32 [49 taps][128 channels]; bias fp32 [128]; out NHWC bf16 [b, ceil(h/2), ceil(w/2), 128].
 extern "C" int gf_stem_conv7x7_bf16(const float* img, const float* wperm, const float* bias, void* out, int batch, int h,
                                     int w, gf_stream_t stream) {
   if (batch <= 0 || h <= 0 || w <= 0) return gf_set_error(GF_ERR_ARG, "gf_stem_conv7x7_bf16: bad shape");

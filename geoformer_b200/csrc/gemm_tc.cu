@@ -71,7 +71,7 @@ __device__ __forceinline__ float fast_tanh(float x) {
 // the per-SM L2 -> smem operand traffic from (A + B) to (A + B/2) per k-block.  Measured on B200: no gain (the
 // short-K GEMMs of this model are bound by their HBM output stream, not by the operand feed), so CL = 1 is default.
 template <int KIND, int BN, bool FULL, int CL>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(FULL ? 192 : 320, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -105,7 +105,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < Cfg::kStages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], CL); }
-      for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], 4); }
+      for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], FULL ? 4 : 8); }
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -174,7 +174,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ------------------------------ epilogue (warps 2..5) ------------------------------
+    // lean epilogue: 8 warps, two per TMEM lane quadrant, each owning half of the tile's columns (with one epilogue
+    // warp per scheduler every dependency stall was exposed); full epilogue (LayerNorm needs whole rows): 4 warps
+    constexpr int EW = FULL ? 4 : 8;
+    constexpr int WCOLS = BN / (EW / 4);                 // columns per epilogue warp
+    constexpr int G = FULL ? 2 : 1;                      // boxes per TMA-store group (ring of 2 groups per warp)
     const int quad = warp & 3;                           // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t grp = 0;          // TMA-store group counter: 2 boxes per fence / commit, ring of 2 groups per warp
     int pend = 0;
@@ -188,12 +194,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::tc_fence_after();
       const int row = m_blk * kBM + quad * 32 + lane;
       const bool row_ok = row < m_live;
-      const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
+      const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + half * WCOLS;
       float* yrow = p.Y + (int64_t)batch * p.y_batch_stride + (int64_t)row * p.ldy;
       const float* rrow = p.residual ? p.residual + (int64_t)row * p.ldres : nullptr;
       const float* rb = p.rowbias ? p.rowbias + (int64_t)(row / p.rowbias_group) * p.N : nullptr;
-      const int col0 = n_blk * BN;
-      uint8_t* wstage = staging + (warp - 2) * 16384;    // this warp's four 4 KB boxes
+      const int col0 = n_blk * BN + half * WCOLS;
+      uint8_t* wstage = staging + (warp - 2) * (2 * G * 4096);   // this warp's ring of 2 groups x G boxes of 4 KB
       // residual tile slice of this lane for one 32x32 chunk: 8 coalesced float4 (4 rows x 128 B per instruction);
       // software-pipelined one chunk ahead so that the global-load latency hides behind the previous chunk
       float4 rnext[8];
@@ -236,7 +242,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // one 32-column chunk: math on v[] (thread == row), swizzled smem box, grouped TMA store
       auto emit_chunk = [&](float (&v)[32], int c, bool prefetch_next) {
         const int gc = col0 + c;
-        uint8_t* box = wstage + ((grp & 1) * 2 + pend) * 4096;
+        uint8_t* box = wstage + ((grp & 1) * G + pend) * 4096;
         if (p.tma_store) {
           if (pend == 0) {
             if (lane == 0) ptx::bulk_wait_read<1>();       // the group issued 2 groups ago no longer reads these boxes
@@ -249,7 +255,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int rr = it * 4 + (lane >> 3), ch = lane & 7;
                 *reinterpret_cast<float4*>(box + rr * 128 + ((ch ^ (rr & 7)) << 4)) = rnext[it];
               }
-              if (c + 32 < BN && gc + 32 < p.N) fetch_residual(gc + 32, rnext);
+              if (c + 32 < WCOLS && gc + 32 < p.N) fetch_residual(gc + 32, rnext);
               __syncwarp();
             }
           }
@@ -331,12 +337,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // proxy fence / TMA store issue below
           if (prefetch_next) ptx::tmem_ld_32x32(t_row + c + 32, v);
           pend_col[pend++] = gc;
-          const bool last = (c + 32 >= BN) || (gc + 32 >= p.N);
-          if (pend == 2 || last) {                         // one proxy fence + commit per two boxes
+          const bool last = (c + 32 >= WCOLS) || (gc + 32 >= p.N);
+          if (pend == G || last) {                         // one proxy fence + commit per group of boxes
             ptx::fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              uint8_t* gbase = wstage + (grp & 1) * 8192;
+              uint8_t* gbase = wstage + (grp & 1) * (G * 4096);
               for (int i = 0; i < pend; ++i)
                 ptx::tma_store_3d(&tmY, gbase + i * 4096, pend_col[i], m_blk * kBM + quad * 32, batch);
               ptx::bulk_commit();
@@ -351,10 +357,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (prefetch_next) ptx::tmem_ld_32x32(t_row + c + 32, v);
         }
       };
-      const int nch = min(BN / 32, (p.N - col0 + 31) / 32);    // live 32-column chunks of this tile (warp-uniform)
+      const int nch = max(0, min(WCOLS / 32, (p.N - col0 + 31) / 32));    // live 32-column chunks of this warp's share
       {
         float v[32];
-        ptx::tmem_ld_32x32(t_row, v);
+        if (nch > 0) ptx::tmem_ld_32x32(t_row, v);
 #pragma unroll 1
         for (int ci = 0; ci < nch; ++ci) {
           ptx::tmem_ld_wait();
@@ -450,7 +456,7 @@ static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& ta2, const CU
   const int64_t max_groups = g_num_sms / CL;
   const int grid = (int)(groups < max_groups ? groups : max_groups) * CL;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = stream;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(FULL ? 192 : 320); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;

@@ -149,12 +149,10 @@ class PackedWeights:
             t["layer2_outconv2.3"] = tc("layer2_outconv2.3")
             t["layer1_outconv2.0"] = tc("layer1_outconv2.0", "layer1_outconv2.1")
             t["layer1_outconv2.3"] = tc("layer1_outconv2.3")
-            # stem: BN-folded 7x7 weights, [49 taps][128] with the kernel's channel permutation
+            # stem: BN-folded 7x7 weights as [49 taps][128 channels]
             w7, b7 = _fold_bn(sd["backbone.conv1.weight"], bsd, "bn1")
             assert w7.shape == (128, 1, 7, 7)
-            wt7 = w7.reshape(128, 49).t().contiguous()                                # [49, 128] natural channel order
-            perm = torch.tensor([j * 32 + cg * 4 + e for j in range(4) for cg in range(8) for e in range(4)])
-            t["stem"] = (wt7[:, perm].contiguous().to(device), b7.float().to(device))
+            t["stem"] = (w7.reshape(128, 49).t().contiguous().to(device), b7.float().to(device))
             self.bb_tc = t
         self._pe: Dict[Tuple[int, int, int], torch.Tensor] = {}
 

@@ -72,8 +72,7 @@ int gf_conv3x3_bf16(const void* x, const void* wt, const float* bias, const void
                     int w, int cin_p, int cout_p, int cin_k, int act, gf_stream_t stream);
 
 /* Backbone stem (resnet_fpn.py:58-60,102): 7x7 / stride 2 / pad 3 conv of the 1-channel fp32 image + folded BN +
- * ReLU -> NHWC bf16 [b, h/2, w/2, 128].  wperm [49][128] holds, for tap t, channel (j*32 + cg*4 + e) at
- * position ((j*8 + cg)*4 + e). */
+ * ReLU -> NHWC bf16 [b, h/2, w/2, 128].  wperm = folded weights as [49 taps][128 channels] fp32. */
 int gf_stem_conv7x7_bf16(const float* img, const float* wperm, const float* bias, void* out, int batch, int h, int w,
                          gf_stream_t stream);
 /* FPN top-down merge (resnet_fpn.py:108-115): out = lateral + bilinear(src -> h x w, align_corners=True); NHWC bf16 */

@@ -387,3 +387,27 @@ def test_fused_coarse_matching_equals_materialised(ops, golden_dir, shape, thr):
     if l <= 333:
         want = O.coarse_match(O.dual_softmax_conf(f0, f1, 0.1), thr, (hw0[0] * 8, hw0[1] * 8), hw0, hw1, 0)
         assert torch.equal(a, torch.stack([want["b_ids"], want["i_ids"], want["j_ids"]], 1))
+
+
+def test_stem_conv7x7(ops):
+    """Stem 7x7/s2 conv + folded BN + ReLU (FFMA kernel, fp32 image -> NHWC bf16) vs F.conv2d; odd sizes hit the
+    partial-tile and zero-padding paths.  Tolerance = bf16 output rounding."""
+    b, h, w = 2, 70, 100
+    img = torch.rand(b, 1, h, w, generator=torch.Generator().manual_seed(1))
+    wgt = rnd(128, 1, 7, 7, seed=2) * 0.2
+    bias = rnd(128, seed=3) * 0.1
+    want = F.relu(F.conv2d(img, wgt, bias, 2, 3))
+    wt7 = wgt.reshape(128, 49).t().contiguous()
+    got = ops.stem_conv(dev(img), dev(wt7), dev(bias)).cpu().float().permute(0, 3, 1, 2)
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() <= 6e-3 * want.abs().max().item()
+
+
+def test_upsample_add(ops):
+    """FPN top-down merge: lateral + bilinear x2 (align_corners=True), NHWC bf16."""
+    b, hs, ws, c = 2, 15, 20, 200
+    lat = rnd(b, c, 2 * hs, 2 * ws, seed=1).bfloat16()
+    src = rnd(b, c, hs, ws, seed=2).bfloat16()
+    want = lat.float() + F.interpolate(src.float(), size=(2 * hs, 2 * ws), mode="bilinear", align_corners=True)
+    got = ops.upsample_add(dev(lat.permute(0, 2, 3, 1)), dev(src.permute(0, 2, 3, 1))).cpu().float().permute(0, 3, 1, 2)
+    assert (got - want).abs().max().item() <= 1e-2 * want.abs().max().item()
