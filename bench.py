@@ -280,7 +280,10 @@ def run_ours(args):
             "algorithmic_flops_per_launch": flops, "issued_flops_per_launch": 3 * flops,
             "issued_frac": 3 * achieved / peak_tf,      # tensor-pipe view: the split-fp16 product issues 3 MMAs per algorithmic one
             "avg_launch_ms": sim_avg_ms, "launches_timed": len(sim_ms),
-            "traffic": None}
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full of the same kernels at this size
+            # (profiles/r01_ncu_final_raw.txt): pass 0 = 236.1 + 97.1 MB, pass 1 = 238.1 + 4.2 MB; algorithmic bytes per
+            # launch = packed operands 235.9 MB (+ 105 MB statistics partials in pass 0) -> no re-reads
+            "traffic": 287.7e6 * args.batch / 16, "tensor_pipe_active_pct_ncu": {"pass0": 68.5, "pass1": 66.5}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "tf32 projections/attention, split-f16 similarity, bf16 backbone" if args.backbone == "bf16"

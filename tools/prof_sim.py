@@ -19,7 +19,7 @@ acnt = torch.full((n,), cnt, device=dev, dtype=torch.int32)
 for _ in range(3):
     att = ops.geo_self_attention(qkv, 3 * c, qkv[:, c:], 3 * c, qkv[:, 2 * c:], 3 * c, n, l, hh, dd, aidx, acnt, max_cnt=cnt, impl="tf32")
     sim = ops.similarity(f0, f1, 0.1)
-    m, cnt = ops.coarse_match_fused(f0, f1, 0.1, 0.0, 0, (60, 80), (60, 80), 8.0)
+    mres, mcounts = ops.coarse_match_fused(f0, f1, 0.1, 0.0, 0, (60, 80), (60, 80), 8.0)
     y = ops.conv3x3(x, wt, bias, None, 1)
     h = ops.linear(a, w, a2=a, epi=ops.EPI_RELU)
 torch.cuda.synchronize()
