@@ -218,6 +218,12 @@ int gf_compact_fine(const int* sel, const int* fi, const int* fj, const float* f
                     float c2f_scale, float fine_scale, float* mkpts0_f, float* mkpts1_f, float* mconf,
                     int64_t* m_bids, int* total, gf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Image ingest, the step before the path (eval_tool/immatch/utils/data_io.py:48-62): OpenCV's 8-bit INTER_LINEAR
+ * cv2.resize reproduced bit-exactly + torchvision to_tensor (/255).  src: uint8 [ho, wo]; dst: fp32 [ht, wt].
+ */
+int gf_resize_gray_u8(const void* src, int ho, int wo, float* dst, int ht, int wt, gf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

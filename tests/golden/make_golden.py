@@ -143,11 +143,48 @@ def full_case(name, h, w, regime, seed0, coarse_thr=0.0):
     print(name, "M_c", len(data["b_ids"]), "M_f", len(data["mkpts0_f"]))
 
 
+def eval_and_ingest_case():
+    """Golden vectors for the 'next' rows: downstream evaluation helpers (hpatches_helper.cal_error_auc /
+    cal_reproj_dists, fire_helper.compute_auc) and the image ingest (data_io.resize_im + cv2.resize + to_tensor)."""
+    import_reference()
+    import cv2
+    import torchvision.transforms as transforms
+    from eval_tool.immatch.utils.hpatches_helper import cal_error_auc, cal_reproj_dists
+    from eval_tool.immatch.utils.fire_helper import compute_auc
+    from eval_tool.immatch.utils.data_io import resize_im
+    rng = np.random.RandomState(3)
+    errs = np.abs(rng.randn(57)) * 4
+    errs[5] = np.nan
+    thr = [1, 3, 5, 10]
+    auc = cal_error_auc(errs[~np.isnan(errs)], thr)
+    auc_empty = cal_error_auc(np.array([]), thr)
+    p1 = rng.rand(40, 2) * 400
+    Hm = np.array([[1.01, 0.02, 3.0], [-0.01, 0.99, -2.0], [1e-5, 2e-5, 1.0]])
+    p2 = rng.rand(40, 2) * 400
+    dists = cal_reproj_dists(p1, p2, Hm)
+    s, p, a = np.abs(rng.randn(71)) * 8, np.abs(rng.randn(48)) * 12, np.abs(rng.randn(14)) * 10
+    fire = compute_auc(list(s), list(p), list(a))
+    dims = []
+    for (wo, ho, imsize, df) in [(1024, 768, 480, 8), (800, 600, 480, 8), (2912, 2912, 768, 8), (517, 333, 480, 8), (640, 480, 480, 8)]:
+        wt, ht, sc = resize_im(wo, ho, imsize=imsize, dfactor=df, value_to_scale=min)
+        dims.append([wo, ho, imsize, df, wt, ht, sc[0], sc[1]])
+    im = rng.randint(0, 256, (333, 517)).astype(np.uint8)
+    wt, ht, sc = resize_im(517, 333, imsize=200, dfactor=8, value_to_scale=min)
+    t = transforms.functional.to_tensor(cv2.resize(im, (wt, ht))).unsqueeze(0)
+    np.savez_compressed(os.path.join(HERE, "eval_ingest.npz"), errs=errs, thr=np.array(thr), auc=auc, auc_empty=auc_empty,
+                        p1=p1, p2=p2, H=Hm, dists=dists, fire_s=s, fire_p=p, fire_a=a,
+                        fire=np.array([fire['s'], fire['p'], fire['a'], fire['mAUC']]), dims=np.array(dims),
+                        im=im, im_resized=t.numpy(), im_hw=np.array([ht, wt]))
+    print("eval_ingest", auc, fire, t.shape)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
-    small_case("small_dense", 96, 128, "dense", 2, 0, True)
-    small_case("small_shift", 96, 128, "shift", 1, 10, True)
-    small_case("small_rect_thr", 64, 96, "dense", 1, 20, False, coarse_thr=0.2)   # zero-match corner
-    if "--full" in sys.argv or True:
+    if "--only-eval" not in sys.argv:
+        small_case("small_dense", 96, 128, "dense", 2, 0, True)
+        small_case("small_shift", 96, 128, "shift", 1, 10, True)
+        small_case("small_rect_thr", 64, 96, "dense", 1, 20, False, coarse_thr=0.2)   # zero-match corner
+    if "--only-eval" not in sys.argv:
         full_case("full_dense_480x640", 480, 640, "dense", 0)
+    eval_and_ingest_case()
