@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--regime", default="dense", choices=["dense", "shift"])
     ap.add_argument("--backbone", default=os.environ.get("GF_BACKBONE", "bf16"))
+    ap.add_argument("--ransac", default=os.environ.get("GF_RANSAC", "cv2"), choices=["cv2", "gpu"],
+                    help="cv2 = host cv2.findHomography as the reference (default); gpu = csrc/ransac.cu (not bit-identical)")
     ap.add_argument("--depth", type=int, default=2, help="batches in flight (MatchPipeline); 1 = plain serial forward")
     ap.add_argument("--hw", default=None, help="HxW override for informational runs of the other BASELINE configs (e.g. 768x768)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -134,7 +136,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------- our arm
-def build_model(device, backbone):
+def build_model(device, backbone, ransac="cv2"):
     from geoformer_b200.model.full_model import GeoFormer
     from geoformer_b200.model.geo_config import default_cfg as geo_cfg
     from geoformer_b200.model.loftr_src.loftr.utils.cvpr_ds_config import default_cfg
@@ -144,6 +146,7 @@ def build_model(device, backbone):
     ckpt = {"state_dict": {"matcher." + k: v for k, v in synth.make_state_dict(0).items()}}   # checkpoint-shaped, as the wrapper loads it
     m.load_state_dict(ckpt["state_dict"], strict=False)
     m.backbone_precision = backbone
+    m.ransac = ransac
     return m.eval().to(device)
 
 
@@ -158,7 +161,7 @@ def run_ours(args):
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    model = build_model(device, args.backbone)
+    model = build_model(device, args.backbone, args.ransac)
 
     # a small pool of distinct batches, resident in HBM (value) and in pinned host memory (e2e)
     pool = 2
@@ -290,7 +293,7 @@ def run_ours(args):
                      else f"tf32 projections/attention, split-f16 similarity, {args.backbone} backbone",
             "data": "synthetic",
             "config": workload_config(args, {"matches_coarse_per_pair": mc, "matches_fine_per_pair": mf,
-                                             "batches_in_flight": args.depth, "exchange_ms_per_batch_gather": exchange_ms,
+                                             "batches_in_flight": args.depth, "ransac": args.ransac, "exchange_ms_per_batch_gather": exchange_ms,
                                              "gathered_matches": gathered,
                                              "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective"}),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * args.batch * H * W * 4, "d2h_bytes_per_step": d2h},

@@ -55,6 +55,8 @@ SIGNATURES = {
     "gf_gather_rows": (I, [P, L, I, P, P, L, P, P]),
     "gf_fine_match": (I, [P, P, L, I, I, F, F, P, P, P, P, P, P]),
     "gf_resize_gray_u8": (I, [P, I, I, P, I, I, P]),
+    "gf_ransac_workspace_bytes": (L, [I, I]),
+    "gf_ransac_homography": (I, [P, P, P, P, L, I, I, F, ctypes.c_uint, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, I, P]),
     "gf_compact_fine": (I, [P, P, P, P, P, P, P, L, I, F, F, F, P, P, P, P, P, P]),
 }
 

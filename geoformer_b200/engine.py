@@ -405,20 +405,34 @@ def geo_cross_layer(lw: dict, x0: torch.Tensor, x1: torch.Tensor, widx_in1: torc
 
 
 def geo_module(pw: PackedWeights, x0: torch.Tensor, x1: torch.Tensor, first: dict, counts, hw0_i, hw1_i, hw0_c, hw1_c,
-               names, heads: int, window: int, ransac_thr: float = 8.0, info: Optional[dict] = None):
+               names, heads: int, window: int, ransac_thr: float = 8.0, info: Optional[dict] = None,
+               ransac: str = "cv2", ransac_hyps: int = 1024):
     n = x0.shape[0]
     dev = x0.device
     scale = int(hw0_i[0] // hw0_c[0])
-    with ops.PROFILE.region("host:ransac"):
-        k0 = first["mkpts0_c"].cpu().numpy()             # device -> host: RANSAC runs in OpenCV (geo_module.py:48)
-        k1 = first["mkpts1_c"].cpu().numpy()
-        hm, has_h_np, aidx_np, acnt_np = geo_prepare_host(k0, k1, np.asarray(counts), hw0_c, hw1_c, scale, ransac_thr)
-    if info is not None:
-        info.update(has_h=has_h_np.copy(), anchor_cnt=acnt_np.copy(), hmat=hm.copy())
-    hm_d = torch.from_numpy(hm).to(dev, non_blocking=True)
-    has_h = torch.from_numpy(has_h_np).to(dev, non_blocking=True)
-    aidx = torch.from_numpy(aidx_np).to(dev, non_blocking=True)
-    acnt = torch.from_numpy(acnt_np).to(dev, non_blocking=True)
+    if ransac == "gpu":
+        # optional device RANSAC (csrc/ransac.cu): no match coordinates leave the GPU; only 3n counters come back
+        with ops.PROFILE.region("ransac_gpu"):
+            cnt_d = torch.as_tensor(np.asarray(counts, dtype=np.int32)).to(dev, non_blocking=True)
+            hm_d, has_h, _, aidx, acnt = ops.ransac_homography(first["mkpts0_c"], first["mkpts1_c"], first["b_ids"], cnt_d,
+                                                               n, hw0_c, hw1_c, scale, ransac_thr, ransac_hyps)
+            small = torch.cat([has_h[None], acnt]).cpu().numpy()
+        has_h_np, acnt_np = small[0], small[1:]
+        if info is not None:
+            info.update(has_h=has_h_np.copy(), anchor_cnt=acnt_np.copy(), hmat=hm_d.cpu().numpy())
+    elif ransac == "cv2":
+        with ops.PROFILE.region("host:ransac"):
+            k0 = first["mkpts0_c"].cpu().numpy()             # device -> host: RANSAC runs in OpenCV (geo_module.py:48)
+            k1 = first["mkpts1_c"].cpu().numpy()
+            hm, has_h_np, aidx_np, acnt_np = geo_prepare_host(k0, k1, np.asarray(counts), hw0_c, hw1_c, scale, ransac_thr)
+        if info is not None:
+            info.update(has_h=has_h_np.copy(), anchor_cnt=acnt_np.copy(), hmat=hm.copy())
+        hm_d = torch.from_numpy(hm).to(dev, non_blocking=True)
+        has_h = torch.from_numpy(has_h_np).to(dev, non_blocking=True)
+        aidx = torch.from_numpy(aidx_np).to(dev, non_blocking=True)
+        acnt = torch.from_numpy(acnt_np).to(dev, non_blocking=True)
+    else:
+        raise ValueError(f"ransac must be 'cv2' or 'gpu', got {ransac!r}")
     x0, x1 = x0.clone(), x1.clone()
     any_h = bool(has_h_np.any())
     if any_h:

@@ -100,6 +100,9 @@ class GeoFormer(nn.Module):
         self.geo_module = _GeoModule(dc, len(geoformer_cfg["layer_names"]))
         # engine options (not part of the reference surface)
         self.backbone_precision = os.environ.get("GF_BACKBONE", "bf16")
+        # "cv2": host cv2.findHomography as the reference (geo_module.py:48); "gpu": csrc/ransac.cu (not bit-identical)
+        self.ransac = os.environ.get("GF_RANSAC", "cv2")
+        self.ransac_hyps = 1024
         self.materialize = False       # also return conf_matrix / dect_conf_matrix / fine_matrix (training-side keys)
         self.capture = False           # keep per-stage tensors in data['_stages'] (tests)
         self._packed: Optional[engine.PackedWeights] = None
@@ -167,7 +170,8 @@ class GeoFormer(nn.Module):
         ginfo = {} if self.capture else None
         with R("stage:geo_module(+host RANSAC)"):
             g0, g1 = engine.geo_module(pw, x0, x1, m1, counts1, hw0_i, hw1_i, hw0_c, hw1_c, gcfg["layer_names"],
-                                       gcfg["nhead"], gcfg["window_size"], info=ginfo)
+                                       gcfg["nhead"], gcfg["window_size"], info=ginfo, ransac=self.ransac,
+                                       ransac_hyps=self.ransac_hyps)
         with R("stage:coarse_matching_2"):
             m2, counts2, conf2 = engine.coarse_matching(g0, g1, thr, temp, 0, hw0_i, hw0_c, hw1_c, self.materialize)
         data.update(m2)

@@ -404,3 +404,30 @@ def fine_match(f0: torch.Tensor, f1: torch.Tensor, temperature: float, thr: floa
               k0.data_ptr(), k1.data_ptr(), mconf.data_ptr(), mb.data_ptr(), total.data_ptr(), _stream())
     t = int(total.item())
     return dict(mkpts0_f=k0[:t], mkpts1_f=k1[:t], mconf=mconf[:t], m_bids=mb[:t]), fmat, (sel, fi, fj, fconf)
+
+
+# --------------------------------------------------------------------------------------------
+# optional GPU RANSAC (csrc/ransac.cu) — replaces the host cv2.findHomography of geo_module.py:45-52
+# --------------------------------------------------------------------------------------------
+def ransac_homography(k0: torch.Tensor, k1: torch.Tensor, b_ids: torch.Tensor, counts: torch.Tensor, n: int,
+                      hw0_c, hw1_c, scale: int, thr: float = 8.0, hyps: int = 1024, seed: int = 0):
+    """k0/k1 [M,2] fp32 first-pass coarse matches, b_ids [M] int64, counts [n] int32 (device).
+    Returns hm [2,n,9] (H and H^-1, fp32), has_h [n], inlier [M], aidx [2,n,cap], acnt [2,n]."""
+    dev = k0.device
+    _chk(k0); _chk(k1); _chk(b_ids, torch.int64); _chk(counts, torch.int32)
+    assert k0.is_contiguous() and k1.is_contiguous()
+    m = int(k0.shape[0])
+    l0, l1 = hw0_c[0] * hw0_c[1], hw1_c[0] * hw1_c[1]
+    cap = max(l0, l1)
+    ws = torch.empty(_lib.load().gf_ransac_workspace_bytes(n, hyps), device=dev, dtype=torch.uint8)
+    hm = torch.empty((2, n, 9), device=dev)
+    has_h = torch.empty(n, device=dev, dtype=torch.int32)
+    inlier = torch.empty(max(m, 1), device=dev, dtype=torch.int32)
+    map0 = torch.empty((n, l0), device=dev, dtype=torch.int32); map1 = torch.empty((n, l1), device=dev, dtype=torch.int32)
+    aidx = torch.zeros((2, n, cap), device=dev, dtype=torch.int32)
+    acnt = torch.empty((2, n), device=dev, dtype=torch.int32)
+    _call("gf_ransac_homography", k0.data_ptr(), k1.data_ptr(), b_ids.data_ptr(), counts.data_ptr(), m, n, hyps,
+          float(thr), int(seed) & 0xffffffff, int(scale), l0, hw0_c[1], l1, hw1_c[1], ws.data_ptr(), hm[0].data_ptr(),
+          hm[1].data_ptr(), has_h.data_ptr(), inlier.data_ptr(), map0.data_ptr(), map1.data_ptr(), aidx[0].data_ptr(),
+          acnt[0].data_ptr(), aidx[1].data_ptr(), acnt[1].data_ptr(), cap, _stream(), tag="ransac")
+    return hm, has_h, inlier[:m], aidx, acnt

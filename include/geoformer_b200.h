@@ -224,6 +224,21 @@ int gf_compact_fine(const int* sel, const int* fi, const int* fj, const float* f
  */
 int gf_resize_gray_u8(const void* src, int ho, int wo, float* dst, int ht, int wt, gf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optional GPU RANSAC (replaces the host cv2.findHomography(kp0, kp1, cv2.RANSAC, 8.0) of model/geo_module.py:45-52
+ * when GeoFormer.ransac == "gpu"; NOT bit-identical to OpenCV, so cv2 stays the default).  hyps % 8 == 0.
+ * k0/k1 [m,2] fp32 first-pass coarse matches grouped by sample, counts[n] (device).  Outputs: hmat/hinv [n,9]
+ * fp32 row-major, has_h[n] (0 when <= 8 matches or degenerate, geo_module.py:47), inlier[m], boolean token maps
+ * map0 [n,l0] / map1 [n,l1] and the ascending anchor lists anchor_idx{0,1} [n,cap] + anchor_cnt{0,1}[n]
+ * (all first-pass matches when has_h == 0, geo_module.py:76-88).
+ */
+int64_t gf_ransac_workspace_bytes(int n, int hyps);
+int gf_ransac_homography(const float* k0, const float* k1, const int64_t* b_ids, const int* counts, int64_t m, int n,
+                         int hyps, float thr, unsigned seed, int scale, int l0, int w0c, int l1, int w1c,
+                         void* workspace, float* hmat, float* hinv, int* has_h, int* inlier, int* map0, int* map1,
+                         int* anchor_idx0, int* anchor_cnt0, int* anchor_idx1, int* anchor_cnt1, int cap,
+                         gf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
