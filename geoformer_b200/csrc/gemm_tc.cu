@@ -13,6 +13,8 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <cuda_fp16.h>
+
 #include <atomic>
 #include <cstdlib>
 
@@ -51,6 +53,11 @@ template <int BN> struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
 __device__ __forceinline__ float ex2_ftz(float x) {      // one MUFU.EX2; elu(x)+1 = e^x for x <= 0 needs no denormal care
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -70,7 +77,10 @@ __device__ __forceinline__ float fast_tanh(float x) {
 // share the B operand: each CTA TMA-loads half of every B box and multicasts it into both shared memories, cutting
 // the per-SM L2 -> smem operand traffic from (A + B) to (A + B/2) per k-block.  Measured on B200: no gain (the
 // short-K GEMMs of this model are bound by their HBM output stream, not by the operand feed), so CL = 1 is default.
-template <int KIND, int BN, bool FULL, int CL>
+// OUT16 (lean epilogue only): the output is stored as fp16 (32 x 32 boxes of 64-byte rows, 64B swizzle).  Used for
+// intermediates whose only consumers round to a 10-bit mantissa anyway (tf32 / fp16 MMA operands) or are the linear
+// attention kernels: halves the HBM stream these short-K GEMMs are bound by.
+template <int KIND, int BN, bool FULL, int CL, bool OUT16>
 __global__ void __launch_bounds__(FULL ? 192 : 320, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY, const GemmParams p) {
@@ -322,7 +332,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) if (gc + j < p.N) v[j] += __ldg(rrow + gc + j);
           }
         }
-        if (p.tma_store) {
+        if constexpr (OUT16) {                               // host guarantees tma_store for fp16 outputs
+          uint8_t* myrow = box + lane * 64;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = pack_half2(v[8 * j], v[8 * j + 1]); u.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+            u.z = pack_half2(v[8 * j + 4], v[8 * j + 5]); u.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+            *reinterpret_cast<uint4*>(myrow + ((j ^ ((lane >> 1) & 3)) << 4)) = u;      // 64B swizzle: addr[5:4] ^= addr[8:7]
+          }
+          if (prefetch_next) ptx::tmem_ld_32x32(t_row + c + 32, v);
+          pend_col[pend++] = gc;
+          const bool last = (c + 32 >= WCOLS) || (gc + 32 >= p.N);
+          if (pend == G || last) {
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              uint8_t* gbase = wstage + (grp & 1) * (G * 4096);
+              for (int i = 0; i < pend; ++i)
+                ptx::tma_store_3d(&tmY, gbase + i * 4096, pend_col[i], m_blk * kBM + quad * 32, batch);
+              ptx::bulk_commit();
+            }
+            pend = 0;
+            ++grp;
+          }
+        } else if (p.tma_store) {
           uint8_t* myrow = box + lane * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -440,12 +474,26 @@ int make_out_tmap(CUtensorMap* m, float* base, int64_t n, int64_t rows, int64_t 
   return GF_OK;
 }
 
-template <int KIND, int BN, bool FULL, int CL>
+// fp16 output map: box {32 cols, 32 rows, 1} of 64-byte rows, 64B swizzle (matches the OUT16 epilogue staging)
+int make_out_tmap16(CUtensorMap* m, void* base, int64_t n, int64_t rows, int64_t batches, int64_t ld, int64_t batch_stride) {
+  if (!g_encode) return gf_set_error(GF_ERR_DRIVER, "gf_init() was not called");
+  cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)rows, (cuuint64_t)batches};
+  cuuint64_t strides[2] = {(cuuint64_t)(ld * 2), (cuuint64_t)(batch_stride * 2)};
+  if (batches == 1 && batch_stride == 0) strides[1] = strides[0] * (cuuint64_t)rows;
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return gf_set_error(GF_ERR_DRIVER, "cuTensorMapEncodeTiled(out16) failed");
+  return GF_OK;
+}
+
+template <int KIND, int BN, bool FULL, int CL, bool OUT16 = false>
 static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& ty,
                          const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<KIND, BN, FULL, CL>;
+  auto kern = gemm_tc_kernel<KIND, BN, FULL, CL, OUT16>;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
       return gf_set_error(GF_ERR_LAUNCH, "cudaFuncSetAttribute(smem) failed");
@@ -472,8 +520,13 @@ static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& ta2, const CU
 
 template <int KIND, int BN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& ty,
-                       const GemmParams& p, cudaStream_t stream) {
+                       const GemmParams& p, cudaStream_t stream, bool out16 = false) {
   const bool full = (p.epi & GF_EPI_LN) || p.residual != nullptr || p.rowbias != nullptr || !p.tma_store;
+  if (out16) {
+    if (full) return gf_set_error(GF_ERR_ARG, "fp16 output is available with the lean epilogue only (no LN / residual / row bias)");
+    if constexpr (KIND == 0) return launch_gemm_t<KIND, BN, false, 1, true>(ta, ta2, tb, ty, p, stream);
+    else return gf_set_error(GF_ERR_ARG, "fp16 output needs fp32 (tf32) operands");
+  }
   if (p.cluster == 2) {
     if (full) return launch_gemm_t<KIND, BN, true, 2>(ta, ta2, tb, ty, p, stream);
     return launch_gemm_t<KIND, BN, false, 2>(ta, ta2, tb, ty, p, stream);
@@ -486,36 +539,59 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta2, const CUte
 
 using namespace gf;
 
-extern "C" int gf_linear_tf32(const float* A, const float* A2, const float* W, float* Y, int64_t M, int N, int K1,
-                              int K2, int epi, int act_cols, const float* bias, const float* rowbias,
-                              int rowbias_group, const float* gamma, const float* beta, const float* residual,
-                              const int* m_dev, gf_stream_t stream) {
-  if (M < 0 || N <= 0 || K1 <= 0 || K2 < 0 || (N % 128) || (K1 % 32) || (K2 % 32) || M > 0x7fffff00LL)
-    return gf_set_error(GF_ERR_ARG, "gf_linear_tf32: need N % 128 == 0, K % 32 == 0");
-  if ((epi & GF_EPI_LN) && !(N == 128 || N == 256)) return gf_set_error(GF_ERR_ARG, "gf_linear_tf32: LN epilogue needs N in {128,256}");
-  if ((epi & GF_EPI_LN) && (!gamma || !beta)) return gf_set_error(GF_ERR_ARG, "gf_linear_tf32: LN epilogue needs gamma/beta");
-  if (K2 > 0 && !A2) return gf_set_error(GF_ERR_ARG, "gf_linear_tf32: A2 missing");
-  if (rowbias && rowbias_group <= 0) return gf_set_error(GF_ERR_ARG, "gf_linear_tf32: rowbias_group");
+// Y = epilogue([A | A2] W^T).  in_f16: A, A2 and W are fp16 (kind::f16, K % 64 == 0), else fp32 (kind::tf32, K % 32 == 0);
+// out_f16: Y is fp16 (lean epilogue only), else fp32.
+static int linear_impl(const void* A, const void* A2, const void* W, void* Y, int in_f16, int out_f16, int64_t M, int N,
+                       int K1, int K2, int epi, int act_cols, const float* bias, const float* rowbias, int rowbias_group,
+                       const float* gamma, const float* beta, const float* residual, const int* m_dev, gf_stream_t stream) {
+  const int bke = in_f16 ? 64 : 32, esz = in_f16 ? 2 : 4;
+  if (M < 0 || N <= 0 || K1 <= 0 || K2 < 0 || (N % 128) || (K1 % bke) || (K2 % bke) || M > 0x7fffff00LL)
+    return gf_set_error(GF_ERR_ARG, "gf_linear: need N % 128 == 0, K % 32 == 0 (fp32) / K % 64 == 0 (fp16)");
+  if ((epi & GF_EPI_LN) && !(N == 128 || N == 256)) return gf_set_error(GF_ERR_ARG, "gf_linear: LN epilogue needs N in {128,256}");
+  if ((epi & GF_EPI_LN) && (!gamma || !beta)) return gf_set_error(GF_ERR_ARG, "gf_linear: LN epilogue needs gamma/beta");
+  if (K2 > 0 && !A2) return gf_set_error(GF_ERR_ARG, "gf_linear: A2 missing");
+  if (rowbias && rowbias_group <= 0) return gf_set_error(GF_ERR_ARG, "gf_linear: rowbias_group");
   if (M == 0) return GF_OK;
   const int BN = (N % 256 == 0) ? 256 : 128;
   CUtensorMap ta, ta2, tb;
   int rc;
-  if ((rc = make_tmap(&ta, A, 4, K1, M, 1, K1, 0, kBM))) return rc;
-  if (K2 > 0) { if ((rc = make_tmap(&ta2, A2, 4, K2, M, 1, K2, 0, kBM))) return rc; } else ta2 = ta;
-  const int cl = (M > kBM && getenv("GF_CLUSTER2") != nullptr) ? 2 : 1;
-  if ((rc = make_tmap(&tb, W, 4, K1 + K2, N, 1, K1 + K2, 0, BN / cl))) return rc;
+  if ((rc = make_tmap(&ta, A, esz, K1, M, 1, K1, 0, kBM))) return rc;
+  if (K2 > 0) { if ((rc = make_tmap(&ta2, A2, esz, K2, M, 1, K2, 0, kBM))) return rc; } else ta2 = ta;
+  const int cl = (!in_f16 && !out_f16 && M > kBM && getenv("GF_CLUSTER2") != nullptr) ? 2 : 1;
+  if ((rc = make_tmap(&tb, W, esz, K1 + K2, N, 1, K1 + K2, 0, BN / cl))) return rc;
   GemmParams p{};
-  p.Y = Y; p.ldy = N; p.y_batch_stride = 0; p.M = (int)M; p.N = N; p.batches = 1;
-  p.kblocks1 = K1 / 32; p.kblocks2 = K2 / 32; p.epi = epi; p.act_cols = act_cols;
+  p.Y = reinterpret_cast<float*>(Y); p.ldy = N; p.y_batch_stride = 0; p.M = (int)M; p.N = N; p.batches = 1;
+  p.kblocks1 = K1 / bke; p.kblocks2 = K2 / bke; p.epi = epi; p.act_cols = act_cols;
   p.bias = bias; p.rowbias = rowbias; p.rowbias_group = rowbias_group > 0 ? rowbias_group : 1;
   p.gamma = gamma; p.beta = beta; p.residual = residual; p.ldres = N; p.out_scale = 1.f; p.m_dev = m_dev;
   p.tiles_n = N / BN;
   p.cluster = cl;
   p.tma_store = 1;
   CUtensorMap ty;
-  if ((rc = make_out_tmap(&ty, Y, N, M, 1, N, 0))) return rc;
-  if (BN == 256) return launch_gemm<0, 256>(ta, ta2, tb, ty, p, (cudaStream_t)stream);
-  return launch_gemm<0, 128>(ta, ta2, tb, ty, p, (cudaStream_t)stream);
+  if (out_f16) { if ((rc = make_out_tmap16(&ty, Y, N, M, 1, N, 0))) return rc; }
+  else if ((rc = make_out_tmap(&ty, reinterpret_cast<float*>(Y), N, M, 1, N, 0))) return rc;
+  if (in_f16) {
+    if (BN == 256) return launch_gemm<1, 256>(ta, ta2, tb, ty, p, (cudaStream_t)stream, out_f16 != 0);
+    return launch_gemm<1, 128>(ta, ta2, tb, ty, p, (cudaStream_t)stream, out_f16 != 0);
+  }
+  if (BN == 256) return launch_gemm<0, 256>(ta, ta2, tb, ty, p, (cudaStream_t)stream, out_f16 != 0);
+  return launch_gemm<0, 128>(ta, ta2, tb, ty, p, (cudaStream_t)stream, out_f16 != 0);
+}
+
+extern "C" int gf_linear_tf32(const float* A, const float* A2, const float* W, float* Y, int64_t M, int N, int K1,
+                              int K2, int epi, int act_cols, const float* bias, const float* rowbias,
+                              int rowbias_group, const float* gamma, const float* beta, const float* residual,
+                              const int* m_dev, gf_stream_t stream) {
+  return linear_impl(A, A2, W, Y, 0, 0, M, N, K1, K2, epi, act_cols, bias, rowbias, rowbias_group, gamma, beta, residual,
+                     m_dev, stream);
+}
+
+extern "C" int gf_linear_mixed(const void* A, const void* A2, const void* W, void* Y, int in_f16, int out_f16, int64_t M,
+                               int N, int K1, int K2, int epi, int act_cols, const float* bias, const float* rowbias,
+                               int rowbias_group, const float* gamma, const float* beta, const float* residual,
+                               const int* m_dev, gf_stream_t stream) {
+  return linear_impl(A, A2, W, Y, in_f16, out_f16, M, N, K1, K2, epi, act_cols, bias, rowbias, rowbias_group, gamma, beta,
+                     residual, m_dev, stream);
 }
 
 extern "C" int gf_similarity_f16x3(const void* a3, const void* b3, float* sim, int n, int l, int s, int c3,

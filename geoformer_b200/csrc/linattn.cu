@@ -2,10 +2,25 @@
 // element-wise helpers.  Q and K arrive already feature-mapped (elu+1 fused into the projection epilogue).
 #include "common.cuh"
 
+#include <cuda_fp16.h>
+
 #include <atomic>
 
 namespace gf {
 extern std::atomic<int64_t> g_launches;
+
+// 4 consecutive elements as float4 / one element from float: the kernels are templated on the storage type of the
+// projected Q/K/V and of the message (fp32, or fp16 written by the OUT16 GEMM epilogue); all arithmetic stays fp32.
+template <typename T> __device__ __forceinline__ float4 ld4(const T* p);
+template <> __device__ __forceinline__ float4 ld4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 ld4<__half>(const __half* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st1(__half* p, float v) { *p = __float2half_rn(v); }
 
 constexpr int kChunk = 256;   // source tokens per partial reduction block
 
@@ -15,8 +30,8 @@ constexpr int kChunk = 256;   // source tokens per partial reduction block
 // from shared memory as float4 (dim/4 LDS.128 + 1 LDS per dim FMAs).  dim == 32.
 // partial[(n, chunk, h)][dim*dim + dim]: KV block (row d, col v) then Ksum.
 // ---------------------------------------------------------------------------------------------
-template <int D>
-__global__ void linattn_partial_kernel(const float* __restrict__ K, int ldk, const float* __restrict__ V, int ldv,
+template <int D, typename T>
+__global__ void linattn_partial_kernel(const T* __restrict__ K, int ldk, const T* __restrict__ V, int ldv,
                                        int s, int heads, float inv_s, float* __restrict__ partial) {
   extern __shared__ float sh[];
   const int c = heads * D;
@@ -37,8 +52,8 @@ __global__ void linattn_partial_kernel(const float* __restrict__ K, int ldk, con
       float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
       if (r < cnt) {
         const int64_t tok = (int64_t)n * s + t0 + r;
-        kv = *reinterpret_cast<const float4*>(K + tok * ldk + 4 * q);
-        vv = *reinterpret_cast<const float4*>(V + tok * ldv + 4 * q);
+        kv = ld4<T>(K + tok * ldk + 4 * q);
+        vv = ld4<T>(V + tok * ldv + 4 * q);
         vv.x *= inv_s; vv.y *= inv_s; vv.z *= inv_s; vv.w *= inv_s;      // values / v_length (linear_attention.py:46)
       }
       *reinterpret_cast<float4*>(Ks + r * c + 4 * q) = kv;
@@ -85,9 +100,9 @@ __global__ void linattn_finalize_kernel(const float* __restrict__ partial, int n
 // blockDim = heads*dim (thread == output channel); the thread keeps its KV column and the head's Ksum in
 // registers; 128 tokens per CTA, Q rows staged in shared memory and read as broadcast float4.
 // ---------------------------------------------------------------------------------------------
-template <int D>
-__global__ void linattn_apply_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ KV,
-                                     const float* __restrict__ Ksum, float* __restrict__ out, int l, int heads,
+template <int D, typename T>
+__global__ void linattn_apply_kernel(const T* __restrict__ Q, int ldq, const float* __restrict__ KV,
+                                     const float* __restrict__ Ksum, T* __restrict__ out, int l, int heads,
                                      float s_len) {
   extern __shared__ float sh[];
   const int c = heads * D;
@@ -108,7 +123,7 @@ __global__ void linattn_apply_kernel(const float* __restrict__ Q, int ldq, const
     for (int e = t; e < 32 * (c / 4); e += blockDim.x) {
       const int r = e / (c / 4), q = e - r * (c / 4);
       float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < cnt) qv = *reinterpret_cast<const float4*>(Q + ((int64_t)n * l + l0 + r) * ldq + 4 * q);
+      if (r < cnt) qv = ld4<T>(Q + ((int64_t)n * l + l0 + r) * ldq + 4 * q);
       *reinterpret_cast<float4*>(qs + r * c + 4 * q) = qv;
     }
     __syncthreads();
@@ -123,7 +138,7 @@ __global__ void linattn_apply_kernel(const float* __restrict__ Q, int ldq, const
         num = fmaf(q4.z, kvcol[4 * q + 2], num); den = fmaf(q4.z, ks[4 * q + 2], den);
         num = fmaf(q4.w, kvcol[4 * q + 3], num); den = fmaf(q4.w, ks[4 * q + 3], den);
       }
-      out[((int64_t)n * l + l0 + r) * c + t] = num * (1.f / (den + 1e-6f)) * s_len;
+      st1(out + ((int64_t)n * l + l0 + r) * c + t, num * (1.f / (den + 1e-6f)) * s_len);
     }
   }
 }
@@ -202,6 +217,93 @@ __global__ void linattn_window_kernel(const float* __restrict__ Q, int ldq, cons
   }
 }
 
+// fp16 storage variant (Q/K/V written by the OUT16 projection, message read by the fp16-operand merge GEMM):
+// blockDim == heads * D == 128; thread t loads channel pair 2*(t & 63) of the rows of parity t >> 6 as half2 (full
+// 128-byte warp requests), the message rows are staged in shared memory and leave as one flat 16-byte-vector copy.
+template <int D, int TOK>
+__global__ void __launch_bounds__(128)
+linattn_window16_kernel(const __half* __restrict__ Q, int ldq, const __half* __restrict__ K, int ldk,
+                        const __half* __restrict__ V, int ldv, __half* __restrict__ out) {
+  constexpr int c = 128, NR = (TOK + 1) / 2;
+  extern __shared__ float sh[];
+  float* qs = sh;                  // [TOK][c]
+  float* ks = qs + TOK * c;
+  float* vs = ks + TOK * c;
+  float* ksum = vs + TOK * c;      // [c]
+  const int64_t w = blockIdx.x;
+  const int t = threadIdx.x;
+  const int cp = (t & 63) * 2, par = t >> 6;
+  constexpr float ftok = (float)TOK;
+  {
+    __half2 qr[NR], kr[NR], vr[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int r = 2 * i + par;
+      if (r < TOK) {
+        const int64_t row = w * TOK + r;
+        qr[i] = __ldg(reinterpret_cast<const __half2*>(Q + row * ldq + cp));
+        kr[i] = __ldg(reinterpret_cast<const __half2*>(K + row * ldk + cp));
+        vr[i] = __ldg(reinterpret_cast<const __half2*>(V + row * ldv + cp));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int r = 2 * i + par;
+      if (r < TOK) {
+        *reinterpret_cast<float2*>(qs + r * c + cp) = __half22float2(qr[i]);
+        *reinterpret_cast<float2*>(ks + r * c + cp) = __half22float2(kr[i]);
+        const float2 v2 = __half22float2(vr[i]);
+        *reinterpret_cast<float2*>(vs + r * c + cp) = make_float2(v2.x / ftok, v2.y / ftok);
+      }
+    }
+  }
+  __syncthreads();
+  {
+    float a = 0.f;
+#pragma unroll
+    for (int r = 0; r < TOK; ++r) a += ks[r * c + t];
+    ksum[t] = a;
+  }
+  const int h = t / D;
+  float kvcol[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) kvcol[d] = 0.f;
+#pragma unroll 5
+  for (int r = 0; r < TOK; ++r) {
+    const float vv = vs[r * c + t];
+    const float4* kr = reinterpret_cast<const float4*>(ks + r * c + h * D);
+#pragma unroll
+    for (int q = 0; q < D / 4; ++q) {
+      const float4 k4 = kr[q];
+      kvcol[4 * q] = fmaf(k4.x, vv, kvcol[4 * q]); kvcol[4 * q + 1] = fmaf(k4.y, vv, kvcol[4 * q + 1]);
+      kvcol[4 * q + 2] = fmaf(k4.z, vv, kvcol[4 * q + 2]); kvcol[4 * q + 3] = fmaf(k4.w, vv, kvcol[4 * q + 3]);
+    }
+  }
+  __syncthreads();                 // ksum complete; every thread is done with vs (reused below as the output stage)
+  float ksr[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) ksr[d] = ksum[h * D + d];
+  __half* os = reinterpret_cast<__half*>(vs);
+#pragma unroll 5
+  for (int r = 0; r < TOK; ++r) {
+    const float4* qr = reinterpret_cast<const float4*>(qs + r * c + h * D);
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int q = 0; q < D / 4; ++q) {
+      const float4 q4 = qr[q];
+      num = fmaf(q4.x, kvcol[4 * q], num); den = fmaf(q4.x, ksr[4 * q], den);
+      num = fmaf(q4.y, kvcol[4 * q + 1], num); den = fmaf(q4.y, ksr[4 * q + 1], den);
+      num = fmaf(q4.z, kvcol[4 * q + 2], num); den = fmaf(q4.z, ksr[4 * q + 2], den);
+      num = fmaf(q4.w, kvcol[4 * q + 3], num); den = fmaf(q4.w, ksr[4 * q + 3], den);
+    }
+    os[r * c + t] = __float2half_rn(num * (1.f / (den + 1e-6f)) * ftok);
+  }
+  __syncthreads();
+  uint4* dst = reinterpret_cast<uint4*>(out + w * (TOK * c));
+  const uint4* src = reinterpret_cast<const uint4*>(os);
+  for (int i = t; i < TOK * c / 8; i += 128) dst[i] = src[i];
+}
+
 __global__ void add_posenc_kernel(const float4* __restrict__ x, const float4* __restrict__ pe, float4* __restrict__ out,
                                   int64_t per_sample4, int64_t total4) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -237,28 +339,62 @@ extern "C" int64_t gf_linattn_partial_floats(int n, int s, int heads, int dim) {
   return (int64_t)n * heads * gf_cdiv(s, kChunk) * (dim * dim + dim);
 }
 
-extern "C" int gf_linattn_reduce(const float* K, int ldk, const float* V, int ldv, int n, int s, int heads, int dim,
-                                 float* partial, float* KV, float* Ksum, gf_stream_t stream) {
+template <typename T>
+static int linattn_reduce_impl(const T* K, int ldk, const T* V, int ldv, int n, int s, int heads, int dim,
+                               float* partial, float* KV, float* Ksum, gf_stream_t stream) {
   if (n <= 0 || s <= 0 || heads <= 0 || heads > 32 || dim != 32 || (ldk % 4) || (ldv % 4))
     return gf_set_error(GF_ERR_ARG, "gf_linattn_reduce: dim must be 32, heads <= 32, 16-byte aligned rows");
   const int nchunks = gf_cdiv(s, kChunk);
   const size_t smem = (size_t)2 * 32 * heads * dim * sizeof(float);
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(linattn_partial_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+  if (!attr) { cudaFuncSetAttribute(linattn_partial_kernel<32, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
   if (smem > 96 * 1024) return gf_set_error(GF_ERR_ARG, "gf_linattn_reduce: shared memory");
-  linattn_partial_kernel<32><<<dim3(nchunks, n), 32 * heads, smem, STREAM>>>(K, ldk, V, ldv, s, heads, 1.f / (float)s, partial);
+  linattn_partial_kernel<32, T><<<dim3(nchunks, n), 32 * heads, smem, STREAM>>>(K, ldk, V, ldv, s, heads, 1.f / (float)s, partial);
   linattn_finalize_kernel<<<n * heads, 256, 0, STREAM>>>(partial, nchunks, heads, dim, KV, Ksum);
   g_launches += 2;
   GF_CHECK_LAUNCH();
   return GF_OK;
 }
 
-extern "C" int gf_linattn_apply(const float* Q, int ldq, const float* KV, const float* Ksum, float* out, int n, int l,
-                                int s, int heads, int dim, gf_stream_t stream) {
+template <typename T>
+static int linattn_apply_impl(const T* Q, int ldq, const float* KV, const float* Ksum, T* out, int n, int l,
+                              int s, int heads, int dim, gf_stream_t stream) {
   const int c = heads * dim;
   if (n <= 0 || l <= 0 || c > 1024 || dim != 32 || (ldq % 4)) return gf_set_error(GF_ERR_ARG, "gf_linattn_apply: dim must be 32");
   const size_t smem = (size_t)32 * c * sizeof(float);
-  linattn_apply_kernel<32><<<dim3(gf_cdiv(l, 128), n), c, smem, STREAM>>>(Q, ldq, KV, Ksum, out, l, heads, (float)s);
+  linattn_apply_kernel<32, T><<<dim3(gf_cdiv(l, 128), n), c, smem, STREAM>>>(Q, ldq, KV, Ksum, out, l, heads, (float)s);
+  g_launches++;
+  GF_CHECK_LAUNCH();
+  return GF_OK;
+}
+
+extern "C" int gf_linattn_reduce(const float* K, int ldk, const float* V, int ldv, int n, int s, int heads, int dim,
+                                 float* partial, float* KV, float* Ksum, gf_stream_t stream) {
+  return linattn_reduce_impl<float>(K, ldk, V, ldv, n, s, heads, dim, partial, KV, Ksum, stream);
+}
+extern "C" int gf_linattn_apply(const float* Q, int ldq, const float* KV, const float* Ksum, float* out, int n, int l,
+                                int s, int heads, int dim, gf_stream_t stream) {
+  return linattn_apply_impl<float>(Q, ldq, KV, Ksum, out, n, l, s, heads, dim, stream);
+}
+// fp16-storage variants (Q/K/V and the message in fp16; KV / Ksum and all arithmetic in fp32)
+extern "C" int gf_linattn_reduce_f16(const void* K, int ldk, const void* V, int ldv, int n, int s, int heads, int dim,
+                                     float* partial, float* KV, float* Ksum, gf_stream_t stream) {
+  return linattn_reduce_impl<__half>((const __half*)K, ldk, (const __half*)V, ldv, n, s, heads, dim, partial, KV, Ksum, stream);
+}
+extern "C" int gf_linattn_apply_f16(const void* Q, int ldq, const float* KV, const float* Ksum, void* out, int n, int l,
+                                    int s, int heads, int dim, gf_stream_t stream) {
+  return linattn_apply_impl<__half>((const __half*)Q, ldq, KV, Ksum, (__half*)out, n, l, s, heads, dim, stream);
+}
+extern "C" int gf_linattn_window_f16(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* out,
+                                     int64_t n_windows, int tokens, int heads, int dim, gf_stream_t stream) {
+  if (n_windows < 0 || tokens != 25 || dim != 16 || heads != 8 || (ldq % 2) || (ldk % 2) || (ldv % 2))
+    return gf_set_error(GF_ERR_ARG, "gf_linattn_window_f16: needs 25-token windows, 8 heads of dim 16");
+  if (n_windows == 0) return GF_OK;
+  const size_t smem = (size_t)(3 * 25 * 128 + 128) * sizeof(float);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(linattn_window16_kernel<16, 25>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+  linattn_window16_kernel<16, 25><<<(unsigned)n_windows, 128, smem, STREAM>>>((const __half*)Q, ldq, (const __half*)K, ldk,
+                                                                            (const __half*)V, ldv, (__half*)out);
   g_launches++;
   GF_CHECK_LAUNCH();
   return GF_OK;

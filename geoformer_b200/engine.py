@@ -61,6 +61,7 @@ class PackedWeights:
 
     def __init__(self, sd: Dict[str, torch.Tensor], device: torch.device, backbone_dtype: torch.dtype):
         f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
+        f16 = lambda t: t.detach().to(device=device, dtype=torch.float16).contiguous()
         self.device = device
         self.backbone_dtype = backbone_dtype
 
@@ -72,6 +73,8 @@ class PackedWeights:
                 layers.append(dict(
                     wq=f32(wq), wkv=f32(torch.cat([wk, wv], 0)), wqkv=f32(torch.cat([wq, wk, wv], 0)),
                     wm=f32(sd[p + "merge.weight"]), w1=f32(sd[p + "mlp.0.weight"]), w2=f32(sd[p + "mlp.2.weight"]),
+                    # fp16 copies for the GEMMs whose A operand is an fp16 intermediate (message, MLP hidden)
+                    wm16=f16(sd[p + "merge.weight"]), w2_16=f16(sd[p + "mlp.2.weight"]),
                     n1w=f32(sd[p + "norm1.weight"]), n1b=f32(sd[p + "norm1.bias"]),
                     n2w=f32(sd[p + "norm2.weight"]), n2b=f32(sd[p + "norm2.bias"])))
             return layers
@@ -249,9 +252,10 @@ def backbone_forward_tc(pw: PackedWeights, img: torch.Tensor) -> Tuple[torch.Ten
 # --------------------------------------------------------------------------------------------
 def _post_attention(lw: dict, x2d: torch.Tensor, msg: torch.Tensor, act: int) -> torch.Tensor:
     """merge -> LN1 -> MLP(cat[x, msg]) -> LN2 -> residual   (transformer.py:53-60)."""
-    m1 = ops.linear(msg, lw["wm"], epi=EPI_LN, gamma=lw["n1w"], beta=lw["n1b"])
-    h = ops.linear(x2d, lw["w1"], a2=m1, epi=act)
-    return ops.linear(h, lw["w2"], epi=EPI_LN, gamma=lw["n2w"], beta=lw["n2b"], residual=x2d)
+    h16 = ops.act16()
+    m1 = ops.linear(msg, lw["wm16"] if msg.dtype == torch.float16 else lw["wm"], epi=EPI_LN, gamma=lw["n1w"], beta=lw["n1b"])
+    h = ops.linear(x2d, lw["w1"], a2=m1, epi=act, out_f16=h16)
+    return ops.linear(h, lw["w2_16"] if h16 else lw["w2"], epi=EPI_LN, gamma=lw["n2w"], beta=lw["n2b"], residual=x2d)
 
 
 def loftr_layer(lw: dict, x: torch.Tensor, src: torch.Tensor, heads: int) -> torch.Tensor:
@@ -260,12 +264,13 @@ def loftr_layer(lw: dict, x: torch.Tensor, src: torch.Tensor, heads: int) -> tor
     s = src.shape[1]
     d = c // heads
     x2d = x.reshape(n * l, c)
+    a16 = ops.act16()
     if x is src:
-        qkv = ops.linear(x2d, lw["wqkv"], epi=EPI_ELU1, act_cols=2 * c)          # [Q=elu+1 | K=elu+1 | V]
+        qkv = ops.linear(x2d, lw["wqkv"], epi=EPI_ELU1, act_cols=2 * c, out_f16=a16)          # [Q=elu+1 | K=elu+1 | V]
         q, k, v, ldq, ldk = qkv, qkv[:, c:], qkv[:, 2 * c:], 3 * c, 3 * c
     else:
-        q = ops.linear(x2d, lw["wq"], epi=EPI_ELU1, act_cols=c)
-        kv = ops.linear(src.reshape(n * s, c), lw["wkv"], epi=EPI_ELU1, act_cols=c)
+        q = ops.linear(x2d, lw["wq"], epi=EPI_ELU1, act_cols=c, out_f16=a16)
+        kv = ops.linear(src.reshape(n * s, c), lw["wkv"], epi=EPI_ELU1, act_cols=c, out_f16=a16)
         k, v, ldq, ldk = kv, kv[:, c:], c, 2 * c
     msg = ops.linattn(q, ldq, k, ldk, v, ldk, n, l, s, heads, d)
     return _post_attention(lw, x2d, msg, EPI_RELU).view(n, l, c)
@@ -302,12 +307,13 @@ def fine_layer(lw: dict, x: torch.Tensor, src: torch.Tensor, heads: int) -> torc
     m, t, c = x.shape
     d = c // heads
     x2d = x.reshape(m * t, c)
+    a16 = ops.act16() and t == 25 and heads == 8 and d == 16
     if x is src:
-        qkv = ops.linear(x2d, lw["wqkv"], epi=EPI_ELU1, act_cols=2 * c)
+        qkv = ops.linear(x2d, lw["wqkv"], epi=EPI_ELU1, act_cols=2 * c, out_f16=a16)
         q, k, v, ldq, ldk = qkv, qkv[:, c:], qkv[:, 2 * c:], 3 * c, 3 * c
     else:
-        q = ops.linear(x2d, lw["wq"], epi=EPI_ELU1, act_cols=c)
-        kv = ops.linear(src.reshape(m * t, c), lw["wkv"], epi=EPI_ELU1, act_cols=c)
+        q = ops.linear(x2d, lw["wq"], epi=EPI_ELU1, act_cols=c, out_f16=a16)
+        kv = ops.linear(src.reshape(m * t, c), lw["wkv"], epi=EPI_ELU1, act_cols=c, out_f16=a16)
         k, v, ldq, ldk = kv, kv[:, c:], c, 2 * c
     msg = ops.linattn_window(q, ldq, k, ldk, v, ldk, m, t, heads, d)
     return _post_attention(lw, x2d, msg, EPI_RELU).view(m, t, c)

@@ -5,6 +5,7 @@ current CUDA stream.  PyTorch is used for device memory and streams only.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -18,11 +19,21 @@ EPI_RELU, EPI_TANH, EPI_ELU1, EPI_LN = 1, 2, 4, 8
 _LINEAR_IMPL = "tf32"
 _SIM_IMPL = "f16x3"
 _ATTN_IMPL = "tf32"
+# fp16 storage of the intermediates that only feed MMAs (which round to a 10-bit mantissa anyway) or the linear
+# attention kernels: projected Q/K/V, attention message, MLP hidden.  The residual stream stays fp32.
+_ACT16 = os.environ.get("GF_ACT16", "1") != "0"
+
+
+def act16() -> bool:
+    return _ACT16 and _LINEAR_IMPL == "tf32"
 
 
 def set_precision(linear: Optional[str] = None, similarity: Optional[str] = None,
-                  attention: Optional[str] = None) -> None:
-    global _LINEAR_IMPL, _SIM_IMPL, _ATTN_IMPL
+                  attention: Optional[str] = None, activations: Optional[str] = None) -> None:
+    global _LINEAR_IMPL, _SIM_IMPL, _ATTN_IMPL, _ACT16
+    if activations is not None:
+        assert activations in ("f16", "f32")
+        _ACT16 = activations == "f16"
     if attention is not None:
         assert attention in ("tf32", "tf32_mat", "ref")
         _ATTN_IMPL = attention
@@ -117,8 +128,12 @@ def linear(a: torch.Tensor, w: torch.Tensor, a2: Optional[torch.Tensor] = None, 
            bias: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None, rowbias_group: int = 0,
            gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None,
            residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-           impl: Optional[str] = None) -> torch.Tensor:
-    """y[M,N] = epilogue([a | a2] @ w.T); a [M,K1], a2 [M,K2] (optional), w [N,K1+K2], all contiguous fp32."""
+           impl: Optional[str] = None, out_f16: bool = False) -> torch.Tensor:
+    """y[M,N] = epilogue([a | a2] @ w.T); a [M,K1], a2 [M,K2] (optional), w [N,K1+K2], all contiguous fp32 — or all
+    fp16 (kind::f16 MMA, tensor-core path only).  out_f16: fp16 result (lean epilogue: no LN / residual / row bias)."""
+    in_f16 = a.dtype == torch.float16
+    if in_f16 or out_f16:
+        return _linear_mixed(a, w, a2, epi, act_cols, bias, rowbias, rowbias_group, gamma, beta, residual, in_f16, out_f16)
     _chk(a); _chk(w)
     m, k1 = a.shape
     n = w.shape[0]
@@ -133,6 +148,27 @@ def linear(a: torch.Tensor, w: torch.Tensor, a2: Optional[torch.Tensor] = None, 
     _call(fn, a.data_ptr(), _ptr(a2), w.data_ptr(), y.data_ptr(), m, n, k1, k2, epi, act_cols, _ptr(bias),
           _ptr(rowbias), rowbias_group, _ptr(gamma), _ptr(beta), _ptr(residual), None, _stream(),
           tag=f"[{n}x{k1 + k2}]")
+    return y
+
+
+def _linear_mixed(a, w, a2, epi, act_cols, bias, rowbias, rowbias_group, gamma, beta, residual, in_f16, out_f16):
+    dt = torch.float16 if in_f16 else torch.float32
+    _chk(a, dt); _chk(w, dt)
+    if (_LINEAR_IMPL != "tf32"):
+        raise _lib.GeoFormerLibError("fp16 activations exist on the tensor-core path only (set_precision(linear='tf32'))")
+    m, k1 = a.shape
+    n = w.shape[0]
+    k2 = 0 if a2 is None else a2.shape[1]
+    assert a.is_contiguous() and w.is_contiguous() and w.shape[1] == k1 + k2
+    if a2 is not None:
+        _chk(a2, dt)
+        assert a2.is_contiguous() and a2.shape[0] == m
+    if residual is not None:
+        assert residual.is_contiguous() and residual.shape == (m, n) and residual.dtype == torch.float32
+    y = torch.empty((m, n), device=a.device, dtype=torch.float16 if out_f16 else torch.float32)
+    _call("gf_linear_mixed", a.data_ptr(), _ptr(a2), w.data_ptr(), y.data_ptr(), int(in_f16), int(out_f16), m, n, k1, k2,
+          epi, act_cols, _ptr(bias), _ptr(rowbias), rowbias_group, _ptr(gamma), _ptr(beta), _ptr(residual), None,
+          _stream(), tag=f"[{n}x{k1 + k2}{'h' if in_f16 else ''}{'>h' if out_f16 else ''}]")
     return y
 
 
@@ -186,18 +222,21 @@ def linattn(q: torch.Tensor, ldq: int, k: torch.Tensor, ldk: int, v: torch.Tenso
     partial = torch.empty(nfl, device=dev, dtype=torch.float32)
     kv = torch.empty((n, heads, dim, dim), device=dev, dtype=torch.float32)
     ksum = torch.empty((n, heads, dim), device=dev, dtype=torch.float32)
-    _call("gf_linattn_reduce", k.data_ptr(), ldk, v.data_ptr(), ldv, n, s, heads, dim, partial.data_ptr(),
+    sfx = "_f16" if q.dtype == torch.float16 else ""          # fp16 storage of Q/K/V and of the message
+    assert q.dtype == k.dtype == v.dtype
+    _call("gf_linattn_reduce" + sfx, k.data_ptr(), ldk, v.data_ptr(), ldv, n, s, heads, dim, partial.data_ptr(),
               kv.data_ptr(), ksum.data_ptr(), _stream())
-    out = torch.empty((n * l, heads * dim), device=dev, dtype=torch.float32)
-    _call("gf_linattn_apply", q.data_ptr(), ldq, kv.data_ptr(), ksum.data_ptr(), out.data_ptr(), n, l, s, heads,
+    out = torch.empty((n * l, heads * dim), device=dev, dtype=q.dtype)
+    _call("gf_linattn_apply" + sfx, q.data_ptr(), ldq, kv.data_ptr(), ksum.data_ptr(), out.data_ptr(), n, l, s, heads,
               dim, _stream())
     return out
 
 
 def linattn_window(q: torch.Tensor, ldq: int, k: torch.Tensor, ldk: int, v: torch.Tensor, ldv: int, n_windows: int,
                    tokens: int, heads: int, dim: int) -> torch.Tensor:
-    out = torch.empty((n_windows * tokens, heads * dim), device=q.device, dtype=torch.float32)
-    _call("gf_linattn_window", q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, out.data_ptr(),
+    assert q.dtype == k.dtype == v.dtype
+    out = torch.empty((n_windows * tokens, heads * dim), device=q.device, dtype=q.dtype)
+    _call("gf_linattn_window" + ("_f16" if q.dtype == torch.float16 else ""), q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, out.data_ptr(),
               n_windows, tokens, heads, dim, _stream())
     return out
 

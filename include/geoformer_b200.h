@@ -59,6 +59,13 @@ int gf_linear_tf32(const float* A, const float* A2, const float* W, float* Y, in
                    int epi, int act_cols, const float* bias, const float* rowbias, int rowbias_group,
                    const float* gamma, const float* beta, const float* residual, const int* m_dev,
                    gf_stream_t stream);
+/* Same GEMM with fp16 storage on either side (tensor-core path only).  in_f16: A, A2 and W are fp16 (tcgen05 kind::f16,
+ * K % 64 == 0), else fp32 (kind::tf32).  out_f16: Y is fp16 (lean epilogue: scale / bias / activation only), else fp32.
+ * Used for the intermediates of a transformer layer that feed only MMAs or the linear-attention kernels (projected
+ * Q/K/V, attention message, MLP hidden): these GEMMs are bound by their HBM streams, the residual stream stays fp32. */
+int gf_linear_mixed(const void* A, const void* A2, const void* W, void* Y, int in_f16, int out_f16, int64_t M, int N,
+                    int K1, int K2, int epi, int act_cols, const float* bias, const float* rowbias, int rowbias_group,
+                    const float* gamma, const float* beta, const float* residual, const int* m_dev, gf_stream_t stream);
 int gf_linear_ref(const float* A, const float* A2, const float* W, float* Y, int64_t M, int N, int K1, int K2,
                   int epi, int act_cols, const float* bias, const float* rowbias, int rowbias_group,
                   const float* gamma, const float* beta, const float* residual, const int* m_dev,
@@ -99,6 +106,14 @@ int gf_linattn_apply(const float* Q, int ldq, const float* KV, const float* Ksum
  * the cross layer pair match m of the query tensor with match m of the source tensor. */
 int gf_linattn_window(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, float* out,
                       int64_t n_windows, int tokens, int heads, int dim, gf_stream_t stream);
+/* fp16-storage variants: Q/K/V (written by gf_linear_mixed out_f16) and the message are fp16; KV, Ksum and all
+ * arithmetic stay fp32.  gf_linattn_window_f16 needs 25-token windows and 8 heads of dim 16. */
+int gf_linattn_reduce_f16(const void* K, int ldk, const void* V, int ldv, int n, int s, int heads, int dim,
+                          float* partial, float* KV, float* Ksum, gf_stream_t stream);
+int gf_linattn_apply_f16(const void* Q, int ldq, const float* KV, const float* Ksum, void* out, int n, int l, int s,
+                         int heads, int dim, gf_stream_t stream);
+int gf_linattn_window_f16(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* out,
+                          int64_t n_windows, int tokens, int heads, int dim, gf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Coarse matching (utils/coarse_matching.py:110-125 and 161-212).

@@ -106,6 +106,51 @@ def test_linear_tf32_large_multi_tile(ops):
     assert (got - ref).abs().max().item() <= 8e-3
 
 
+F16_OUT_CASES = [c for c in LIN_CASES if not c[8] and not c[9] and not c[7]]          # lean epilogue only
+F16_IN_CASES = [c for c in LIN_CASES if c[2] % 64 == 0 and c[3] % 64 == 0]
+
+
+@pytest.mark.parametrize("case", F16_OUT_CASES)
+def test_linear_tf32_fp16_output(ops, case):
+    """gf_linear_mixed, fp32 operands (kind::tf32) -> fp16 result: tf32 tolerance 8e-3 + one fp16 rounding of an
+    O(1..8) value (2^-11 relative)."""
+    M, N, K1, K2, epi, act_cols, bias, rbg, ln, res = case
+    a, a2, w, b, rb, gamma, beta, r = _lin_inputs(case, 21)
+    want = _lin_torch(case, a, a2, w, b, rb, gamma, beta, r)
+    d = lambda t: None if t is None else dev(t)
+    got = ops.linear(d(a), d(w), a2=d(a2), epi=epi, act_cols=act_cols, bias=d(b), impl="tf32", out_f16=True)
+    assert got.dtype == torch.float16
+    got = got.float().cpu()
+    err = (got - want).abs().max().item()
+    assert err <= 8e-3 + want.abs().max().item() * 2.0 ** -11, f"{case}: max-abs {err}"
+
+
+@pytest.mark.parametrize("case", F16_IN_CASES)
+def test_linear_fp16_operands(ops, case):
+    """gf_linear_mixed with fp16 A / A2 / W (kind::f16, fp32 accumulate and epilogue, fp32 result) against fp64 on the
+    SAME fp16-rounded operands: only accumulation-order error remains (1e-4)."""
+    M, N, K1, K2, epi, act_cols, bias, rbg, ln, res = case
+    a, a2, w, b, rb, gamma, beta, r = _lin_inputs(case, 31)
+    h = lambda t: None if t is None else t.half()
+    a, a2, w = h(a), h(a2), h(w)
+    want = _lin_torch(case, a.float(), None if a2 is None else a2.float(), w.float(), b, rb, gamma, beta, r)
+    d = lambda t: None if t is None else dev(t)
+    got = ops.linear(d(a), d(w), a2=d(a2), epi=epi, act_cols=act_cols, bias=d(b), rowbias=d(rb), rowbias_group=rbg,
+                     gamma=d(gamma), beta=d(beta), residual=d(r), impl="tf32")
+    assert got.dtype == torch.float32
+    err = (got.cpu() - want).abs().max().item()
+    assert err <= 1e-4, f"{case}: max-abs {err}"
+
+
+def test_linear_fp16_large_multi_tile(ops):
+    M, N, K = 128 * 301 + 5, 768, 256
+    a, w = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5)
+    got = ops.linear(dev(a), dev(w), impl="tf32", out_f16=True).float()
+    ref = ops.linear(dev(a), dev(w), impl="ref")
+    torch.cuda.synchronize()
+    assert (got - ref).abs().max().item() <= 8e-3 + ref.abs().max().item() * 2.0 ** -11
+
+
 # ------------------------------------------------------------------------------------------- similarity / conf
 def _feat(n, l, c, seed, rms=3.0, offset=1.5):
     # coarse features under random init have rms ~3 and a common offset -> logits ~40-95 (SURVEY fact 5)
@@ -203,6 +248,35 @@ def test_linear_attention_window(ops):
     got = ops.linattn_window(dev(Q.reshape(m * t, h * d)), h * d, dev(K.reshape(m * t, h * d)), h * d,
                              dev(v.reshape(m * t, h * d)), h * d, m, t, h, d).cpu()
     assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
+
+
+def test_linear_attention_fp16_storage(ops):
+    """fp16-storage variants (Q/K/V and message fp16, arithmetic fp32) against the oracle on the same fp16-rounded
+    inputs: fp32-kernel tolerance + one fp16 rounding of the output."""
+    n, l, s, h, d = 2, 500, 300, 8, 32
+    q, k, v = rnd(n, l, h, d, seed=1), rnd(n, s, h, d, seed=2), rnd(n, s, h, d, seed=3)
+    Q, K, V = (F.elu(q) + 1).half(), (F.elu(k) + 1).half(), v.half()
+    # oracle applies elu+1 itself: feed it inverse-mapped values is not possible, so restate the two lines here
+    Qf, Kf, Vf = Q.double(), K.double(), V.double()
+    KV = torch.einsum("nshd,nshv->nhdv", Kf, Vf / s)
+    Z = 1 / (torch.einsum("nlhd,nhd->nlh", Qf, Kf.sum(1)) + 1e-6)
+    want = (torch.einsum("nlhd,nhdv,nlh->nlhv", Qf, KV, Z) * s).reshape(n * l, h * d).float()
+    got = ops.linattn(dev(Q.reshape(n * l, h * d)), h * d, dev(K.reshape(n * s, h * d)), h * d,
+                      dev(V.reshape(n * s, h * d)), h * d, n, l, s, h, d)
+    assert got.dtype == torch.float16
+    assert (got.float().cpu() - want).abs().max().item() <= (2e-5 + 2.0 ** -11) * max(1.0, want.abs().max().item())
+    # strided Q|K|V buffer, window kernel
+    m, t, h, d = 37, 25, 8, 16
+    c = h * d
+    qkv = torch.cat([F.elu(rnd(m * t, c, seed=4)) + 1, F.elu(rnd(m * t, c, seed=5)) + 1, rnd(m * t, c, seed=6)], 1).half()
+    Qf, Kf, Vf = (qkv[:, i * c:(i + 1) * c].double().reshape(m, t, h, d) for i in range(3))
+    KV = torch.einsum("nshd,nshv->nhdv", Kf, Vf / t)
+    Z = 1 / (torch.einsum("nlhd,nhd->nlh", Qf, Kf.sum(1)) + 1e-6)
+    want = (torch.einsum("nlhd,nhdv,nlh->nlhv", Qf, KV, Z) * t).reshape(m * t, c).float()
+    g = dev(qkv)
+    got = ops.linattn_window(g, 3 * c, g[:, c:], 3 * c, g[:, 2 * c:], 3 * c, m, t, h, d)
+    assert got.dtype == torch.float16
+    assert (got.float().cpu() - want).abs().max().item() <= (2e-5 + 2.0 ** -11) * max(1.0, want.abs().max().item())
 
 
 # ------------------------------------------------------------------------------------------- geo attention
