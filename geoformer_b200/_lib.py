@@ -27,6 +27,7 @@ SIGNATURES = {
     "gf_add_posenc": (I, [P, P, P, I, L, I, P]),
     "gf_linattn_partial_floats": (L, [I, I, I, I]),
     "gf_linear_mixed": (I, [P, P, P, P, I, I, L, I, I, I, I, I, P, P, I, P, P, P, P, P]),
+    "gf_fine_layer": (I, [P, P, P, P, P, P, P, P, L, P]),
     "gf_linattn_reduce_f16": (I, [P, I, P, I, I, I, I, I, P, P, P, P]),
     "gf_linattn_apply_f16": (I, [P, I, P, P, P, I, I, I, I, I, P]),
     "gf_linattn_window_f16": (I, [P, I, P, I, P, I, P, L, I, I, I, P]),

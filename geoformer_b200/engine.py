@@ -23,6 +23,8 @@ _POOL: Optional[ThreadPoolExecutor] = None
 # inference default: coarse matching without materialising the L x S matrix (conf_matrix is only produced when
 # model.materialize is set); GF_FUSED_MATCHING=0 selects the materialised kernels
 FUSED_MATCHING = os.environ.get("GF_FUSED_MATCHING", "1") != "0"
+# fine-level LoFTR layers as one kernel per layer call (csrc/fine_layer.cu); GF_FUSED_FINE=0 selects the per-op kernels
+FUSED_FINE_LAYER = os.environ.get("GF_FUSED_FINE", "1") != "0"
 
 
 def _pool() -> ThreadPoolExecutor:
@@ -56,6 +58,29 @@ def pack_conv3x3(w: torch.Tensor, b: Optional[torch.Tensor], cin_p: int, cout_p:
     return wt.to(device=device, dtype=torch.bfloat16).contiguous(), bias.to(device)
 
 
+def pack_fine_layer(wq, wk, wv, wm, w1, w2, device) -> torch.Tensor:
+    """Weights of one fine-level layer as the 30 operand blocks [30][128 rows][128 B] gf_fine_layer streams per tile:
+    12 fp32 blocks of Wq|Wk|Wv (n-chunk major, 32-float k-blocks), 2 fp16 blocks of merge (64-half k-blocks), 8 fp32
+    blocks of mlp.0[:, :128], 4 fp16 blocks of mlp.0[:, 128:], 4 fp16 blocks of mlp.2."""
+    assert wq.shape == (128, 128) and w1.shape == (256, 256) and w2.shape == (128, 256)
+    blocks = []
+
+    def add(w, nchunks, k0, kblocks, half):
+        kw = 64 if half else 32
+        for nc in range(nchunks):
+            for kb in range(kblocks):
+                blk = w[nc * 128:(nc + 1) * 128, k0 + kb * kw:k0 + (kb + 1) * kw].detach().cpu()
+                blk = blk.to(torch.float16 if half else torch.float32).contiguous()
+                blocks.append(blk.view(torch.uint8).reshape(128, 128))
+
+    add(torch.cat([wq, wk, wv], 0), 3, 0, 4, False)
+    add(wm, 1, 0, 2, True)
+    add(w1, 2, 0, 4, False)
+    add(w1, 2, 128, 2, True)
+    add(w2, 1, 0, 4, True)
+    return torch.stack(blocks).contiguous().to(device)
+
+
 class PackedWeights:
     """Device-resident, kernel-ready weights derived from a reference-schema state dict."""
 
@@ -82,6 +107,11 @@ class PackedWeights:
         self.coarse = enc("loftr_coarse", 8)
         self.geo = enc("geo_module.des_transformer", 4)
         self.fine = enc("loftr_fine", 2)
+        for i, lw in enumerate(self.fine):
+            p = f"loftr_fine.layers.{i}."
+            if tuple(sd[p + "q_proj.weight"].shape) == (128, 128):
+                lw["wpack"] = pack_fine_layer(sd[p + "q_proj.weight"], sd[p + "k_proj.weight"], sd[p + "v_proj.weight"],
+                                              sd[p + "merge.weight"], sd[p + "mlp.0.weight"], sd[p + "mlp.2.weight"], device)
         wm = sd["fine_preprocess.merge_feat.weight"]
         cf = wm.shape[0]
         self.fp = dict(wd=f32(sd["fine_preprocess.down_proj.weight"]), bd=f32(sd["fine_preprocess.down_proj.bias"]),
@@ -306,6 +336,8 @@ def fine_layer(lw: dict, x: torch.Tensor, src: torch.Tensor, heads: int) -> torc
     """LoFTR layer at the fine level: x/src [m, 25, 128]; one CTA per window for the attention."""
     m, t, c = x.shape
     d = c // heads
+    if FUSED_FINE_LAYER and ops.act16() and (t, c, heads) == (25, 128, 8) and "wpack" in lw:
+        return ops.fine_layer_fused(x.contiguous(), src.contiguous(), lw["wpack"], lw["n1w"], lw["n1b"], lw["n2w"], lw["n2b"])
     x2d = x.reshape(m * t, c)
     a16 = ops.act16() and t == 25 and heads == 8 and d == 16
     if x is src:

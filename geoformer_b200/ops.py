@@ -241,6 +241,18 @@ def linattn_window(q: torch.Tensor, ldq: int, k: torch.Tensor, ldk: int, v: torc
     return out
 
 
+def fine_layer_fused(x: torch.Tensor, src: torch.Tensor, wpack: torch.Tensor, n1w, n1b, n2w, n2b) -> torch.Tensor:
+    """One fine-level LoFTR layer in a single kernel (csrc/fine_layer.cu).  x/src [m, 25, 128] fp32 contiguous."""
+    _chk(x); _chk(src)
+    m, t, c = x.shape
+    assert (t, c) == (25, 128) and src.shape == x.shape and x.is_contiguous() and src.is_contiguous()
+    assert wpack.dtype == torch.uint8 and wpack.shape == (30, 128, 128) and wpack.is_contiguous()
+    y = torch.empty_like(x)
+    _call("gf_fine_layer", x.data_ptr(), src.data_ptr(), wpack.data_ptr(), n1w.data_ptr(), n1b.data_ptr(), n2w.data_ptr(),
+          n2b.data_ptr(), y.data_ptr(), m, _stream(), tag="[cross]" if src.data_ptr() != x.data_ptr() else "[self]")
+    return y
+
+
 # ------------------------------------------------------------------ coarse matching
 def similarity(f0: torch.Tensor, f1: torch.Tensor, temperature: float, impl: Optional[str] = None) -> torch.Tensor:
     """sim[n,l,s] = (f0/sqrt(C)) . (f1/sqrt(C)) / temperature  (coarse_matching.py:110-119)."""

@@ -485,3 +485,35 @@ def test_upsample_add(ops):
     want = lat.float() + F.interpolate(src.float(), size=(2 * hs, 2 * ws), mode="bilinear", align_corners=True)
     got = ops.upsample_add(dev(lat.permute(0, 2, 3, 1)), dev(src.permute(0, 2, 3, 1))).cpu().float().permute(0, 3, 1, 2)
     assert (got - want).abs().max().item() <= 1e-2 * want.abs().max().item()
+
+
+# ------------------------------------------------------------------------------------------- fused fine layer
+@pytest.mark.parametrize("windows", [3, 37, 1003])
+@pytest.mark.parametrize("cross", [False, True])
+def test_fine_layer_fused(ops, windows, cross):
+    """gf_fine_layer (whole LoFTR layer of the fine level in one tcgen05 kernel) against the per-op fp32 FFMA kernels
+    of the same library.  Operands are tf32 / fp16 (10-bit mantissa) with fp32 accumulation: 8e-3 max-abs on the
+    LayerNorm'd O(1) output (same bar as gf_linear_tf32), partial last tile and ragged window counts included."""
+    from geoformer_b200 import engine
+    g = lambda *sh, seed, scale=1.0: rnd(*sh, seed=seed, scale=scale)
+    wq, wk, wv, wm = (g(128, 128, seed=s, scale=128 ** -0.5) for s in (1, 2, 3, 4))
+    w1, w2 = g(256, 256, seed=5, scale=256 ** -0.5), g(128, 256, seed=6, scale=256 ** -0.5)
+    lw = dict(wq=dev(wq), wkv=dev(torch.cat([wk, wv], 0)), wqkv=dev(torch.cat([wq, wk, wv], 0)), wm=dev(wm), w1=dev(w1), w2=dev(w2),
+              wm16=dev(wm.half()), w2_16=dev(w2.half()),
+              n1w=dev(1 + 0.1 * g(128, seed=7)), n1b=dev(0.1 * g(128, seed=8)),
+              n2w=dev(1 + 0.1 * g(128, seed=9)), n2b=dev(0.1 * g(128, seed=10)))
+    lw["wpack"] = engine.pack_fine_layer(wq, wk, wv, wm, w1, w2, "cuda:0")
+    x = dev(g(windows, 25, 128, seed=11))
+    src = dev(g(windows, 25, 128, seed=12)) if cross else x
+    try:
+        ops.set_precision(linear="ref")
+        engine.FUSED_FINE_LAYER = False
+        want = engine.fine_layer(lw, x, src, 8)
+    finally:
+        ops.set_precision(linear="tf32")
+        engine.FUSED_FINE_LAYER = True
+    got = engine.fine_layer(lw, x, src, 8)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape and torch.isfinite(got).all()
+    err = (got - want).abs().max().item()
+    assert err <= 8e-3, f"windows={windows} cross={cross}: max-abs {err}"
