@@ -9,8 +9,9 @@
 //               message = Q KV / (Q Ksum + eps), written over Q in place in UMMA operand layout
 //   GEMM1  merge (kind::f16, A = that message) -> LayerNorm1
 //   GEMM2  MLP up: x W1x^T (tf32) + m1 W1m^T (f16) into one accumulator -> ReLU
-//   GEMM3  MLP down (f16) -> LayerNorm2 -> + x (still resident) -> coalesced store
-// Weights stream from L2 through a 3-stage TMA ring in a fixed order of 30 [128 x 128 B] blocks per tile.
+//   GEMM3  MLP down (f16) -> LayerNorm2 -> + x (still resident) -> TMA store (boxes of 125 rows)
+// Weights stream from L2 through a 3-stage TMA ring in a fixed order of 30 [128 x 128 B] blocks per tile
+// (q|k|v, MLP-up x half, merge, MLP-up m1 half, MLP-down).
 // HBM traffic per token-layer: 512 B (x) [+ 512 B src] + 512 B (y) instead of ~6.9 KB for the unfused kernels.
 //
 // warp 0: TMA producer | warp 1: MMA issuer + TMEM owner | warps 2..9: epilogue (two warps per TMEM lane quadrant).
@@ -101,7 +102,7 @@ __device__ __forceinline__ void normalize64(float (&v)[64], float mean, float rs
 
 __global__ void __launch_bounds__(320, 1)
 fine_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmS,
-                  const __grid_constant__ CUtensorMap tmW, const Params p) {
+                  const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BARS);
@@ -110,11 +111,13 @@ fine_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint64_t* tile_free = x_full + 1;
   uint64_t* d_full = tile_free + 1;          // [4]: D0..D3 accumulators complete
   uint64_t* a_full = d_full + 4;             // [3]: message, m1, hidden written as A operands
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 3);
+  uint64_t* d0_free = a_full + 3;            // q|k|v copied out of TMEM: the MLP-up accumulator may overwrite them
+  uint64_t* r1_free = d0_free + 1;           // residual read done: the next x tile may land
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r1_free + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmX); ptx::prefetch_tmap(&tmS); ptx::prefetch_tmap(&tmW); }
+  if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmX); ptx::prefetch_tmap(&tmS); ptx::prefetch_tmap(&tmW); ptx::prefetch_tmap(&tmY); }
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
@@ -122,6 +125,8 @@ fine_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       ptx::mbar_init(tile_free, 1);
       for (int i = 0; i < 4; ++i) ptx::mbar_init(&d_full[i], 1);
       for (int i = 0; i < 3; ++i) ptx::mbar_init(&a_full[i], 256);
+      ptx::mbar_init(d0_free, 1);
+      ptx::mbar_init(r1_free, 1);
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -138,12 +143,14 @@ fine_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
-        if (it > 0) ptx::mbar_wait(tile_free, (it - 1) & 1);
+        if (it > 0) ptx::mbar_wait(r1_free, (it - 1) & 1);
         const int row0 = t * ROWS;
         ptx::mbar_expect_tx(x_full, p.cross ? 2 * 4 * BLK : 4 * BLK);
         for (int kb = 0; kb < 4; ++kb) ptx::tma_load_3d(smem + R1 + kb * BLK, &tmX, x_full, kb * 32, row0, 0);
-        if (p.cross)
+        if (p.cross) {
+          if (it > 0) ptx::mbar_wait(tile_free, (it - 1) & 1);      // R2 (output staging) has been read by the TMA store
           for (int kb = 0; kb < 4; ++kb) ptx::tma_load_3d(smem + R2 + kb * BLK, &tmS, x_full, kb * 32, row0, 0);
+        }
         if ((p.debug & 1) && it > 0) continue;
         for (int b = 0; b < NBLK; ++b) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -187,14 +194,17 @@ fine_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           for (int kb = 0; kb < 4; ++kb) step(0, a0 + kb * BLK, D0 + nc * 128, kb == 0);
         }
         ptx::umma_commit(&d_full[0]);
+        // GEMM2, x half (tf32): runs under the attention math as soon as q|k|v have left TMEM
+        ptx::mbar_wait(d0_free, par);
+        ptx::tc_fence_after();
+        for (int nc = 0; nc < 2; ++nc)
+          for (int kb = 0; kb < 4; ++kb) step(0, s_r1 + kb * BLK, D2 + nc * 128, kb == 0);
         // GEMM1: merge(message)
         ptx::mbar_wait(&a_full[0], par);
         ptx::tc_fence_after();
         for (int kb = 0; kb < 2; ++kb) step(1, s_r3 + kb * BLK, D1, kb == 0);
         ptx::umma_commit(&d_full[1]);
-        // GEMM2: x half (tf32) then m1 half (f16) into the same accumulator
-        for (int nc = 0; nc < 2; ++nc)
-          for (int kb = 0; kb < 4; ++kb) step(0, s_r1 + kb * BLK, D2 + nc * 128, kb == 0);
+        // GEMM2, m1 half (f16) into the same accumulator
         ptx::mbar_wait(&a_full[1], par);
         ptx::tc_fence_after();
         for (int nc = 0; nc < 2; ++nc)
@@ -229,6 +239,7 @@ fine_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       // ---------------- E0a: Q (elu+1) -> fp16 UMMA layout in R3; K (elu+1), V -> fp16 [row][256 B] in R2 ----------------
       ptx::mbar_wait(&d_full[0], par);
       ptx::tc_fence_after();
+      epi_sync();                                      // thread 0 has seen the previous tile's TMA store finish reading R2
 #pragma unroll 1
       for (int i = 0; i < 6; ++i) {
         const int c = 2 * i + half;                    // 32-column chunk of q|k|v: 0..3 q, 4..7 k, 8..11 v
@@ -255,7 +266,9 @@ fine_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + (((((c - 4) & 3) * 4 + j) ^ (r & 15)) << 4)) = u[j];
         }
       }
+      ptx::tc_fence_before();
       epi_sync();
+      if (et == 0) ptx::mbar_arrive(d0_free);
       // ---------------- E0b: linear attention per (window, head) on mma.sync; message overwrites Q in place ----------------
       if (!(p.debug & 2)) {
         const uint32_t k16 = ptx::smem_addr(r2), v16 = k16 + 32768, q16 = ptx::smem_addr(r3);
@@ -374,26 +387,25 @@ fine_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj) {
             const int j = 16 * half + jj;                  // float4 index inside the 128-wide row
-            const float4 x4 = *reinterpret_cast<const float4*>(r1 + (j >> 3) * BLK + r * 128 + (((j & 7) ^ sw7) << 4));
-            *reinterpret_cast<float4*>(r2 + r * 512 + ((j ^ lane) << 4)) =
+            const int off = (j >> 3) * BLK + r * 128 + (((j & 7) ^ sw7) << 4);     // same swizzled block layout for x and y
+            const float4 x4 = *reinterpret_cast<const float4*>(r1 + off);
+            *reinterpret_cast<float4*>(r2 + off) =
                 make_float4(v[4 * jj] + x4.x, v[4 * jj + 1] + x4.y, v[4 * jj + 2] + x4.z, v[4 * jj + 3] + x4.w);
           }
         }
       }
+      ptx::fence_proxy_async();
       ptx::tc_fence_before();
       epi_sync();
-      {
-        const int64_t left = p.rows - row0;
-        const int nrows = (int)(left < ROWS ? left : ROWS);
-        float4* dst = reinterpret_cast<float4*>(p.y + row0 * C);
-        for (int i = et; i < nrows * 32; i += 256) {
-          const int rr = i >> 5, j = i & 31;
-          dst[i] = *reinterpret_cast<const float4*>(r2 + rr * 512 + ((j ^ (rr & 31)) << 4));
-        }
+      if (et == 0) {
+        ptx::mbar_arrive(r1_free);
+        for (int kb = 0; kb < 4; ++kb) ptx::tma_store_3d(&tmY, r2 + kb * BLK, kb * 32, (int)row0, 0);   // box = 125 rows
+        ptx::bulk_commit();
+        ptx::bulk_wait_read<0>();
+        ptx::mbar_arrive(tile_free);
       }
-      epi_sync();
-      if (et == 0) ptx::mbar_arrive(tile_free);
     }
+    if (et == 0) ptx::bulk_wait<0>();                  // output stores have landed
   }
 
   ptx::tc_fence_before();
@@ -417,11 +429,12 @@ extern "C" int gf_fine_layer(const float* x, const float* src, const void* wpack
   if (windows == 0) return GF_OK;
   const int64_t rows = windows * fl::TOK;
   if (rows > 0x7fffff00LL) return gf_set_error(GF_ERR_ARG, "gf_fine_layer: too many rows");
-  CUtensorMap tx, ts, tw;
+  CUtensorMap tx, ts, tw, ty;
   int rc;
   if ((rc = make_tmap(&tx, x, 4, fl::C, rows, 1, fl::C, 0, 128))) return rc;
   if ((rc = make_tmap(&ts, src, 4, fl::C, rows, 1, fl::C, 0, 128))) return rc;
   if ((rc = make_tmap(&tw, wpack, 4, 32, (int64_t)fl::NBLK * 128, 1, 32, 0, 128))) return rc;
+  if ((rc = make_tmap(&ty, y, 4, fl::C, rows, 1, fl::C, 0, fl::ROWS))) return rc;      // store boxes of 125 rows: tiles do not overlap
   fl::Params p{};
   p.y = y; p.gamma1 = gamma1; p.beta1 = beta1; p.gamma2 = gamma2; p.beta2 = beta2;
   p.rows = rows; p.tiles = (int)((windows + fl::WIN - 1) / fl::WIN); p.cross = (src != x) ? 1 : 0;
@@ -433,7 +446,7 @@ extern "C" int gf_fine_layer(const float* x, const float* src, const void* wpack
     attr_set = true;
   }
   const int grid = p.tiles < num_sms() ? p.tiles : num_sms();
-  fl::fine_layer_kernel<<<grid, 320, fl::SMEM_BYTES, (cudaStream_t)stream>>>(tx, ts, tw, p);
+  fl::fine_layer_kernel<<<grid, 320, fl::SMEM_BYTES, (cudaStream_t)stream>>>(tx, ts, tw, ty, p);
   g_launches++;
   GF_CHECK_LAUNCH();
   return GF_OK;

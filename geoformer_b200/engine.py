@@ -60,8 +60,8 @@ def pack_conv3x3(w: torch.Tensor, b: Optional[torch.Tensor], cin_p: int, cout_p:
 
 def pack_fine_layer(wq, wk, wv, wm, w1, w2, device) -> torch.Tensor:
     """Weights of one fine-level layer as the 30 operand blocks [30][128 rows][128 B] gf_fine_layer streams per tile:
-    12 fp32 blocks of Wq|Wk|Wv (n-chunk major, 32-float k-blocks), 2 fp16 blocks of merge (64-half k-blocks), 8 fp32
-    blocks of mlp.0[:, :128], 4 fp16 blocks of mlp.0[:, 128:], 4 fp16 blocks of mlp.2."""
+    12 fp32 blocks of Wq|Wk|Wv (n-chunk major, 32-float k-blocks), 8 fp32 blocks of mlp.0[:, :128], 2 fp16 blocks of
+    merge (64-half k-blocks), 4 fp16 blocks of mlp.0[:, 128:], 4 fp16 blocks of mlp.2."""
     assert wq.shape == (128, 128) and w1.shape == (256, 256) and w2.shape == (128, 256)
     blocks = []
 
@@ -74,8 +74,8 @@ def pack_fine_layer(wq, wk, wv, wm, w1, w2, device) -> torch.Tensor:
                 blocks.append(blk.view(torch.uint8).reshape(128, 128))
 
     add(torch.cat([wq, wk, wv], 0), 3, 0, 4, False)
-    add(wm, 1, 0, 2, True)
     add(w1, 2, 0, 4, False)
+    add(wm, 1, 0, 2, True)
     add(w1, 2, 128, 2, True)
     add(w2, 1, 0, 4, True)
     return torch.stack(blocks).contiguous().to(device)

@@ -217,7 +217,7 @@ int gf_select_rows(float* dst, const float* src, const int* flag, int n, int64_t
 /* One whole LoFTR encoder layer of the fine level (loftr_module/transformer.py:28-60 + linear_attention.py:33-49) as
  * one persistent tcgen05 kernel: 25-token windows, d_model 128, 8 heads.  x/src [windows*25, 128] fp32 (src == x for a
  * 'self' layer), y likewise (must not alias x/src).  wpack: the layer's weights as 30 operand blocks [30][128][128 B] in
- * streaming order (12 fp32 blocks Wq|Wk|Wv, 2 fp16 merge, 8 fp32 mlp.0[:, :128], 4 fp16 mlp.0[:, 128:], 4 fp16 mlp.2;
+ * streaming order (12 fp32 blocks Wq|Wk|Wv, 8 fp32 mlp.0[:, :128], 2 fp16 merge, 4 fp16 mlp.0[:, 128:], 4 fp16 mlp.2;
  * geoformer_b200/engine.py::pack_fine_layer).  Intermediates never leave the SM. */
 int gf_fine_layer(const float* x, const float* src, const void* wpack, const float* gamma1, const float* beta1,
                   const float* gamma2, const float* beta2, float* y, int64_t windows, gf_stream_t stream);
