@@ -22,7 +22,8 @@ template <> __device__ __forceinline__ float4 ld4<__half>(const __half* p) {
 __device__ __forceinline__ void st1(float* p, float v) { *p = v; }
 __device__ __forceinline__ void st1(__half* p, float v) { *p = __float2half_rn(v); }
 
-constexpr int kChunk = 256;   // source tokens per partial reduction block
+constexpr int kChunk = 256;      // source tokens per partial reduction block (fp32 kernels)
+constexpr int kChunkMma = 128;   // same for the mma.sync kernel (2 resident CTAs per SM: more, smaller blocks)
 
 // ---------------------------------------------------------------------------------------------
 // reduce, stage 1.  One CTA per (256-token chunk, sample); warp w == head w (blockDim = 32 * heads).
@@ -217,6 +218,182 @@ __global__ void linattn_window_kernel(const float* __restrict__ Q, int ldq, cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp16-storage path on the warp-level tensor cores (mma.sync m16n8k16, fp32 accumulate): 8 heads of dim 32.
+// Both products of the linear attention have a tiny M/N (32 x 32 per head) and a long or streaming third dimension,
+// so they run as register-fragment MMAs with the operands staged once in shared memory:
+//   reduce: C' = V_h^T K_h over the tokens (tokens = MMA K); a constant "ones" A tile yields Ksum = 1^T K_h for free
+//   apply : out = Q_h (KV_h | Ksum_h/S): the KV block is held as B fragments in registers for the whole CTA
+// Rows are padded to 528 B in shared memory so that every ldmatrix phase (8 rows x 16 B) is conflict-free.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPitch = 528;          // bytes per staged row: 256 fp16 channels + 16 B pad
+
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pk2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// reduce, stage 1 (same partial[] format as linattn_partial_kernel).  grid (chunks of 256 tokens, n), 256 threads.
+__global__ void __launch_bounds__(256)
+linattn_partial_mma_kernel(const __half* __restrict__ K, int ldk, const __half* __restrict__ V, int ldv, int s,
+                           int chunk_tokens, float inv_s, float* __restrict__ partial) {
+  constexpr int D = 32, HEADS = 8, SLAB = 32, BUF = 2 * SLAB * kPitch;       // one buffer: K slab | V slab
+  extern __shared__ __align__(16) uint8_t dyn_smem[];                        // two buffers, filled by cp.async one slab ahead
+  const int chunk = blockIdx.x, n = blockIdx.y, nchunks = gridDim.x;
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3, lrow = lane & 7, lmat = lane >> 3;
+  const int s0 = chunk * chunk_tokens, s1 = min(s, s0 + chunk_tokens);
+  float cv[2][4][4], co[4][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) cv[a][b][c] = 0.f;
+#pragma unroll
+  for (int b = 0; b < 4; ++b)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) co[b][c] = 0.f;
+  const uint32_t sm_a = smem_u32(dyn_smem);
+  const uint32_t one = (g == 0) ? 0x3C003C00u : 0u;
+  const uint32_t ao[4] = {one, 0u, one, 0u};
+  auto issue = [&](int t0, int buf) {           // rows past the end of the sequence are zero-filled (src-size 0)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = threadIdx.x + 256 * i, r = e >> 5, q = e & 31;
+      const bool ok = t0 + r < s1;
+      const int64_t tok = (int64_t)n * s + (ok ? t0 + r : s0);
+      const uint32_t dst = sm_a + buf * BUF + r * kPitch + q * 16;
+      const uint32_t nbytes = ok ? 16u : 0u;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(K + tok * ldk + q * 8), "r"(nbytes) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + SLAB * kPitch), "l"(V + tok * ldv + q * 8), "r"(nbytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue(s0, 0);
+  int buf = 0;
+  for (int t0 = s0; t0 < s1; t0 += SLAB, buf ^= 1) {
+    if (t0 + SLAB < s1) { issue(t0 + SLAB, buf ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const uint32_t ks_a = sm_a + buf * BUF, vs_a = ks_a + SLAB * kPitch;
+#pragma unroll
+    for (int kk = 0; kk < SLAB / 16; ++kk) {
+      uint32_t b[2][4];
+#pragma unroll
+      for (int ip = 0; ip < 2; ++ip) {      // n-tiles (d1) 2ip, 2ip+1: matrices (tok lo, c), (tok hi, c), (tok lo, c+1), (tok hi, c+1)
+        const int row = kk * 16 + lrow + ((lmat & 1) << 3), c16 = 4 * h + 2 * ip + (lmat >> 1);
+        ldsm4t(b[ip], ks_a + row * kPitch + c16 * 16);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {      // d2 = 16 mt ..: matrices (tok lo, ch lo), (tok lo, ch hi), (tok hi, ch lo), (tok hi, ch hi)
+        uint32_t a[4];
+        const int row = kk * 16 + lrow + ((lmat >> 1) << 3), c16 = 4 * h + 2 * mt + (lmat & 1);
+        ldsm4t(a, vs_a + row * kPitch + c16 * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mma_f16(cv[mt][i], a, b[i >> 1][2 * (i & 1)], b[i >> 1][2 * (i & 1) + 1]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mma_f16(co[i], ao, b[i >> 1][2 * (i & 1)], b[i >> 1][2 * (i & 1) + 1]);
+    }
+    __syncthreads();                             // this buffer is refilled by the cp.async issued in the next iteration
+  }
+  float* out = partial + (((int64_t)n * nchunks + chunk) * HEADS + h) * (D * D + D);
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {           // cv[mt][i]: rows d2 = 16mt + g (+8), cols d1 = 8i + 2t (+1); stored as KV[d1][d2]
+      const int d2 = 16 * mt + g, d1 = 8 * i + 2 * t;
+      out[d1 * D + d2] = cv[mt][i][0] * inv_s; out[(d1 + 1) * D + d2] = cv[mt][i][1] * inv_s;
+      out[d1 * D + d2 + 8] = cv[mt][i][2] * inv_s; out[(d1 + 1) * D + d2 + 8] = cv[mt][i][3] * inv_s;
+    }
+  if (g == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { out[D * D + 8 * i + 2 * t] = co[i][0]; out[D * D + 8 * i + 2 * t + 1] = co[i][1]; }
+  }
+}
+
+// apply.  grid (ceil(l / 64), n), 256 threads (warp == head); the message overwrites Q in shared memory and leaves
+// as full 512-byte rows.
+__global__ void __launch_bounds__(256)
+linattn_apply_mma_kernel(const __half* __restrict__ Q, int ldq, const float* __restrict__ KV, const float* __restrict__ Ksum,
+                         __half* __restrict__ out, int l, float s_len) {
+  constexpr int D = 32, HEADS = 8, ROWS = 64, C = HEADS * D;
+  __shared__ __align__(16) uint8_t qs[ROWS * kPitch];
+  const int n = blockIdx.y, l0 = blockIdx.x * ROWS;
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3, lrow = lane & 7, lmat = lane >> 3;
+  const int rows = min(ROWS, l - l0);
+  for (int e = threadIdx.x; e < ROWS * 32; e += 256) {
+    const int r = e >> 5, q = e & 31;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows) v = __ldg(reinterpret_cast<const uint4*>(Q + ((int64_t)n * l + l0 + r) * ldq) + q);
+    *reinterpret_cast<uint4*>(qs + r * kPitch + q * 16) = v;
+  }
+  // B fragments: k = d1 (two k-steps), n = d2 (four tiles) + one tile whose column 0 is Ksum / S
+  const float* kv = KV + ((int64_t)n * HEADS + h) * D * D;
+  const float* ksum = Ksum + ((int64_t)n * HEADS + h) * D;
+  const float inv_s = 1.f / s_len;
+  uint32_t b[2][5][2];
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d1 = 16 * kk + 2 * t, d2 = 8 * j + g;
+      b[kk][j][0] = pk2(kv[d1 * D + d2], kv[(d1 + 1) * D + d2]);
+      b[kk][j][1] = pk2(kv[(d1 + 8) * D + d2], kv[(d1 + 9) * D + d2]);
+    }
+    const int d1 = 16 * kk + 2 * t;
+    b[kk][4][0] = (g == 0) ? pk2(ksum[d1] * inv_s, ksum[d1 + 1] * inv_s) : 0u;
+    b[kk][4][1] = (g == 0) ? pk2(ksum[d1 + 8] * inv_s, ksum[d1 + 9] * inv_s) : 0u;
+  }
+  __syncthreads();
+  const uint32_t qs_a = smem_u32(qs);
+  const float eps = 1e-6f * inv_s;
+#pragma unroll 1
+  for (int mt = 0; mt < ROWS / 16; ++mt) {
+    float acc[5][4];
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {      // matrices (tok lo, k lo), (tok hi, k lo), (tok lo, k hi), (tok hi, k hi)
+      uint32_t a[4];
+      const int row = 16 * mt + lrow + ((lmat & 1) << 3), c16 = 4 * h + 2 * kk + (lmat >> 1);
+      ldsm4(a, qs_a + row * kPitch + c16 * 16);
+#pragma unroll
+      for (int j = 0; j < 5; ++j) mma_f16(acc[j], a, b[kk][j][0], b[kk][j][1]);
+    }
+    const float z_lo = 1.f / (__shfl_sync(0xffffffffu, acc[4][0], lane & ~3) + eps);
+    const float z_hi = 1.f / (__shfl_sync(0xffffffffu, acc[4][2], lane & ~3) + eps);
+    uint8_t* row_lo = qs + (16 * mt + g) * kPitch + (D * h + 2 * t) * 2;
+    uint8_t* row_hi = row_lo + 8 * kPitch;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      *reinterpret_cast<uint32_t*>(row_lo + 16 * j) = pk2(acc[j][0] * z_lo, acc[j][1] * z_lo);
+      *reinterpret_cast<uint32_t*>(row_hi + 16 * j) = pk2(acc[j][2] * z_hi, acc[j][3] * z_hi);
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < rows * 32; e += 256) {
+    const int r = e >> 5, q = e & 31;
+    reinterpret_cast<uint4*>(out + ((int64_t)n * l + l0 + r) * C)[q] = *reinterpret_cast<const uint4*>(qs + r * kPitch + q * 16);
+  }
+}
+
 // fp16 storage variant (Q/K/V written by the OUT16 projection, message read by the fp16-operand merge GEMM):
 // blockDim == heads * D == 128; thread t loads channel pair 2*(t & 63) of the rows of parity t >> 6 as half2 (full
 // 128-byte warp requests), the message rows are staged in shared memory and leave as one flat 16-byte-vector copy.
@@ -336,7 +513,7 @@ using namespace gf;
 #define STREAM ((cudaStream_t)stream)
 
 extern "C" int64_t gf_linattn_partial_floats(int n, int s, int heads, int dim) {
-  return (int64_t)n * heads * gf_cdiv(s, kChunk) * (dim * dim + dim);
+  return (int64_t)n * heads * gf_cdiv(s, kChunkMma) * (dim * dim + dim);      // sized for the finer of the two chunkings
 }
 
 template <typename T>
@@ -379,10 +556,32 @@ extern "C" int gf_linattn_apply(const float* Q, int ldq, const float* KV, const 
 // fp16-storage variants (Q/K/V and the message in fp16; KV / Ksum and all arithmetic in fp32)
 extern "C" int gf_linattn_reduce_f16(const void* K, int ldk, const void* V, int ldv, int n, int s, int heads, int dim,
                                      float* partial, float* KV, float* Ksum, gf_stream_t stream) {
+  if (heads == 8 && dim == 32 && n > 0 && s > 0 && (ldk % 8) == 0 && (ldv % 8) == 0 &&
+      (reinterpret_cast<uintptr_t>(K) % 16) == 0 && (reinterpret_cast<uintptr_t>(V) % 16) == 0) {
+    // ~600 blocks (two resident per SM) whatever the batch: fewer, longer chunks keep the partial-sum traffic small
+    int chunk_tokens = (int)(((int64_t)s * n / 592 + 31) / 32 * 32);
+    chunk_tokens = chunk_tokens < kChunkMma ? kChunkMma : (chunk_tokens > 512 ? 512 : chunk_tokens);
+    const int nchunks = gf_cdiv(s, chunk_tokens);
+    constexpr int kSmem = 2 * 2 * 32 * kPitch;
+    static bool attr16 = false;
+    if (!attr16) { cudaFuncSetAttribute(linattn_partial_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem); attr16 = true; }
+    linattn_partial_mma_kernel<<<dim3(nchunks, n), 256, kSmem, STREAM>>>((const __half*)K, ldk, (const __half*)V, ldv, s,
+                                                                        chunk_tokens, 1.f / (float)s, partial);
+    linattn_finalize_kernel<<<n * heads, 256, 0, STREAM>>>(partial, nchunks, heads, dim, KV, Ksum);
+    g_launches += 2;
+    GF_CHECK_LAUNCH();
+    return GF_OK;
+  }
   return linattn_reduce_impl<__half>((const __half*)K, ldk, (const __half*)V, ldv, n, s, heads, dim, partial, KV, Ksum, stream);
 }
 extern "C" int gf_linattn_apply_f16(const void* Q, int ldq, const float* KV, const float* Ksum, void* out, int n, int l,
                                     int s, int heads, int dim, gf_stream_t stream) {
+  if (heads == 8 && dim == 32 && n > 0 && l > 0 && (ldq % 8) == 0 && (reinterpret_cast<uintptr_t>(Q) % 16) == 0) {
+    linattn_apply_mma_kernel<<<dim3(gf_cdiv(l, 64), n), 256, 0, STREAM>>>((const __half*)Q, ldq, KV, Ksum, (__half*)out, l, (float)s);
+    g_launches++;
+    GF_CHECK_LAUNCH();
+    return GF_OK;
+  }
   return linattn_apply_impl<__half>((const __half*)Q, ldq, KV, Ksum, (__half*)out, n, l, s, heads, dim, stream);
 }
 extern "C" int gf_linattn_window_f16(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* out,

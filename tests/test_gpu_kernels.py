@@ -251,8 +251,9 @@ def test_linear_attention_window(ops):
 
 
 def test_linear_attention_fp16_storage(ops):
-    """fp16-storage variants (Q/K/V and message fp16, arithmetic fp32) against the oracle on the same fp16-rounded
-    inputs: fp32-kernel tolerance + one fp16 rounding of the output."""
+    """fp16-storage variants (Q/K/V and message fp16, fp32 accumulation; the 8x32 coarse shape runs on mma.sync with
+    the KV / Ksum blocks as fp16 B fragments) against fp64 on the same fp16-rounded inputs: fp32-kernel tolerance + one
+    fp16 rounding each of KV, Ksum and the output (3 * 2^-11 of the largest magnitude)."""
     n, l, s, h, d = 2, 500, 300, 8, 32
     q, k, v = rnd(n, l, h, d, seed=1), rnd(n, s, h, d, seed=2), rnd(n, s, h, d, seed=3)
     Q, K, V = (F.elu(q) + 1).half(), (F.elu(k) + 1).half(), v.half()
@@ -264,7 +265,7 @@ def test_linear_attention_fp16_storage(ops):
     got = ops.linattn(dev(Q.reshape(n * l, h * d)), h * d, dev(K.reshape(n * s, h * d)), h * d,
                       dev(V.reshape(n * s, h * d)), h * d, n, l, s, h, d)
     assert got.dtype == torch.float16
-    assert (got.float().cpu() - want).abs().max().item() <= (2e-5 + 2.0 ** -11) * max(1.0, want.abs().max().item())
+    assert (got.float().cpu() - want).abs().max().item() <= (2e-5 + 3 * 2.0 ** -11) * max(1.0, want.abs().max().item())
     # strided Q|K|V buffer, window kernel
     m, t, h, d = 37, 25, 8, 16
     c = h * d
