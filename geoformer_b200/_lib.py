@@ -22,6 +22,7 @@ SIGNATURES = {
     "gf_linear_tf32": (I, [P, P, P, P, L, I, I, I, I, I, P, P, I, P, P, P, P, P]),
     "gf_linear_ref": (I, [P, P, P, P, L, I, I, I, I, I, P, P, I, P, P, P, P, P]),
     "gf_conv3x3_bf16": (I, [P, P, P, P, P, I, I, I, I, I, I, I, P]),
+    "gf_conv_bf16": (I, [P, P, P, P, P, I, I, I, I, I, I, I, I, I, P]),
     "gf_stem_conv7x7_bf16": (I, [P, P, P, P, I, I, I, P]),
     "gf_upsample_add_bf16": (I, [P, P, P, I, I, I, I, I, I, P]),
     "gf_add_posenc": (I, [P, P, P, I, L, I, P]),

@@ -1,4 +1,4 @@
-// 3x3 / stride-1 / pad-1 convolution as a tcgen05 implicit GEMM (backbone: resnet_fpn.py:32-40, 70-82, 100-118;
+// 3x3 (pad 1) and 1x1 convolutions, stride 1 or 2, as a tcgen05 implicit GEMM (backbone: resnet_fpn.py:32-40, 70-82, 100-118;
 // SURVEY.md §8f rank 1).  NHWC bf16 activations, BN folded into weights + bias.
 //
 //   Y[b,y,x,co] = act( bias[co] + sum_{dy,dx,ci} X[b,y+dy-1,x+dx-1,ci] * W[co,dy,dx,ci]  (+ R[b,y,x,co]) )
@@ -24,6 +24,7 @@ struct ConvParams {
   const __nv_bfloat16* residual;     // NHWC [b,h,w,cout_p] or null
   int batch, h, w, cout_p;
   int kbc;                           // 64-channel k-blocks per tap
+  int taps, stride, pad;             // 9 taps / pad 1 (3x3) or 1 tap / pad 0 (1x1); stride 1 or 2; h, w are OUTPUT sizes
   int tiles_x, tiles_y;
   int act;                           // 0 none, 1 relu, 2 leaky relu (0.01)
 };
@@ -68,7 +69,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int total_tiles = p.batch * tiles_per_img;
-  const int kblocks = 9 * p.kbc;
+  const int kblocks = p.taps * p.kbc;
 
   if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmX); ptx::prefetch_tmap(&tmW); ptx::prefetch_tmap(&tmY); }
   if (warp == 1) {
@@ -93,11 +94,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int y0 = (r / p.tiles_x) * 8, x0 = (r % p.tiles_x) * 16;
         for (int kb = 0; kb < kblocks; ++kb) {
           const int tap = kb / p.kbc, cb = kb - tap * p.kbc;
-          const int dy = tap / 3, dx = tap - dy * 3;
+          const int dy = tap / 3, dx = tap - dy * 3;       // single-tap (1x1) convolutions: tap == 0, pad == 0
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStage;
           ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStage);
-          ptx::tma_load_4d(sa, &tmX, &full_bar[stage], cb * 64, x0 + dx - 1, y0 + dy - 1, b);
+          // the input map traverses W and H with element stride == conv stride: the box is 16 x 8 OUTPUT pixels
+          ptx::tma_load_4d(sa, &tmX, &full_bar[stage], cb * 64, x0 * p.stride + dx - p.pad, y0 * p.stride + dy - p.pad, b);
           ptx::tma_load_3d(sa + Cfg::kStageA, &tmW, &full_bar[stage], kb * 64, 0, 0);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
@@ -334,13 +336,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn encode_fn();
 
 // NHWC bf16 map: dims {C, W, H, B}; box {64, box_w, box_h, 1}; 128B swizzle; OOB -> 0 on load, clipped on store
-static int make_nhwc_tmap(CUtensorMap* m, const void* base, int c, int w, int h, int b, int box_w, int box_h) {
+// `stride` > 1: W and H are traversed with that element stride; the box then spans box_w*stride x box_h*stride source
+// elements and delivers box_w x box_h of them (cuTensorMapEncodeTiled: ceil(boxDim / elementStride) per dimension).
+static int make_nhwc_tmap(CUtensorMap* m, const void* base, int c, int w, int h, int b, int box_w, int box_h, int stride = 1) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return gf_set_error(GF_ERR_DRIVER, "gf_init() was not called");
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)b};
   cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)c * 2 * w, (cuuint64_t)c * 2 * w * h};
-  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -371,24 +375,35 @@ static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const CUten
 
 using namespace gf;
 
-// x NHWC bf16 [b,h,w,cin_p]; wt bf16 [cout_p][9][cin_k] (cin_k = cin_p rounded up to 64, zero padded);
-// bias fp32 [cout_p]; residual / y NHWC bf16 [b,h,w,cout_p].  cin_p, cout_p multiples of 8; cout_p <= 256.
-extern "C" int gf_conv3x3_bf16(const void* x, const void* wt, const float* bias, const void* residual, void* y,
-                               int batch, int h, int w, int cin_p, int cout_p, int cin_k, int act, gf_stream_t stream) {
-  if (batch <= 0 || h <= 0 || w <= 0 || (cin_p % 8) || (cout_p % 8) || cout_p > 256 || (cin_k % 64) || cin_k < cin_p)
-    return gf_set_error(GF_ERR_ARG, "gf_conv3x3_bf16: channels must be multiples of 8, cout <= 256, cin_k % 64 == 0");
+// x NHWC bf16 [b,h,w,cin_p]; wt bf16 [cout_p][taps][cin_k] (taps = ksize^2, cin_k = cin_p rounded up to 64, zero padded);
+// bias fp32 [cout_p]; residual / y NHWC bf16 [b,ho,wo,cout_p], ho = (h - 1) / stride + 1.  ksize 3 (pad 1) or 1 (pad 0),
+// stride 1 or 2; cin_p, cout_p multiples of 8; cout_p <= 256.
+extern "C" int gf_conv_bf16(const void* x, const void* wt, const float* bias, const void* residual, void* y, int batch,
+                            int h, int w, int cin_p, int cout_p, int cin_k, int ksize, int stride, int act,
+                            gf_stream_t stream) {
+  if (batch <= 0 || h <= 0 || w <= 0 || (cin_p % 8) || (cout_p % 8) || cout_p > 256 || (cin_k % 64) || cin_k < cin_p ||
+      !(ksize == 1 || ksize == 3) || !(stride == 1 || stride == 2) || bias == nullptr)
+    return gf_set_error(GF_ERR_ARG, "gf_conv_bf16: channels % 8, cout <= 256, cin_k % 64 == 0, ksize in {1,3}, stride in {1,2}");
+  const int taps = ksize * ksize;
+  const int ho = (h - 1) / stride + 1, wo = (w - 1) / stride + 1;
   const int BN = cout_p <= 128 ? 128 : (cout_p <= 208 ? 208 : 256);
   CUtensorMap tx, tw, ty;
   int rc;
-  if ((rc = make_nhwc_tmap(&tx, x, cin_p, w, h, batch, 16, 8))) return rc;
-  if ((rc = make_nhwc_tmap(&ty, y, cout_p, w, h, batch, 16, 2))) return rc;
-  if ((rc = make_tmap(&tw, wt, 2, 9 * (int64_t)cin_k, cout_p, 1, 9 * (int64_t)cin_k, 0, BN))) return rc;
+  if ((rc = make_nhwc_tmap(&tx, x, cin_p, w, h, batch, 16, 8, stride))) return rc;
+  if ((rc = make_nhwc_tmap(&ty, y, cout_p, wo, ho, batch, 16, 2))) return rc;
+  if ((rc = make_tmap(&tw, wt, 2, taps * (int64_t)cin_k, cout_p, 1, taps * (int64_t)cin_k, 0, BN))) return rc;
   ConvParams p{};
-  p.bias = bias; p.residual = (const __nv_bfloat16*)residual; p.batch = batch; p.h = h; p.w = w; p.cout_p = cout_p;
-  p.kbc = cin_k / 64; p.tiles_x = gf_cdiv(w, 16); p.tiles_y = gf_cdiv(h, 8); p.act = act;
+  p.bias = bias; p.residual = (const __nv_bfloat16*)residual; p.batch = batch; p.h = ho; p.w = wo; p.cout_p = cout_p;
+  p.kbc = cin_k / 64; p.taps = taps; p.stride = stride; p.pad = ksize / 2;
+  p.tiles_x = gf_cdiv(wo, 16); p.tiles_y = gf_cdiv(ho, 8); p.act = act;
   if (BN == 128) return launch_conv<128>(tx, tw, ty, p, (cudaStream_t)stream);
   if (BN == 208) return launch_conv<208>(tx, tw, ty, p, (cudaStream_t)stream);
   return launch_conv<256>(tx, tw, ty, p, (cudaStream_t)stream);
+}
+
+extern "C" int gf_conv3x3_bf16(const void* x, const void* wt, const float* bias, const void* residual, void* y,
+                               int batch, int h, int w, int cin_p, int cout_p, int cin_k, int act, gf_stream_t stream) {
+  return gf_conv_bf16(x, wt, bias, residual, y, batch, h, w, cin_p, cout_p, cin_k, 3, 1, act, stream);
 }
 
 extern "C" int gf_upsample_add_bf16(const void* lateral, const void* src, void* out, int batch, int h, int w, int hs,

@@ -46,12 +46,13 @@ def _fold_bn(w: torch.Tensor, sd: Dict[str, torch.Tensor], bn: str, eps: float =
 
 
 def pack_conv3x3(w: torch.Tensor, b: Optional[torch.Tensor], cin_p: int, cout_p: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
-    """[Cout,Cin,3,3] fp32 (+bias) -> tap-major K-major bf16 [cout_p, 9, cin_k] and fp32 bias [cout_p] for
-    gf_conv3x3_bf16 (cin_k = cin_p rounded up to a multiple of 64; all padding is zero)."""
+    """[Cout,Cin,k,k] fp32 (+bias), k in {3, 1} -> tap-major K-major bf16 [cout_p, k*k, cin_k] and fp32 bias [cout_p]
+    for gf_conv_bf16 (cin_k = cin_p rounded up to a multiple of 64; all padding is zero)."""
     co, ci = w.shape[:2]
+    taps = w.shape[2] * w.shape[3]
     cin_k = (cin_p + 63) // 64 * 64
-    wt = torch.zeros((cout_p, 9, cin_k), dtype=torch.float32)
-    wt[:co, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, 9, ci)
+    wt = torch.zeros((cout_p, taps, cin_k), dtype=torch.float32)
+    wt[:co, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, taps, ci)
     bias = torch.zeros(cout_p, dtype=torch.float32)
     if b is not None:
         bias[:co] = b
@@ -175,9 +176,12 @@ class PackedWeights:
             for li in (1, 2, 3):
                 for bi in (0, 1):
                     p = f"layer{li}.{bi}"
-                    if not (li > 1 and bi == 0):
-                        t[p + ".conv1"] = tc(p + ".conv1", p + ".bn1")
+                    t[p + ".conv1"] = tc(p + ".conv1", p + ".bn1")            # stride 2 in the entry block of layer 2 / 3
                     t[p + ".conv2"] = tc(p + ".conv2", p + ".bn2")
+                    if li > 1 and bi == 0:
+                        t[p + ".down"] = tc(p + ".downsample.0", p + ".downsample.1")   # 1x1 / stride 2
+            for name in ("layer3_outconv", "layer2_outconv", "layer1_outconv"):        # 1x1 FPN laterals
+                t[name] = tc(name)
             t["layer2_outconv2.0"] = tc("layer2_outconv2.0", "layer2_outconv2.1")
             t["layer2_outconv2.3"] = tc("layer2_outconv2.3")
             t["layer1_outconv2.0"] = tc("layer1_outconv2.0", "layer1_outconv2.1")
@@ -242,25 +246,19 @@ def backbone_forward(pw: PackedWeights, img: torch.Tensor) -> Tuple[torch.Tensor
 
 
 def backbone_forward_tc(pw: PackedWeights, img: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Same network; every 3x3 / stride-1 convolution (95 % of the backbone FLOPs) runs in the tcgen05
-    implicit-GEMM kernel with BN, residual add and activation fused into its epilogue.  The 7x7 stem, the three
-    stride-2 convolutions and the 1x1 laterals stay on cuDNN; the FPN upsample+add is one fused kernel."""
-    bb, tc = pw.bb, pw.bb_tc
-    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous()   # channels-last NCHW -> NHWC (no copy when already channels-last)
-    nchw = lambda t: t.permute(0, 3, 1, 2)
+    """Same network on this library's kernels only: every 3x3 and 1x1 convolution (stride 1 or 2) runs in the tcgen05
+    implicit-GEMM kernel with BN, residual add and activation fused into its epilogue; the 7x7 stem is a register-
+    tiled FFMA kernel and the FPN upsample+add one fused kernel.  Activations are NHWC bf16 throughout."""
+    tc = pw.bb_tc
 
-    def cudnn(name, t, stride=1, pad=1):
-        w, b = bb[name]
-        return F.conv2d(t, w, b, stride, pad)
-
-    def conv(name, t, act, residual=None):
+    def conv(name, t, act, residual=None, stride=1):
         wt, b = tc[name]
-        return ops.conv3x3(t, wt, b, residual, act)
+        return ops.conv(t, wt, b, residual, act, stride)
 
     def block(p, a):                                  # a: NHWC
-        if (p + ".down") in bb:                       # stride-2 entry block
-            y = nhwc(F.relu_(cudnn(p + ".conv1", nchw(a), 2)))
-            a = nhwc(cudnn(p + ".down", nchw(a), 2, 0))
+        if (p + ".down") in tc:                       # stride-2 entry block: 3x3/s2 + ReLU, 1x1/s2 shortcut
+            y = conv(p + ".conv1", a, 1, stride=2)
+            a = conv(p + ".down", a, 0, stride=2)
         else:
             y = conv(p + ".conv1", a, 1)
         return conv(p + ".conv2", y, 1, residual=a)
@@ -269,10 +267,10 @@ def backbone_forward_tc(pw: PackedWeights, img: torch.Tensor) -> Tuple[torch.Ten
     x1 = block("layer1.1", block("layer1.0", x0))
     x2 = block("layer2.1", block("layer2.0", x1))
     x3 = block("layer3.1", block("layer3.0", x2))
-    x3o = nhwc(cudnn("layer3_outconv", nchw(x3), 1, 0))
-    x2o = ops.upsample_add(nhwc(cudnn("layer2_outconv", nchw(x2), 1, 0)), x3o)
+    x3o = conv("layer3_outconv", x3, 0)
+    x2o = ops.upsample_add(conv("layer2_outconv", x2, 0), x3o)
     x2o = conv("layer2_outconv2.3", conv("layer2_outconv2.0", x2o, 2), 0)
-    x1o = ops.upsample_add(nhwc(cudnn("layer1_outconv", nchw(x1), 1, 0)), x2o)
+    x1o = ops.upsample_add(conv("layer1_outconv", x1, 0), x2o)
     x1o = conv("layer1_outconv2.3", conv("layer1_outconv2.0", x1o, 2), 0)
     return x3o.float().contiguous(), x1o          # the fine map stays bf16 NHWC: fine_gather reads it directly
 

@@ -176,14 +176,23 @@ def conv3x3(x: torch.Tensor, wt: torch.Tensor, bias: torch.Tensor, residual: Opt
             act: int = 0) -> torch.Tensor:
     """3x3/s1/p1 conv + folded BN (+ residual) + activation on NHWC bf16 (tcgen05 implicit GEMM).
     x [b,h,w,cin_p]; wt [cout_p, 9, cin_k]; bias fp32 [cout_p]; returns [b,h,w,cout_p] bf16."""
+    return conv(x, wt, bias, residual, act, 1)
+
+
+def conv(x: torch.Tensor, wt: torch.Tensor, bias: torch.Tensor, residual: Optional[torch.Tensor] = None,
+         act: int = 0, stride: int = 1) -> torch.Tensor:
+    """3x3 (pad 1) or 1x1 (pad 0) conv, stride 1 or 2, + bias (+ residual) + activation on NHWC bf16.
+    wt [cout_p, taps, cin_k] with taps in {9, 1}; returns [b, (h-1)//stride+1, (w-1)//stride+1, cout_p] bf16."""
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and wt.dtype == torch.bfloat16 and wt.is_contiguous()
     b, h, w, cin_p = x.shape
-    cout_p, _, cin_k = wt.shape
-    y = torch.empty((b, h, w, cout_p), device=x.device, dtype=torch.bfloat16)
+    cout_p, taps, cin_k = wt.shape
+    assert taps in (1, 9)
+    y = torch.empty((b, (h - 1) // stride + 1, (w - 1) // stride + 1, cout_p), device=x.device, dtype=torch.bfloat16)
     if residual is not None:
         assert residual.shape == y.shape and residual.is_contiguous() and residual.dtype == torch.bfloat16
-    _call("gf_conv3x3_bf16", x.data_ptr(), wt.data_ptr(), bias.data_ptr(), _ptr(residual), y.data_ptr(), b, h, w, cin_p,
-          cout_p, cin_k, act, _stream(), tag=f"[{cin_p}->{cout_p}@{h}x{w}]")
+    _call("gf_conv_bf16", x.data_ptr(), wt.data_ptr(), bias.data_ptr(), _ptr(residual), y.data_ptr(), b, h, w, cin_p,
+          cout_p, cin_k, 3 if taps == 9 else 1, stride, act, _stream(),
+          tag=f"[{cin_p}->{cout_p}@{h}x{w}{'k1' if taps == 1 else ''}{'s2' if stride == 2 else ''}]")
     return y
 
 

@@ -77,6 +77,11 @@ int gf_linear_ref(const float* A, const float* A2, const float* W, float* Y, int
  *   bias fp32 [cout_p]; residual (optional) and y [b,h,w,cout_p] bf16.  act: 0 none, 1 ReLU, 2 LeakyReLU(0.01). */
 int gf_conv3x3_bf16(const void* x, const void* wt, const float* bias, const void* residual, void* y, int batch, int h,
                     int w, int cin_p, int cout_p, int cin_k, int act, gf_stream_t stream);
+/* Generalisation used for the rest of the backbone: ksize 3 (pad 1) or 1 (pad 0), stride 1 or 2 (the stride-2 entry
+ * convolutions and 1x1 downsample / FPN lateral convolutions of resnet_fpn.py:18-29, 62-82).  h, w are the INPUT sizes;
+ * y is [batch, (h-1)/stride+1, (w-1)/stride+1, cout_p].  wt: [cout_p][ksize*ksize][cin_k] bf16. */
+int gf_conv_bf16(const void* x, const void* wt, const float* bias, const void* residual, void* y, int batch, int h, int w,
+                 int cin_p, int cout_p, int cin_k, int ksize, int stride, int act, gf_stream_t stream);
 
 /* Backbone stem (resnet_fpn.py:58-60,102): 7x7 / stride 2 / pad 3 conv of the 1-channel fp32 image + folded BN +
  * ReLU -> NHWC bf16 [b, h/2, w/2, 128].  wperm = folded weights as [49 taps][128 channels] fp32. */

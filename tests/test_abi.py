@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(_lib.SIGNATURES) == declared, set(_lib.SIGNATURES) ^ set(declared)
     assert lib.gf_abi_version() == 1
-    assert lib.gf_linattn_partial_floats(2, 4800, 8, 32) == 2 * 8 * 19 * (32 * 32 + 32)
+    assert lib.gf_linattn_partial_floats(2, 4800, 8, 32) == 2 * 8 * 38 * (32 * 32 + 32)     # 128-token chunks
 
 
 def test_header_argument_counts_match_ctypes_table():

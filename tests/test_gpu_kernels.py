@@ -431,6 +431,34 @@ def test_conv3x3_tcgen05(ops, cin, cout, cin_p, cout_p, res, act):
     assert err <= 1e-2 * want.abs().max().item(), err
 
 
+@pytest.mark.parametrize("cin,cout,cin_p,cout_p,ksize,stride,hw,act", [
+    (128, 196, 128, 200, 3, 2, (20, 40), 1),      # layer2.0.conv1: 3x3 / stride 2 + ReLU
+    (128, 196, 128, 200, 1, 2, (20, 40), 0),      # layer2.0.downsample: 1x1 / stride 2
+    (196, 256, 200, 256, 3, 2, (21, 37), 1),      # odd sizes: (h-1)//2+1 outputs, partial tiles
+    (196, 256, 200, 256, 1, 2, (21, 37), 0),
+    (256, 256, 256, 256, 1, 1, (15, 20), 0),      # layer3_outconv (1x1 lateral, no bias in the reference)
+    (128, 196, 128, 200, 1, 1, (24, 33), 0),      # layer1_outconv
+])
+def test_conv_strided_and_1x1_tcgen05(ops, cin, cout, cin_p, cout_p, ksize, stride, hw, act):
+    """The generalised implicit-GEMM conv (TMA element stride 2 on W/H for stride-2 layers; a single tap for 1x1)
+    vs F.conv2d in fp32 on the same bf16-rounded operands; same tolerance as the 3x3 / stride-1 test."""
+    from geoformer_b200.engine import pack_conv3x3
+    b, (h, w) = 2, hw
+    x = rnd(b, cin, h, w, seed=1).bfloat16()
+    wgt = (rnd(cout, cin, ksize, ksize, seed=2) * (cin * ksize * ksize) ** -0.5).bfloat16()
+    bias = rnd(cout, seed=3) * 0.1
+    want = F.conv2d(x.float(), wgt.float(), bias, stride, ksize // 2)
+    want = F.relu(want) if act == 1 else want
+    xp = torch.zeros(b, h, w, cin_p, dtype=torch.bfloat16); xp[..., :cin] = x.permute(0, 2, 3, 1)
+    wt, bp = pack_conv3x3(wgt.float(), bias, cin_p, cout_p, "cuda")
+    y = ops.conv(dev(xp), wt, bp, None, act, stride).cpu().float()
+    assert tuple(y.shape) == (b, want.shape[2], want.shape[3], cout_p)
+    got = y[..., :cout].permute(0, 3, 1, 2)
+    assert (y[..., cout:] == 0).all()
+    err = (got - want).abs().max().item()
+    assert err <= 1e-2 * want.abs().max().item(), err
+
+
 # ------------------------------------------------------------------------------------------- fused coarse matching
 def _match_lists(d):
     return torch.stack([d["b_ids"].cpu(), d["i_ids"].cpu(), d["j_ids"].cpu()], 1)
