@@ -8,7 +8,7 @@ of one batch fill the host gaps of another, which is the reference's serial per-
 """
 from __future__ import annotations
 
-from concurrent.futures import ThreadPoolExecutor
+import threading
 from typing import Callable, Dict, Iterable, List, Optional
 
 import torch
@@ -20,10 +20,8 @@ class MatchPipeline:
         self.depth = max(1, int(depth))
         self.device = device or next(model.parameters()).device
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.depth)]
-        self.pool = ThreadPoolExecutor(max_workers=self.depth)
 
     def _job(self, slot: int, data: Dict[str, torch.Tensor], post: Optional[Callable]):
-        torch.cuda.set_device(self.device)
         s = self.streams[slot]
         with torch.cuda.stream(s):
             data = {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) and not v.is_cuda else v)
@@ -35,15 +33,41 @@ class MatchPipeline:
 
     def run(self, batches: Iterable[Dict[str, torch.Tensor]], post: Optional[Callable] = None) -> List:
         """``batches``: dicts with 'image0'/'image1' (CUDA tensors, or pinned host tensors which are uploaded
-        inside the pipeline).  ``post(data)`` runs on the batch's stream (e.g. device->host of the results)."""
+        inside the pipeline).  ``post(data)`` runs on the batch's stream (e.g. device->host of the results).
+        ``depth`` worker threads, each owning one stream, pull batches from the shared iterator, so ``depth``
+        batches stay in flight until the input is exhausted; results keep the input order."""
         main = torch.cuda.current_stream(self.device)
         for s in self.streams:
             s.wait_stream(main)
-        futs = [self.pool.submit(self._job, i % self.depth, b, post) for i, b in enumerate(batches)]
-        out = [f.result() for f in futs]
+        it = enumerate(batches)
+        lock = threading.Lock()
+        results: Dict[int, object] = {}
+        errors: List[BaseException] = []
+
+        def worker(slot: int):
+            torch.cuda.set_device(self.device)
+            while not errors:
+                with lock:
+                    nxt = next(it, None)
+                if nxt is None:
+                    return
+                idx, batch = nxt
+                try:
+                    results[idx] = self._job(slot, batch, post)
+                except BaseException as e:      # surfaced to the caller below (the helpers count match failures)
+                    errors.append(e)
+                    return
+
+        threads = [threading.Thread(target=worker, args=(i,), daemon=True) for i in range(self.depth)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
         for s in self.streams:
             main.wait_stream(s)
-        return out
+        if errors:
+            raise errors[0]
+        return [results[i] for i in range(len(results))]
 
     def close(self):
-        self.pool.shutdown(wait=True)
+        pass
