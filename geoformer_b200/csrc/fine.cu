@@ -131,6 +131,97 @@ fine_match_kernel(const float* __restrict__ f0, const float* __restrict__ f1, in
   }
 }
 
+// Warp-per-match variant for the shipped shape (25 cells, 128 channels): lane t < 25 owns the 5 x 5 block
+// S[5(t/5) .. +4][5(t%5) .. +4] in registers, so a 4-channel step costs 10 LDS.128 for 100 FMAs (the CTA-per-match
+// kernel above needs 2 LDS.128 per 4 FMAs and is shared-memory bound).  Channels are staged 32 at a time
+// (2 x 25 rows x 128 B, coalesced), everything else is warp-local: no block-wide barrier, 8 matches per CTA.
+__global__ void __launch_bounds__(256)
+fine_match_warp_kernel(const float* __restrict__ f0, const float* __restrict__ f1, int64_t m_total, float temperature,
+                       float thr, int* __restrict__ sel, int* __restrict__ fi, int* __restrict__ fj,
+                       float* __restrict__ fconf, float* __restrict__ fine_matrix) {
+  constexpr int WW = 25, C = 128, KC = 32, PITCH = KC + 4, SP = 27;
+  extern __shared__ __align__(16) float fm_smem[];          // per warp: a chunk | b chunk | S
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m = (int64_t)blockIdx.x * 8 + warp;
+  if (m >= m_total) return;
+  float* sa = fm_smem + warp * (2 * WW * PITCH + WW * SP + 1);
+  float* sb = sa + WW * PITCH;
+  float* S = sb + WW * PITCH;
+  const float inv_norm = 1.f / sqrtf((float)C);           // feat / C**.5 (fine_matching2.py:52)
+  const int ti = (lane < WW ? lane : 0) / 5, tj = (lane < WW ? lane : 0) % 5;
+  float acc[5][5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) acc[i][j] = 0.f;
+  const float4* g0 = reinterpret_cast<const float4*>(f0 + m * WW * C);
+  const float4* g1 = reinterpret_cast<const float4*>(f1 + m * WW * C);
+#pragma unroll 1
+  for (int kc = 0; kc < C / KC; ++kc) {
+    __syncwarp();
+    for (int e = lane; e < WW * (KC / 4); e += 32) {      // 25 rows x 8 float4 per operand
+      const int r = e >> 3, q = e & 7;
+      float4 x = __ldg(g0 + r * (C / 4) + kc * (KC / 4) + q), y = __ldg(g1 + r * (C / 4) + kc * (KC / 4) + q);
+      x.x *= inv_norm; x.y *= inv_norm; x.z *= inv_norm; x.w *= inv_norm;
+      y.x *= inv_norm; y.y *= inv_norm; y.z *= inv_norm; y.w *= inv_norm;
+      *reinterpret_cast<float4*>(sa + r * PITCH + 4 * q) = x;
+      *reinterpret_cast<float4*>(sb + r * PITCH + 4 * q) = y;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < KC / 4; ++q) {
+      float4 a[5], b[5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        a[i] = *reinterpret_cast<const float4*>(sa + (5 * ti + i) * PITCH + 4 * q);
+        b[i] = *reinterpret_cast<const float4*>(sb + (5 * tj + i) * PITCH + 4 * q);
+      }
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]); acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
+          acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]); acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
+        }
+    }
+  }
+  if (lane < WW) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) S[(5 * ti + i) * SP + 5 * tj + j] = acc[i][j] / temperature;
+  }
+  __syncwarp();
+  // lane t < 25: statistics of row t (softmax over j) and of column t (softmax over i)
+  const int t = lane < WW ? lane : 0;
+  float rmax = -INFINITY, cmax = -INFINITY;
+  for (int j = 0; j < WW; ++j) { rmax = fmaxf(rmax, S[t * SP + j]); cmax = fmaxf(cmax, S[j * SP + t]); }
+  float rsum = 0.f, csum = 0.f;
+  for (int j = 0; j < WW; ++j) { rsum += expf(S[t * SP + j] - rmax); csum += expf(S[j * SP + t] - cmax); }
+  float bv = -1.f;
+  int bi = 0x7fffffff;
+  for (int j = 0; j < WW; ++j) {
+    const float cm = __shfl_sync(0xffffffffu, cmax, j), cs = __shfl_sync(0xffffffffu, csum, j);
+    const float sv = S[t * SP + j];
+    const float cf = (expf(sv - cm) / cs) * (expf(sv - rmax) / rsum);
+    if (lane < WW) {
+      if (fine_matrix) fine_matrix[m * WW * WW + t * WW + j] = cf;
+      if (cf > bv) { bv = cf; bi = t * WW + j; }           // ascending j: first index on ties inside the row
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if (lane == 0) {
+    sel[m] = bv > thr ? 1 : 0;
+    fi[m] = bi / WW; fj[m] = bi % WW;
+    fconf[m] = bv;
+  }
+}
+
 // Ordered compaction of kept fine matches (single CTA, 1024 threads, running base).
 //   mkpts_f = ([cell % W - W/2, cell / W - W/2] + mkpts_c / coarse_scale * c2f_scale) * fine_scale
 __global__ void __launch_bounds__(1024)
@@ -201,6 +292,15 @@ extern "C" int gf_fine_match(const float* f0, const float* f1, int64_t m, int ww
                              int* sel, int* fi, int* fj, float* fconf, float* fine_matrix, gf_stream_t stream) {
   if (m < 0 || ww <= 0 || ww > 25 || c <= 0 || c > 128) return gf_set_error(GF_ERR_ARG, "gf_fine_match: ww <= 25, c <= 128");
   if (m == 0) return GF_OK;
+  if (ww == 25 && c == 128) {
+    constexpr int kSmem = 8 * (2 * 25 * 36 + 25 * 27 + 1) * 4;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(fine_match_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem); attr = true; }
+    fine_match_warp_kernel<<<(unsigned)((m + 7) / 8), 256, kSmem, STREAM>>>(f0, f1, m, temperature, thr, sel, fi, fj, fconf, fine_matrix);
+    g_launches++;
+    GF_CHECK_LAUNCH();
+    return GF_OK;
+  }
   fine_match_kernel<<<(unsigned)m, 128, 0, STREAM>>>(f0, f1, ww, c, temperature, thr, sel, fi, fj, fconf, fine_matrix);
   g_launches++;
   GF_CHECK_LAUNCH();

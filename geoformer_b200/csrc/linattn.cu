@@ -84,16 +84,26 @@ __global__ void linattn_partial_kernel(const T* __restrict__ K, int ldk, const T
   }
 }
 
+// reduce, stage 2: one thread per (sample, head, entry); the chunk partials of an entry are nchunks independent,
+// coalesced loads (4 in flight per thread)
 __global__ void linattn_finalize_kernel(const float* __restrict__ partial, int nchunks, int heads, int dim,
                                         float* __restrict__ KV, float* __restrict__ Ksum) {
-  const int n = blockIdx.x / heads, h = blockIdx.x % heads;
-  const int entries = dim * dim;
-  for (int e = threadIdx.x; e < entries + dim; e += blockDim.x) {
-    float a = 0.f;
-    for (int c = 0; c < nchunks; ++c) a += partial[(((int64_t)n * nchunks + c) * heads + h) * (entries + dim) + e];
-    if (e < entries) KV[((int64_t)n * heads + h) * entries + e] = a;
-    else Ksum[((int64_t)n * heads + h) * dim + (e - entries)] = a;
+  const int entries = dim * dim, per = entries + dim;
+  const int nh = blockIdx.y;                      // sample * heads + head
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= per) return;
+  const int n = nh / heads, h = nh - n * heads;
+  const float* p = partial + ((int64_t)n * nchunks * heads + h) * per + e;
+  const int64_t stride = (int64_t)heads * per;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int c = 0;
+  for (; c + 4 <= nchunks; c += 4) {
+    a0 += p[(c + 0) * stride]; a1 += p[(c + 1) * stride]; a2 += p[(c + 2) * stride]; a3 += p[(c + 3) * stride];
   }
+  for (; c < nchunks; ++c) a0 += p[c * stride];
+  const float a = (a0 + a1) + (a2 + a3);
+  if (e < entries) KV[(int64_t)nh * entries + e] = a;
+  else Ksum[(int64_t)nh * dim + (e - entries)] = a;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -527,7 +537,7 @@ static int linattn_reduce_impl(const T* K, int ldk, const T* V, int ldv, int n, 
   if (!attr) { cudaFuncSetAttribute(linattn_partial_kernel<32, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
   if (smem > 96 * 1024) return gf_set_error(GF_ERR_ARG, "gf_linattn_reduce: shared memory");
   linattn_partial_kernel<32, T><<<dim3(nchunks, n), 32 * heads, smem, STREAM>>>(K, ldk, V, ldv, s, heads, 1.f / (float)s, partial);
-  linattn_finalize_kernel<<<n * heads, 256, 0, STREAM>>>(partial, nchunks, heads, dim, KV, Ksum);
+  linattn_finalize_kernel<<<dim3(gf_cdiv(dim * dim + dim, 128), n * heads), 128, 0, STREAM>>>(partial, nchunks, heads, dim, KV, Ksum);
   g_launches += 2;
   GF_CHECK_LAUNCH();
   return GF_OK;
@@ -567,7 +577,7 @@ extern "C" int gf_linattn_reduce_f16(const void* K, int ldk, const void* V, int 
     if (!attr16) { cudaFuncSetAttribute(linattn_partial_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem); attr16 = true; }
     linattn_partial_mma_kernel<<<dim3(nchunks, n), 256, kSmem, STREAM>>>((const __half*)K, ldk, (const __half*)V, ldv, s,
                                                                         chunk_tokens, 1.f / (float)s, partial);
-    linattn_finalize_kernel<<<n * heads, 256, 0, STREAM>>>(partial, nchunks, heads, dim, KV, Ksum);
+    linattn_finalize_kernel<<<dim3(gf_cdiv(dim * dim + dim, 128), n * heads), 128, 0, STREAM>>>(partial, nchunks, heads, dim, KV, Ksum);
     g_launches += 2;
     GF_CHECK_LAUNCH();
     return GF_OK;
