@@ -30,7 +30,12 @@ FUSED_FINE_LAYER = os.environ.get("GF_FUSED_FINE", "1") != "0"
 def _pool() -> ThreadPoolExecutor:
     global _POOL
     if _POOL is None:
-        _POOL = ThreadPoolExecutor(max_workers=max(2, min(16, os.cpu_count() or 2)))
+        # GF_RANSAC_THREADS: host threads for the per-sample cv2.findHomography calls (default: one per core, <= 16)
+        nthr = int(os.environ.get("GF_RANSAC_THREADS", "0")) or max(2, min(16, os.cpu_count() or 2))
+        _POOL = ThreadPoolExecutor(max_workers=nthr)
+        if os.environ.get("GF_CV2_THREADS"):            # OpenCV's own parallel_for_ width inside each findHomography call
+            import cv2
+            cv2.setNumThreads(int(os.environ["GF_CV2_THREADS"]))
     return _POOL
 
 
@@ -379,32 +384,46 @@ def _ransac_one(kp0: np.ndarray, kp1: np.ndarray, thr: float):
 
 def geo_prepare_host(k0: np.ndarray, k1: np.ndarray, counts: np.ndarray, hw0_c, hw1_c, scale: int, ransac_thr: float):
     """Host side of geo_module.py:39-94: per-sample RANSAC, homographies (fp64 inverse, fp32 cast),
-    anchor (inlier) token lists in ascending token order (== boolean-mask order)."""
+    anchor (inlier) token lists in ascending token order (== boolean-mask order).
+    Only cv2.findHomography runs per sample (thread pool, GIL released); the bookkeeping around it is vectorised over
+    the batch: one batched fp64 inverse, one boolean token map per image and one nonzero() for all samples."""
     n = len(counts)
-    offs = np.concatenate([[0], np.cumsum(counts)])
-    kps = [(k0[offs[b]:offs[b + 1]].astype(np.int64), k1[offs[b]:offs[b + 1]].astype(np.int64)) for b in range(n)]
+    offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    k0i, k1i = k0.astype(np.int64), k1.astype(np.int64)
+    kps = [(k0i[offs[b]:offs[b + 1]], k1i[offs[b]:offs[b + 1]]) for b in range(n)]
     if n > 1:
         res = list(_pool().map(lambda ab: _ransac_one(ab[0], ab[1], ransac_thr), kps))
     else:
         res = [_ransac_one(kps[0][0], kps[0][1], ransac_thr)]
     hm = np.zeros((2, n, 9), dtype=np.float32)
-    has_h = np.zeros(n, dtype=np.int32)
-    anchors0: List[np.ndarray] = []
-    anchors1: List[np.ndarray] = []
-    for b, ((a, c), (M, inl)) in enumerate(zip(kps, res)):
-        if M is not None:
-            has_h[b] = 1
-            hm[0, b] = M.astype(np.float32).reshape(9)
-            hm[1, b] = torch.inverse(torch.from_numpy(M)[None])[0].to(torch.float32).numpy().reshape(9)
-            a, c = a[inl], c[inl]
-        anchors0.append(np.unique((a[:, 1] // scale) * hw0_c[1] + (a[:, 0] // scale)))
-        anchors1.append(np.unique((c[:, 1] // scale) * hw1_c[1] + (c[:, 0] // scale)))
-    cap = max(1, max(len(x) for x in anchors0 + anchors1))
+    has_h = np.array([1 if M is not None else 0 for M, _ in res], dtype=np.int32)
+    if has_h.any():
+        sel = np.flatnonzero(has_h)
+        ms = np.stack([res[b][0] for b in sel])                                  # [k, 3, 3] fp64
+        hm[0, sel] = ms.astype(np.float32).reshape(-1, 9)
+        hm[1, sel] = torch.inverse(torch.from_numpy(ms)).to(torch.float32).numpy().reshape(-1, 9)
+    # anchors: all first-pass matches of samples without a homography, the RANSAC inliers otherwise
+    keep = np.ones(len(k0i), dtype=bool)
+    for b in range(n):
+        if has_h[b]:
+            keep[offs[b]:offs[b + 1]] = res[b][1]
+    bidx = np.repeat(np.arange(n, dtype=np.int64), counts)
+    l0, l1 = hw0_c[0] * hw0_c[1], hw1_c[0] * hw1_c[1]
+    lists = []
+    for kk, wc, l in ((k0i, hw0_c[1], l0), (k1i, hw1_c[1], l1)):
+        tok = (kk[:, 1] // scale) * wc + (kk[:, 0] // scale)
+        m = np.zeros(n * l, dtype=bool)
+        m[(bidx * l + tok)[keep]] = True
+        flat = np.flatnonzero(m)                                                 # ascending (sample, token)
+        cnt = np.bincount(flat // l, minlength=n).astype(np.int32)
+        lists.append((flat % l, cnt))
+    cap = max(1, int(max(lists[0][1].max(), lists[1][1].max())))
     aidx = np.zeros((2, n, cap), dtype=np.int32)
     acnt = np.zeros((2, n), dtype=np.int32)
-    for b in range(n):
-        aidx[0, b, :len(anchors0[b])] = anchors0[b]; acnt[0, b] = len(anchors0[b])
-        aidx[1, b, :len(anchors1[b])] = anchors1[b]; acnt[1, b] = len(anchors1[b])
+    for side, (toks, cnt) in enumerate(lists):
+        acnt[side] = cnt
+        col = np.arange(len(toks)) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+        aidx[side, np.repeat(np.arange(n), cnt), col] = toks
     return hm, has_h, aidx, acnt
 
 
