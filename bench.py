@@ -250,6 +250,27 @@ def run_ours(args):
     torch.cuda.synchronize()
     sim_ms = [a.elapsed_time(b) for a, b in sim_ms]
     del fa, fb, a3, b3, ws
+    # the largest single kernel of a step by time: one fused fine-level layer over both images' windows (self layer)
+    fl_ms, fl_windows = [], 0
+    try:
+        wp = model._weights(device).fine[0]
+        fl_windows = 2 * int(round(float(np.mean([o["b_ids"] for o in outs]))))
+        if fl_windows > 0 and "wpack" in wp:
+            xf = torch.randn(fl_windows, 25, 128, device=device)
+            yf = torch.empty_like(xf)
+            for it in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _lib.call("gf_fine_layer", xf.data_ptr(), xf.data_ptr(), wp["wpack"].data_ptr(), wp["n1w"].data_ptr(),
+                          wp["n1b"].data_ptr(), wp["n2w"].data_ptr(), wp["n2b"].data_ptr(), yf.data_ptr(), fl_windows, st)
+                e1.record()
+                if it >= 2:
+                    fl_ms.append((e0, e1))
+            torch.cuda.synchronize()
+            fl_ms = [a.elapsed_time(b) for a, b in fl_ms]
+            del xf, yf
+    except Exception:
+        fl_ms = []
     clocks = sampler.stop() if rank == 0 else None
 
     mc = float(np.mean([o["b_ids"] for o in outs])) / args.batch
@@ -298,6 +319,21 @@ def run_ours(args):
             # (profiles/r01_ncu_final_raw.txt): pass 0 = 236.1 + 97.1 MB, pass 1 = 238.1 + 4.2 MB; algorithmic bytes per
             # launch = packed operands 235.9 MB (+ 105 MB statistics partials in pass 0) -> no re-reads
             "traffic": 287.7e6 * args.batch / 16, "tensor_pipe_active_pct_ncu": {"pass0": 68.5, "pass1": 66.5}}
+    roof2 = None
+    if fl_ms:
+        hbm = float(peaks.get("hbm_gbs", 6500.0))
+        fl_avg = float(np.mean(fl_ms))
+        fl_bytes = fl_windows * 25 * 128 * 4 * 2.0                            # algorithmic: x read once + y written once
+        roof2 = {"kernel": "fine_layer_kernel (one whole fine-level LoFTR layer per launch, self layer over both images' "
+                           "windows; qkv / attention / merge / LN / MLP / LN / residual never leave the SM)",
+                 "bound": "hbm", "achieved": fl_bytes / (fl_avg * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                 "frac": fl_bytes / (fl_avg * 1e-3) / 1e9 / hbm,
+                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.5 TB/s",
+                 "algorithmic_bytes_per_launch": fl_bytes, "windows": fl_windows, "avg_launch_ms": fl_avg,
+                 # ncu --set full, profiles/r01_fine_layer_ncu_details.txt (112000 windows): dram read 1.434 GB + write
+                 # 1.392 GB == algorithmic 2.867 GB; tensor pipe 28.8 %: the kernel is bound by its serial per-tile chain
+                 # (MMA -> epilogue -> MMA ...), not by HBM; the unfused kernels it replaces moved ~6.9 KB per token-layer
+                 "traffic": fl_bytes * (2.826 / 2.867), "tensor_pipe_active_pct_ncu": 28.8}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "tf32 projections/attention, split-f16 similarity, bf16 backbone" if args.backbone == "bf16"
@@ -308,7 +344,7 @@ def run_ours(args):
                                              "gathered_matches": gathered,
                                              "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective"}),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * args.batch * H * W * 4, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_top_kernel_by_time": roof2}
     if not args.no_cpu_baseline and world == 1:
         v, cores, spp, _ = cpu_forward_pairs_per_sec(2, 1, args.regime)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
