@@ -31,7 +31,8 @@ def _pool() -> ThreadPoolExecutor:
     global _POOL
     if _POOL is None:
         # GF_RANSAC_THREADS: host threads for the per-sample cv2.findHomography calls (default: one per core, <= 16)
-        nthr = int(os.environ.get("GF_RANSAC_THREADS", "0")) or max(2, min(16, os.cpu_count() or 2))
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))        # one process per GPU shares the host cores
+        nthr = int(os.environ.get("GF_RANSAC_THREADS", "0")) or max(2, min(16, (os.cpu_count() or 2) // ranks))
         _POOL = ThreadPoolExecutor(max_workers=nthr)
         if os.environ.get("GF_CV2_THREADS"):            # OpenCV's own parallel_for_ width inside each findHomography call
             import cv2
