@@ -51,7 +51,8 @@ SIGNATURES = {
     "gf_geo_self_attention": (I, [P, I, P, I, P, I, P, I, I, I, I, P, P, I, P]),
     "gf_gather_anchor_kv": (I, [P, I, P, I, I, I, I, I, P, P, I, I, P, P, P]),
     "gf_gather_anchor_kv_f16": (I, [P, I, P, I, P, I, I, I, I, I, P, P, I, I, P, P, P, P]),
-    "gf_geo_self_attention_tc": (I, [P, P, P, P, I, I, I, I, I, P, P]),
+    "gf_geo_self_attention_tc": (I, [P, I, P, P, P, I, I, I, I, I, P, P]),
+    "gf_gather_anchor_kv_h16": (I, [P, I, P, I, I, I, I, I, P, P, I, I, P, P, P]),
     "gf_masked_softmax_rows": (I, [P, I, I, I, I, P, P]),
     "gf_gemm_tf32_batched": (I, [P, L, L, P, L, L, P, L, L, I, I, I, I, F, P]),
     "gf_geo_cross_attention": (I, [P, I, P, I, P, I, P, I, I, I, I, I, P, I, P]),

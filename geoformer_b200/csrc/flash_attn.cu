@@ -299,14 +299,14 @@ using namespace gf;
 
 // fp16 operands from gf_gather_anchor_kv_f16: q16 [n*l, heads*64] (head h at columns [h*64, h*64+64)),
 // kg [heads][n][s_pad][64], vt [heads][n][64][s_pad]; out fp32 [n*l, heads*64].
-extern "C" int gf_geo_self_attention_tc(const void* q16, const void* kg, const void* vt, float* out, int n, int l,
+extern "C" int gf_geo_self_attention_tc(const void* q16, int ldq, const void* kg, const void* vt, float* out, int n, int l,
                                         int heads, int dim, int s_pad, const int* anchor_cnt, gf_stream_t stream) {
-  if (n <= 0 || l <= 0 || heads <= 0 || dim != 64 || s_pad <= 0 || (s_pad % 8))
-    return gf_set_error(GF_ERR_ARG, "gf_geo_self_attention_tc: dim must be 64, s_pad % 8 == 0");
+  const int c = heads * dim;
+  if (n <= 0 || l <= 0 || heads <= 0 || dim != 64 || s_pad <= 0 || (s_pad % 8) || ldq < c || (ldq % 8))
+    return gf_set_error(GF_ERR_ARG, "gf_geo_self_attention_tc: dim must be 64, s_pad % 8 == 0, ldq % 8 == 0");
   CUtensorMap tq, tk, tv, to;
   int rc;
-  const int c = heads * dim;
-  if ((rc = make_tmap(&tq, q16, 2, c, l, n, c, (int64_t)l * c, fa::kBQ))) return rc;
+  if ((rc = make_tmap(&tq, q16, 2, c, l, n, ldq, (int64_t)l * ldq, fa::kBQ))) return rc;
   if ((rc = make_tmap(&tk, kg, 2, dim, s_pad, (int64_t)heads * n, dim, (int64_t)s_pad * dim, fa::kBK))) return rc;
   if ((rc = make_tmap(&tv, vt, 2, s_pad, dim, (int64_t)heads * n, s_pad, (int64_t)dim * s_pad, fa::kD))) return rc;
   if ((rc = make_out_tmap(&to, out, c, l, n, c, (int64_t)l * c))) return rc;

@@ -283,6 +283,46 @@ __global__ void gather_anchor_kv_f16_kernel(const float* __restrict__ q, int ldq
   }
 }
 
+// Same gather from fp16 K / V rows (the OUT16 projection): kg rows are copied as 16-byte chunks, the V tile of 64
+// anchors is transposed through shared memory so that vt rows leave as 16-byte vectors too.  grid (s_pad / 64, n),
+// 256 threads; heads * dim == 256, dim == 64.
+__global__ void __launch_bounds__(256)
+gather_anchor_kv_h16_kernel(const __half* __restrict__ k, int ldk, const __half* __restrict__ v, int ldv, int n, int l,
+                            const int* __restrict__ anchor_idx, const int* __restrict__ anchor_cnt, int anchor_cap,
+                            int s_pad, __half* __restrict__ kg, __half* __restrict__ vt) {
+  constexpr int C = 256, D = 64, PITCH = C + 8;
+  __shared__ __align__(16) __half vs[64 * PITCH];
+  const int b = blockIdx.y, s0 = blockIdx.x * 64, t = threadIdx.x;
+  const int cnt = anchor_cnt[b];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int e = t + 256 * i, r = e >> 5, q = e & 31;       // anchor row r of the tile, 16-byte chunk q of its 512 B
+    const int s = s0 + r;
+    uint4 kq = make_uint4(0u, 0u, 0u, 0u), vq = kq;
+    if (s < cnt) {
+      const int64_t tok = (int64_t)b * l + anchor_idx[(int64_t)b * anchor_cap + s];
+      kq = __ldg(reinterpret_cast<const uint4*>(k + tok * ldk) + q);
+      vq = __ldg(reinterpret_cast<const uint4*>(v + tok * ldv) + q);
+    }
+    if (s < s_pad) {
+      const int h = q >> 3;
+      *reinterpret_cast<uint4*>(kg + (((int64_t)h * n + b) * s_pad + s) * D + (q & 7) * 8) = kq;
+    }
+    *reinterpret_cast<uint4*>(vs + r * PITCH + q * 8) = vq;
+  }
+  __syncthreads();
+  const int h = t >> 6, d = t & 63;                           // thread == channel
+  __half* dst = vt + (((int64_t)h * n + b) * D + d) * s_pad + s0;
+#pragma unroll
+  for (int g8 = 0; g8 < 8; ++g8) {
+    if (s0 + 8 * g8 >= s_pad) break;
+    __half tmp[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tmp[j] = vs[(8 * g8 + j) * PITCH + t];
+    *reinterpret_cast<uint4*>(dst + 8 * g8) = *reinterpret_cast<const uint4*>(tmp);
+  }
+}
+
 // rows of [heads][n][l][s_pad]: p = softmax(x[0:cnt]) (x is already scaled), zeros beyond cnt.  One warp per row.
 // PER_LANE > 0: the whole row (s_pad <= 32 * PER_LANE) lives in registers -> one read and one write of the block.
 template <int PER_LANE>
@@ -389,6 +429,19 @@ extern "C" int gf_gather_anchor_kv_f16(const float* q, int ldq, const float* k, 
   gather_anchor_kv_f16_kernel<<<gf_cdiv(total, 256), 256, 0, STREAM>>>(q, ldq, k, ldk, v, ldv, n, l, heads, dim, anchor_idx,
                                                                        anchor_cnt, anchor_cap, s_pad, (__half*)q16, (__half*)kg,
                                                                        (__half*)vt);
+  g_launches++;
+  GF_CHECK_LAUNCH();
+  return GF_OK;
+}
+
+extern "C" int gf_gather_anchor_kv_h16(const void* k, int ldk, const void* v, int ldv, int n, int l, int heads, int dim,
+                                       const int* anchor_idx, const int* anchor_cnt, int anchor_cap, int s_pad, void* kg,
+                                       void* vt, gf_stream_t stream) {
+  if (n <= 0 || l <= 0 || heads * dim != 256 || dim != 64 || s_pad <= 0 || (s_pad % 8) || (ldk % 8) || (ldv % 8))
+    return gf_set_error(GF_ERR_ARG, "gf_gather_anchor_kv_h16: needs 4 heads of dim 64, s_pad % 8 == 0, 16-byte aligned rows");
+  gather_anchor_kv_h16_kernel<<<dim3(gf_cdiv(s_pad, 64), n), 256, 0, STREAM>>>((const __half*)k, ldk, (const __half*)v, ldv, n, l,
+                                                                             anchor_idx, anchor_cnt, anchor_cap, s_pad,
+                                                                             (__half*)kg, (__half*)vt);
   g_launches++;
   GF_CHECK_LAUNCH();
   return GF_OK;

@@ -433,7 +433,9 @@ def geo_self_layer(lw: dict, x: torch.Tensor, aidx: torch.Tensor, acnt: torch.Te
     """All tokens attend to the anchor tokens of their own image (geo_transformer/transformer.py:111-124)."""
     n, l, c = x.shape
     x2d = x.reshape(n * l, c)
-    qkv = ops.linear(x2d, lw["wqkv"])
+    # product mode: Q|K|V stored fp16 (the flash kernel's operands are fp16 anyway: no conversion pass, half the gather)
+    a16 = ops.act16() and ops._ATTN_IMPL == "tf32" and max_cnt > 0 and (heads, c // heads) == (4, 64)
+    qkv = ops.linear(x2d, lw["wqkv"], out_f16=a16)
     att = ops.geo_self_attention(qkv, 3 * c, qkv[:, c:], 3 * c, qkv[:, 2 * c:], 3 * c, n, l, heads, c // heads, aidx, acnt,
                                  max_cnt)
     y = _post_attention(lw, x2d, att, EPI_TANH)

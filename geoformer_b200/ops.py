@@ -385,13 +385,19 @@ def geo_self_attention(q, ldq, k, ldk, v, ldv, n, l, heads, dim, anchor_idx, anc
         s_pad = (max_cnt + 63) // 64 * 64
         dev = q.device
         if mode == "tf32":           # fused flash-style tcgen05 kernel (fp16 operands): scores never leave the SM
-            q16 = torch.empty((n * l, c), device=dev, dtype=torch.float16)
             kg = torch.empty((heads, n, s_pad, dim), device=dev, dtype=torch.float16)
             vt = torch.empty((heads, n, dim, s_pad), device=dev, dtype=torch.float16)
-            _call("gf_gather_anchor_kv_f16", q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, n, l, heads, dim,
-                  anchor_idx.data_ptr(), anchor_cnt.data_ptr(), anchor_idx.shape[1], s_pad, q16.data_ptr(),
-                  kg.data_ptr(), vt.data_ptr(), _stream())
-            _call("gf_geo_self_attention_tc", q16.data_ptr(), kg.data_ptr(), vt.data_ptr(), out.data_ptr(), n, l,
+            if q.dtype == torch.float16:     # Q|K|V already fp16 (OUT16 projection): queries are read in place
+                _call("gf_gather_anchor_kv_h16", k.data_ptr(), ldk, v.data_ptr(), ldv, n, l, heads, dim,
+                      anchor_idx.data_ptr(), anchor_cnt.data_ptr(), anchor_idx.shape[1], s_pad, kg.data_ptr(),
+                      vt.data_ptr(), _stream())
+                q16, ld16 = q, ldq
+            else:
+                q16, ld16 = torch.empty((n * l, c), device=dev, dtype=torch.float16), c
+                _call("gf_gather_anchor_kv_f16", q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, n, l, heads, dim,
+                      anchor_idx.data_ptr(), anchor_cnt.data_ptr(), anchor_idx.shape[1], s_pad, q16.data_ptr(),
+                      kg.data_ptr(), vt.data_ptr(), _stream())
+            _call("gf_geo_self_attention_tc", q16.data_ptr(), ld16, kg.data_ptr(), vt.data_ptr(), out.data_ptr(), n, l,
                   heads, dim, s_pad, anchor_cnt.data_ptr(), _stream())
             return out
         kg = torch.empty((heads, n, s_pad, dim), device=dev, dtype=torch.float32)

@@ -201,8 +201,13 @@ int gf_masked_softmax_rows(float* x, int heads, int n, int l, int s_pad, const i
 int gf_gather_anchor_kv_f16(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int n, int l,
                             int heads, int dim, const int* anchor_idx, const int* anchor_cnt, int anchor_cap, int s_pad,
                             void* q16, void* kg, void* vt, gf_stream_t stream);
-int gf_geo_self_attention_tc(const void* q16, const void* kg, const void* vt, float* out, int n, int l, int heads,
-                             int dim, int s_pad, const int* anchor_cnt, gf_stream_t stream);
+/* same gather when K / V are already fp16 (Q|K|V written by gf_linear_mixed out_f16; 4 heads of dim 64): no query copy
+ * is needed, gf_geo_self_attention_tc reads the query rows in place through ldq */
+int gf_gather_anchor_kv_h16(const void* k, int ldk, const void* v, int ldv, int n, int l, int heads, int dim,
+                            const int* anchor_idx, const int* anchor_cnt, int anchor_cap, int s_pad, void* kg, void* vt,
+                            gf_stream_t stream);
+int gf_geo_self_attention_tc(const void* q16, int ldq, const void* kg, const void* vt, float* out, int n, int l,
+                             int heads, int dim, int s_pad, const int* anchor_cnt, gf_stream_t stream);
 /* Y[b] = out_scale * A[b] (M x K, row stride lda) * B[b]^T (N x K, row stride ldb); strides in floats */
 int gf_gemm_tf32_batched(const float* A, int64_t lda, int64_t a_batch_stride, const float* B, int64_t ldb,
                          int64_t b_batch_stride, float* Y, int64_t ldy, int64_t y_batch_stride, int M, int N, int K,

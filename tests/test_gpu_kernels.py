@@ -337,6 +337,32 @@ def test_geo_self_attention(ops, impl, tol):
         assert (got[b] - want).abs().max().item() <= tol
 
 
+def test_geo_self_attention_fp16_qkv(ops):
+    """Product path of the geo self layers: Q|K|V already stored fp16 (strided buffer), anchors gathered by
+    gf_gather_anchor_kv_h16 (incl. the smem-transposed V), queries read in place.  Reference: the oracle's softmax
+    attention on the same fp16-rounded values; fp16 P operand inside the kernel -> 5e-3 like the tf32 bar."""
+    n, l, h, d = 3, 333, 4, 64
+    c = h * d
+    qkv = rnd(n * l, 3 * c, seed=4).half()
+    cnts = [0, 70, 200]
+    g = torch.Generator().manual_seed(1)
+    aidx = torch.zeros(n, 256, dtype=torch.int32)
+    for b, cnt in enumerate(cnts):
+        aidx[b, :cnt] = torch.sort(torch.randperm(l, generator=g)[:cnt])[0].int()
+    dq = dev(qkv)
+    got = ops.geo_self_attention(dq, 3 * c, dq[:, c:], 3 * c, dq[:, 2 * c:], 3 * c, n, l, h, d, dev(aidx),
+                                 dev(torch.tensor(cnts, dtype=torch.int32)), max_cnt=max(cnts), impl="tf32").cpu().view(n, l, c)
+    x = qkv.float().view(n, l, 3 * c)
+    for b, cnt in enumerate(cnts):
+        if cnt == 0:
+            assert (got[b] == 0).all()
+            continue
+        sel = aidx[b, :cnt].long()
+        want = O.softmax_attention(x[b, :, :c].view(1, l, h, d), x[b, sel, c:2 * c].view(1, cnt, h, d),
+                                   x[b, sel, 2 * c:].view(1, cnt, h, d)).view(l, c)
+        assert (got[b] - want).abs().max().item() <= 5e-3
+
+
 def test_geo_cross_attention(ops):
     n, l, s, h, d = 2, 150, 170, 4, 64
     c = h * d
