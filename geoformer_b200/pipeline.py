@@ -8,6 +8,7 @@ of one batch fill the host gaps of another, which is the reference's serial per-
 """
 from __future__ import annotations
 
+import gc
 import threading
 from typing import Callable, Dict, Iterable, List, Optional
 
@@ -20,6 +21,7 @@ class MatchPipeline:
         self.depth = max(1, int(depth))
         self.device = device or next(model.parameters()).device
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.depth)]
+        self._frozen = False
 
     def _job(self, slot: int, data: Dict[str, torch.Tensor], post: Optional[Callable]):
         s = self.streams[slot]
@@ -39,6 +41,13 @@ class MatchPipeline:
         main = torch.cuda.current_stream(self.device)
         for s in self.streams:
             s.wait_stream(main)
+        if not self._frozen:
+            # a full (generation-2) collection walks every tracked object of the process (model, torch, cv2 ...) while
+            # holding the GIL: measured as 200+ ms stalls of ALL launch threads.  Moving what is alive now to the
+            # permanent generation keeps later collections proportional to the garbage the pipeline itself creates.
+            gc.collect()
+            gc.freeze()
+            self._frozen = True
         it = enumerate(batches)
         lock = threading.Lock()
         results: Dict[int, object] = {}
