@@ -56,6 +56,7 @@ SIGNATURES = {
     "gf_masked_softmax_rows": (I, [P, I, I, I, I, P, P]),
     "gf_gemm_tf32_batched": (I, [P, L, L, P, L, L, P, L, L, I, I, I, I, F, P]),
     "gf_geo_cross_attention": (I, [P, I, P, I, P, I, P, I, I, I, I, I, P, I, P]),
+    "gf_geo_cross_attention_f16": (I, [P, I, P, I, P, I, P, I, I, I, I, I, P, I, P]),
     "gf_select_rows": (I, [P, P, P, I, L, I, P]),
     "gf_fine_gather": (I, [P, I, I, I, P, P, L, I, I, I, P, P]),
     "gf_fine_gather_bf16": (I, [P, I, I, I, P, P, L, I, I, I, P, P]),

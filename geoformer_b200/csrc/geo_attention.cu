@@ -170,16 +170,45 @@ geo_self_attention_kernel(const float* __restrict__ q, int ldq, const float* __r
 // once-projected K/V of the other image (project-then-gather; the reference gathers-then-projects,
 // which is the same arithmetic per row but 25x the FLOPs).
 // ---------------------------------------------------------------------------------------------
-__global__ void geo_cross_attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ kp, int ldk,
-                                           const float* __restrict__ vp, int ldv, float* __restrict__ out, int n, int l,
+// T = float, or __half when Q|K|V come from the OUT16 projection (the message is then fp16 too and feeds the fp16 merge)
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
+  uint4 u;
+  __half2 h;
+  h = __floats2half2_rn(v[0], v[1]); u.x = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2half2_rn(v[2], v[3]); u.y = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2half2_rn(v[4], v[5]); u.z = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2half2_rn(v[6], v[7]); u.w = *reinterpret_cast<uint32_t*>(&h);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+template <typename T>
+__global__ void geo_cross_attention_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ kp, int ldk,
+                                           const T* __restrict__ vp, int ldv, T* __restrict__ out, int n, int l,
                                            int s, const int* __restrict__ widx, int window2, float softmax_scale) {
   const int64_t tok = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (tok >= (int64_t)n * l) return;
   const int b = (int)(tok / l);
   const int* wi = widx + tok * window2;
-  const float4 q0 = *reinterpret_cast<const float4*>(q + tok * ldq + lane * 8);
-  const float4 q1 = *reinterpret_cast<const float4*>(q + tok * ldq + lane * 8 + 4);
+  float qv[8];
+  load8(q + tok * ldq + lane * 8, qv);
   float sc[25];
   int id[25];
   float mx = -INFINITY;
@@ -190,10 +219,9 @@ __global__ void geo_cross_attention_kernel(const float* __restrict__ q, int ldq,
     id[w] = t;
     float d = 0.f;
     if (t >= 0) {
-      const float* kr = kp + ((int64_t)b * s + t) * ldk + lane * 8;
-      const float4 k0 = *reinterpret_cast<const float4*>(kr);
-      const float4 k1 = *reinterpret_cast<const float4*>(kr + 4);
-      d = q0.x * k0.x + q0.y * k0.y + q0.z * k0.z + q0.w * k0.w + q1.x * k1.x + q1.y * k1.y + q1.z * k1.z + q1.w * k1.w;
+      float kv[8];
+      load8(kp + ((int64_t)b * s + t) * ldk + lane * 8, kv);
+      d = qv[0] * kv[0] + qv[1] * kv[1] + qv[2] * kv[2] + qv[3] * kv[3] + qv[4] * kv[4] + qv[5] * kv[5] + qv[6] * kv[6] + qv[7] * kv[7];
       ++live;
     }
     d += __shfl_xor_sync(0xffffffffu, d, 1);
@@ -215,17 +243,14 @@ __global__ void geo_cross_attention_kernel(const float* __restrict__ q, int ldq,
     for (int w = 0; w < 25; ++w) {
       if (w < window2 && id[w] >= 0) {
         const float p = sc[w] * inv;
-        const float* vr = vp + ((int64_t)b * s + id[w]) * ldv + lane * 8;
-        const float4 v0 = *reinterpret_cast<const float4*>(vr);
-        const float4 v1 = *reinterpret_cast<const float4*>(vr + 4);
-        acc[0] = fmaf(p, v0.x, acc[0]); acc[1] = fmaf(p, v0.y, acc[1]); acc[2] = fmaf(p, v0.z, acc[2]); acc[3] = fmaf(p, v0.w, acc[3]);
-        acc[4] = fmaf(p, v1.x, acc[4]); acc[5] = fmaf(p, v1.y, acc[5]); acc[6] = fmaf(p, v1.z, acc[6]); acc[7] = fmaf(p, v1.w, acc[7]);
+        float vv[8];
+        load8(vp + ((int64_t)b * s + id[w]) * ldv + lane * 8, vv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(p, vv[i], acc[i]);
       }
     }
   }
-  float* o = out + tok * 256 + lane * 8;
-  *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-  *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  store8(out + tok * 256 + lane * 8, acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -402,8 +427,21 @@ extern "C" int gf_geo_cross_attention(const float* q, int ldq, const float* kpro
                                       gf_stream_t stream) {
   if (n <= 0 || l <= 0 || s <= 0 || heads * dim != 256 || dim != 64 || window2 <= 0 || window2 > 25)
     return gf_set_error(GF_ERR_ARG, "gf_geo_cross_attention: needs heads*dim == 256, dim == 64, window <= 25");
-  geo_cross_attention_kernel<<<gf_cdiv((int64_t)n * l, 4), 128, 0, STREAM>>>(q, ldq, kproj, ldk, vproj, ldv, out, n, l, s,
-                                                                            widx, window2, 1.f / sqrtf((float)dim));
+  geo_cross_attention_kernel<float><<<gf_cdiv((int64_t)n * l, 4), 128, 0, STREAM>>>(q, ldq, kproj, ldk, vproj, ldv, out, n, l, s,
+                                                                                   widx, window2, 1.f / sqrtf((float)dim));
+  g_launches++;
+  GF_CHECK_LAUNCH();
+  return GF_OK;
+}
+
+extern "C" int gf_geo_cross_attention_f16(const void* q, int ldq, const void* kproj, int ldk, const void* vproj, int ldv,
+                                          void* out, int n, int l, int s, int heads, int dim, const int* widx, int window2,
+                                          gf_stream_t stream) {
+  if (n <= 0 || l <= 0 || s <= 0 || heads * dim != 256 || dim != 64 || window2 <= 0 || window2 > 25 || (ldq % 8) || (ldk % 8) || (ldv % 8))
+    return gf_set_error(GF_ERR_ARG, "gf_geo_cross_attention_f16: needs heads*dim == 256, dim == 64, window <= 25, 16-byte rows");
+  geo_cross_attention_kernel<__half><<<gf_cdiv((int64_t)n * l, 4), 128, 0, STREAM>>>(
+      (const __half*)q, ldq, (const __half*)kproj, ldk, (const __half*)vproj, ldv, (__half*)out, n, l, s, widx, window2,
+      1.f / sqrtf((float)dim));
   g_launches++;
   GF_CHECK_LAUNCH();
   return GF_OK;

@@ -451,8 +451,9 @@ def geo_cross_layer(lw: dict, x0: torch.Tensor, x1: torch.Tensor, widx_in1: torc
     s = x1.shape[1]
     d = c // heads
     a2d, b2d = x0.reshape(n * l, c), x1.reshape(n * s, c)
-    qkv0 = ops.linear(a2d, lw["wqkv"])
-    qkv1 = ops.linear(b2d, lw["wqkv"])
+    a16 = ops.act16() and (heads, d) == (4, 64)         # Q|K|V and the message in fp16 storage (product mode)
+    qkv0 = ops.linear(a2d, lw["wqkv"], out_f16=a16)
+    qkv1 = ops.linear(b2d, lw["wqkv"], out_f16=a16)
     att0 = ops.geo_cross_attention(qkv0, 3 * c, qkv1[:, c:], 3 * c, qkv1[:, 2 * c:], 3 * c, n, l, s, heads, d, widx_in1)
     att1 = ops.geo_cross_attention(qkv1, 3 * c, qkv0[:, c:], 3 * c, qkv0[:, 2 * c:], 3 * c, n, s, l, heads, d, widx_in0)
     y0 = _post_attention(lw, a2d, att0, EPI_TANH)

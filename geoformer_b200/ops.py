@@ -419,8 +419,8 @@ def geo_self_attention(q, ldq, k, ldk, v, ldv, n, l, heads, dim, anchor_idx, anc
 
 
 def geo_cross_attention(q, ldq, kp, ldk, vp, ldv, n, l, s, heads, dim, widx) -> torch.Tensor:
-    out = torch.empty((n * l, heads * dim), device=q.device, dtype=torch.float32)
-    _call("gf_geo_cross_attention", q.data_ptr(), ldq, kp.data_ptr(), ldk, vp.data_ptr(), ldv, out.data_ptr(), n,
+    out = torch.empty((n * l, heads * dim), device=q.device, dtype=q.dtype)
+    _call("gf_geo_cross_attention" + ("_f16" if q.dtype == torch.float16 else ""), q.data_ptr(), ldq, kp.data_ptr(), ldk, vp.data_ptr(), ldv, out.data_ptr(), n,
               l, s, heads, dim, widx.data_ptr(), widx.shape[2], _stream())
     return out
 

@@ -218,6 +218,9 @@ int gf_gemm_tf32_batched(const float* A, int64_t lda, int64_t a_batch_stride, co
 int gf_geo_cross_attention(const float* q, int ldq, const float* kproj, int ldk, const float* vproj, int ldv,
                            float* out, int n, int l, int s, int heads, int dim, const int* widx, int window2,
                            gf_stream_t stream);
+/* fp16-storage variant (Q|K|V from gf_linear_mixed out_f16; the message is fp16 and feeds the fp16-operand merge) */
+int gf_geo_cross_attention_f16(const void* q, int ldq, const void* kproj, int ldk, const void* vproj, int ldv, void* out,
+                               int n, int l, int s, int heads, int dim, const int* widx, int window2, gf_stream_t stream);
 /* rows of samples whose flag[n]==0 are restored from src (layers skipped per sample) */
 int gf_select_rows(float* dst, const float* src, const int* flag, int n, int64_t l, int c, gf_stream_t stream);
 

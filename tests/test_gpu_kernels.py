@@ -382,6 +382,31 @@ def test_geo_cross_attention(ops):
     assert (got[0, 5] == 0).all()
 
 
+def test_geo_cross_attention_fp16_storage(ops):
+    """fp16-stored Q / K / V (strided Q|K|V buffers) and fp16 message, fp32 arithmetic: the oracle on the same
+    fp16-rounded inputs + one fp16 rounding of the O(1) output."""
+    n, l, s, h, d = 2, 150, 170, 4, 64
+    c = h * d
+    qkv0, qkv1 = rnd(n * l, 3 * c, seed=1).half(), rnd(n * s, 3 * c, seed=2).half()
+    g = torch.Generator().manual_seed(2)
+    widx = torch.randint(-1, s, (n, l, 25), generator=g).int()
+    widx[0, 5] = -1
+    widx[1, 7, 1:] = -1
+    d0, d1 = dev(qkv0), dev(qkv1)
+    got = ops.geo_cross_attention(d0, 3 * c, d1[:, c:], 3 * c, d1[:, 2 * c:], 3 * c, n, l, s, h, d, dev(widx))
+    assert got.dtype == torch.float16
+    got = got.float().cpu().view(n, l, c)
+    q, kp, vp = qkv0[:, :c].float(), qkv1[:, c:2 * c].float(), qkv1[:, 2 * c:].float()
+    for b in range(n):
+        idx = widx[b].long().clamp(min=0)
+        mask = widx[b] >= 0
+        kk = kp.view(n, s, c)[b][idx].view(l, 25, h, d)
+        vv = vp.view(n, s, c)[b][idx].view(l, 25, h, d)
+        want = O.softmax_attention(q.view(n, l, c)[b].view(l, 1, h, d), kk, vv, kv_mask=mask).view(l, c)
+        assert (got[b] - want).abs().max().item() <= 2e-5 + 2.0 ** -11 * max(1.0, want.abs().max().item())
+    assert (got[0, 5] == 0).all()
+
+
 # ------------------------------------------------------------------------------------------- fine level
 def test_fine_gather_exact(ops):
     n, c, hf, wf, wc = 2, 128, 48, 64, 16
