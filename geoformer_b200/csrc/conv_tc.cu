@@ -24,6 +24,7 @@ struct ConvParams {
   const __nv_bfloat16* residual;     // NHWC [b,h,w,cout_p] or null
   int batch, h, w, cout_p;
   int kbc;                           // 64-channel k-blocks per tap
+  int last_k;                        // MMAs (16 channels each) that carry real channels in the last k-block of a tap
   int taps, stride, pad;             // 9 taps / pad 1 (3x3) or 1 tap / pad 0 (1x1); stride 1 or 2; h, w are OUTPUT sizes
   int tiles_x, tiles_y;
   int act;                           // 0 none, 1 relu, 2 leaky relu (0.01)
@@ -114,14 +115,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
+        int cb = 0;
         for (int kb = 0; kb < kblocks; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_addr(smem + stage * Cfg::kStage);
           const uint64_t adesc = ptx::umma_desc_sw128(sa);
           const uint64_t bdesc = ptx::umma_desc_sw128(sa + Cfg::kStageA);
+          // channel tail (e.g. 200 = 3 x 64 + 8): the zero-filled part of the last k-block is not multiplied
+          const int nk = (cb == p.kbc - 1) ? p.last_k : 4;
+          if (++cb == p.kbc) cb = 0;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) ptx::umma<1>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            if (k < nk) ptx::umma<1>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
           ptx::umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
@@ -395,6 +401,8 @@ extern "C" int gf_conv_bf16(const void* x, const void* wt, const float* bias, co
   ConvParams p{};
   p.bias = bias; p.residual = (const __nv_bfloat16*)residual; p.batch = batch; p.h = ho; p.w = wo; p.cout_p = cout_p;
   p.kbc = cin_k / 64; p.taps = taps; p.stride = stride; p.pad = ksize / 2;
+  p.last_k = (cin_p - (p.kbc - 1) * 64 + 15) / 16;
+  if (p.last_k < 1 || p.last_k > 4) return gf_set_error(GF_ERR_ARG, "gf_conv_bf16: cin_k must be cin_p rounded up to 64");
   p.tiles_x = gf_cdiv(wo, 16); p.tiles_y = gf_cdiv(ho, 8); p.act = act;
   if (BN == 128) return launch_conv<128>(tx, tw, ty, p, (cudaStream_t)stream);
   if (BN == 208) return launch_conv<208>(tx, tw, ty, p, (cudaStream_t)stream);
