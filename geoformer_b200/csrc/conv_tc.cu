@@ -14,6 +14,7 @@
 #include "ptx.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 namespace gf {
@@ -30,13 +31,15 @@ struct ConvParams {
   int act;                           // 0 none, 1 relu, 2 leaky relu (0.01)
 };
 
-template <int BN> struct ConvCfg {
-  static constexpr int kStageA = 128 * 128;
+// MT = pixel tiles (8 x 16 each, stacked vertically) per k-block: with MT == 2 one weight box feeds two accumulators,
+// i.e. 48 KB instead of 64 KB of operands per 2 x 128 pixels (the N = 128 layers are bound by the L2 -> smem feed).
+template <int BN, int MT = 1> struct ConvCfg {
+  static constexpr int kStageA = MT * 128 * 128;
   static constexpr int kStageB = BN * 128;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (BN <= 128) ? 5 : 3;
-  static constexpr int kAccStride = (BN <= 128) ? 128 : 256;      // TMEM column offset of accumulator 1
-  static constexpr int kTmemCols = (BN <= 128) ? 256 : 512;
+  static constexpr int kStages = (BN <= 128) ? (MT == 2 ? 4 : 5) : 3;
+  static constexpr int kAccStride = (BN <= 128) ? MT * 128 : 256;      // TMEM column offset of accumulator buffer 1
+  static constexpr int kTmemCols = (BN <= 128 && MT == 1) ? 256 : 512;
   static constexpr int kStaging = 4 * 2 * 4096;                   // per epilogue warp: 2 boxes of 32 px x 128 B
   static constexpr int kSmem = kStages * kStage + kStaging + 1024 + 256;
 };
@@ -53,11 +56,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-template <int BN>
+template <int BN, int MT = 1>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmY, const ConvParams p) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, MT>;
+  static_assert(MT == 1 || BN <= 128, "two pixel tiles per step need 2 x 2 x BN TMEM columns");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + Cfg::kStages * Cfg::kStage;
@@ -92,7 +96,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int b = t / tiles_per_img, r = t - b * tiles_per_img;
-        const int y0 = (r / p.tiles_x) * 8, x0 = (r % p.tiles_x) * 16;
+        const int y0 = (r / p.tiles_x) * (8 * MT), x0 = (r % p.tiles_x) * 16;
         for (int kb = 0; kb < kblocks; ++kb) {
           const int tap = kb / p.kbc, cb = kb - tap * p.kbc;
           const int dy = tap / 3, dx = tap - dy * 3;       // single-tap (1x1) convolutions: tap == 0, pad == 0
@@ -100,7 +104,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           uint8_t* sa = smem + stage * Cfg::kStage;
           ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStage);
           // the input map traverses W and H with element stride == conv stride: the box is 16 x 8 OUTPUT pixels
-          ptx::tma_load_4d(sa, &tmX, &full_bar[stage], cb * 64, x0 * p.stride + dx - p.pad, y0 * p.stride + dy - p.pad, b);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            ptx::tma_load_4d(sa + mt * 16384, &tmX, &full_bar[stage], cb * 64, x0 * p.stride + dx - p.pad,
+                             (y0 + 8 * mt) * p.stride + dy - p.pad, b);
           ptx::tma_load_3d(sa + Cfg::kStageA, &tmW, &full_bar[stage], kb * 64, 0, 0);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
@@ -120,14 +127,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_addr(smem + stage * Cfg::kStage);
-          const uint64_t adesc = ptx::umma_desc_sw128(sa);
           const uint64_t bdesc = ptx::umma_desc_sw128(sa + Cfg::kStageA);
           // channel tail (e.g. 200 = 3 x 64 + 8): the zero-filled part of the last k-block is not multiplied
           const int nk = (cb == p.kbc - 1) ? p.last_k : 4;
           if (++cb == p.kbc) cb = 0;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (k < nk) ptx::umma<1>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t adesc_mt = ptx::umma_desc_sw128(sa + mt * 16384);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < nk) ptx::umma<1>(d_tmem + mt * 128, adesc_mt + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          }
           ptx::umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
@@ -142,10 +152,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     uint32_t box_ctr = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int b = t / tiles_per_img, r = t - b * tiles_per_img;
-      const int y0 = (r / p.tiles_x) * 8, x0 = (r % p.tiles_x) * 16;
+      const int ty0 = (r / p.tiles_x) * (8 * MT), x0 = (r % p.tiles_x) * 16;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * Cfg::kAccStride;
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+      const int y0 = ty0 + 8 * mt;
+      if (y0 >= p.h) break;
+      const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * Cfg::kAccStride + mt * 128;
       for (int c0 = 0; c0 < BN; c0 += 64) {
         if (c0 >= p.cout_p) break;
         uint8_t* box = wstage + (box_ctr & 1) * 4096;
@@ -212,6 +226,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           tma_store_4d(&tmY, box, c0, x0, y0 + quad * 2, b);
           ptx::bulk_commit();
         }
+      }
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -358,12 +373,12 @@ static int make_nhwc_tmap(CUtensorMap* m, const void* base, int c, int w, int h,
   return GF_OK;
 }
 
-template <int BN>
+template <int BN, int MT = 1>
 static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const ConvParams& p,
                        cudaStream_t stream) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, MT>;
   static bool attr = false;
-  auto kern = conv3x3_tc_kernel<BN>;
+  auto kern = conv3x3_tc_kernel<BN, MT>;
   if (!attr) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem) != cudaSuccess)
       return gf_set_error(GF_ERR_LAUNCH, "cudaFuncSetAttribute(conv smem) failed");
@@ -404,6 +419,10 @@ extern "C" int gf_conv_bf16(const void* x, const void* wt, const float* bias, co
   p.last_k = (cin_p - (p.kbc - 1) * 64 + 15) / 16;
   if (p.last_k < 1 || p.last_k > 4) return gf_set_error(GF_ERR_ARG, "gf_conv_bf16: cin_k must be cin_p rounded up to 64");
   p.tiles_x = gf_cdiv(wo, 16); p.tiles_y = gf_cdiv(ho, 8); p.act = act;
+  if (BN == 128 && ho >= 32 && getenv("GF_CONV_MT1") == nullptr) {     // two stacked pixel tiles per weight box
+    p.tiles_y = gf_cdiv(ho, 16);
+    return launch_conv<128, 2>(tx, tw, ty, p, (cudaStream_t)stream);
+  }
   if (BN == 128) return launch_conv<128>(tx, tw, ty, p, (cudaStream_t)stream);
   if (BN == 208) return launch_conv<208>(tx, tw, ty, p, (cudaStream_t)stream);
   return launch_conv<256>(tx, tw, ty, p, (cudaStream_t)stream);

@@ -482,6 +482,26 @@ def test_conv3x3_tcgen05(ops, cin, cout, cin_p, cout_p, res, act):
     assert err <= 1e-2 * want.abs().max().item(), err
 
 
+@pytest.mark.parametrize("h,w,cin,cin_p,res", [(41, 40, 128, 128, True), (48, 17, 196, 200, False), (33, 64, 128, 128, False)])
+def test_conv3x3_two_pixel_tiles_per_weight_box(ops, h, w, cin, cin_p, res):
+    """N = 128 layers on images of >= 32 rows take the MT = 2 variant (two stacked 8 x 16 pixel tiles per weight box,
+    two accumulators); odd heights leave the second tile partially or completely outside the image."""
+    from geoformer_b200.engine import pack_conv3x3
+    b, cout = 2, 128
+    x = rnd(b, cin, h, w, seed=1).bfloat16()
+    wgt = (rnd(cout, cin, 3, 3, seed=2) * (cin * 9) ** -0.5).bfloat16()
+    bias = rnd(cout, seed=3) * 0.1
+    r = rnd(b, cout, h, w, seed=4).bfloat16() if res else None
+    want = F.conv2d(x.float(), wgt.float(), bias, 1, 1)
+    want = F.relu(want + r.float()) if res else F.relu(want)
+    xp = torch.zeros(b, h, w, cin_p, dtype=torch.bfloat16); xp[..., :cin] = x.permute(0, 2, 3, 1)
+    rp = dev(r.permute(0, 2, 3, 1)) if res else None
+    wt, bp = pack_conv3x3(wgt.float(), bias, cin_p, cout, "cuda")
+    got = ops.conv3x3(dev(xp), wt, bp, rp, 1).cpu().float().permute(0, 3, 1, 2)
+    err = (got - want).abs().max().item()
+    assert err <= 1e-2 * want.abs().max().item(), err
+
+
 @pytest.mark.parametrize("cin,cout,cin_p,cout_p,ksize,stride,hw,act", [
     (128, 196, 128, 200, 3, 2, (20, 40), 1),      # layer2.0.conv1: 3x3 / stride 2 + ReLU
     (128, 196, 128, 200, 1, 2, (20, 40), 0),      # layer2.0.downsample: 1x1 / stride 2
