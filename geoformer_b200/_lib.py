@@ -60,6 +60,7 @@ SIGNATURES = {
     "gf_select_rows": (I, [P, P, P, I, L, I, P]),
     "gf_fine_gather": (I, [P, I, I, I, P, P, L, I, I, I, P, P]),
     "gf_fine_gather_bf16": (I, [P, I, I, I, P, P, L, I, I, I, P, P]),
+    "gf_fine_gather_bf16_f16": (I, [P, I, I, I, P, P, L, I, I, I, P, P]),
     "gf_gather_rows": (I, [P, L, I, P, P, L, P, P]),
     "gf_fine_match": (I, [P, P, L, I, I, F, F, P, P, P, P, P, P]),
     "gf_resize_gray_u8": (I, [P, I, I, P, I, I, P]),

@@ -3,21 +3,32 @@
 
 #include <atomic>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace gf {
 extern std::atomic<int64_t> g_launches;
 
-// same gather from a bf16 NHWC fine map (the tcgen05 backbone's native output): 8-byte loads, fp32 windows out
+// same gather from a bf16 NHWC fine map (the tcgen05 backbone's native output): 8-byte loads; windows out as fp32, or as
+// fp16 (exact for bf16 values in fp16's range) when they feed the fp16-operand merge GEMM
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(__half* p, float4 v) {
+  const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&a); u.y = *reinterpret_cast<const uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <typename TO>
 __global__ void fine_gather_bf16_kernel(const __nv_bfloat16* __restrict__ fine, int hf, int wf, int c,
                                         const int64_t* __restrict__ b_ids, const int64_t* __restrict__ tok_ids, int wc,
-                                        int stride, int window, float* __restrict__ out) {
+                                        int stride, int window, TO* __restrict__ out) {
   const int64_t m = blockIdx.x;
   const int b = (int)b_ids[m];
   const int tok = (int)tok_ids[m];
   const int cy = (tok / wc) * stride, cx = (tok % wc) * stride;
   const int half = window / 2;
   const int c4 = c >> 2;
-  float4* o = reinterpret_cast<float4*>(out + m * window * window * c);
+  TO* o = out + m * window * window * c;
   for (int e = threadIdx.x; e < window * window * c4; e += blockDim.x) {
     const int slot = e / c4, q = e - slot * c4;
     const int py = cy + slot / window - half, px = cx + slot % window - half;
@@ -28,7 +39,7 @@ __global__ void fine_gather_bf16_kernel(const __nv_bfloat16* __restrict__ fine, 
       const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
       v = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
     }
-    o[e] = v;
+    store4(o + 4 * e, v);
   }
 }
 
@@ -281,8 +292,20 @@ extern "C" int gf_fine_gather_bf16(const void* fine_nhwc, int hf, int wf, int c,
                                    gf_stream_t stream) {
   if (m < 0 || c <= 0 || (c % 4) || window <= 0) return gf_set_error(GF_ERR_ARG, "gf_fine_gather_bf16: bad shape");
   if (m == 0) return GF_OK;
-  fine_gather_bf16_kernel<<<(unsigned)m, 128, 0, STREAM>>>((const __nv_bfloat16*)fine_nhwc, hf, wf, c, b_ids, tok_ids, wc,
-                                                          stride, window, out);
+  fine_gather_bf16_kernel<float><<<(unsigned)m, 128, 0, STREAM>>>((const __nv_bfloat16*)fine_nhwc, hf, wf, c, b_ids, tok_ids, wc,
+                                                                 stride, window, out);
+  g_launches++;
+  GF_CHECK_LAUNCH();
+  return GF_OK;
+}
+
+extern "C" int gf_fine_gather_bf16_f16(const void* fine_nhwc, int hf, int wf, int c, const int64_t* b_ids,
+                                       const int64_t* tok_ids, int64_t m, int wc, int stride, int window, void* out,
+                                       gf_stream_t stream) {
+  if (m < 0 || c <= 0 || (c % 4) || window <= 0) return gf_set_error(GF_ERR_ARG, "gf_fine_gather_bf16_f16: bad shape");
+  if (m == 0) return GF_OK;
+  fine_gather_bf16_kernel<__half><<<(unsigned)m, 128, 0, STREAM>>>((const __nv_bfloat16*)fine_nhwc, hf, wf, c, b_ids, tok_ids, wc,
+                                                                  stride, window, (__half*)out);
   g_launches++;
   GF_CHECK_LAUNCH();
   return GF_OK;

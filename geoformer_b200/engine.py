@@ -122,7 +122,8 @@ class PackedWeights:
         wm = sd["fine_preprocess.merge_feat.weight"]
         cf = wm.shape[0]
         self.fp = dict(wd=f32(sd["fine_preprocess.down_proj.weight"]), bd=f32(sd["fine_preprocess.down_proj.bias"]),
-                       wa=f32(wm[:, :cf]), wb=f32(wm[:, cf:]), bm=f32(sd["fine_preprocess.merge_feat.bias"]))
+                       wa=f32(wm[:, :cf]), wa16=f16(wm[:, :cf]), wb=f32(wm[:, cf:]),
+                       bm=f32(sd["fine_preprocess.merge_feat.bias"]))
 
         # backbone: BN folded, channels-last, tensor-core dtype (cuDNN through torch).  Channel counts that
         # are not a multiple of `cpad_to` (the 196-wide stage) are zero-padded in the weights: padded output
@@ -284,16 +285,16 @@ def backbone_forward_tc(pw: PackedWeights, img: torch.Tensor) -> Tuple[torch.Ten
 # --------------------------------------------------------------------------------------------
 # transformer layers
 # --------------------------------------------------------------------------------------------
-def _post_attention(lw: dict, x2d: torch.Tensor, msg: torch.Tensor, act: int) -> torch.Tensor:
+def _post_attention(lw: dict, x2d: torch.Tensor, msg: torch.Tensor, act: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """merge -> LN1 -> MLP(cat[x, msg]) -> LN2 -> residual   (transformer.py:53-60)."""
     h16 = ops.act16()
     m1 = ops.linear(msg, lw["wm16"] if msg.dtype == torch.float16 else lw["wm"], epi=EPI_LN, gamma=lw["n1w"], beta=lw["n1b"])
     h = ops.linear(x2d, lw["w1"], a2=m1, epi=act, out_f16=h16)
-    return ops.linear(h, lw["w2_16"] if h16 else lw["w2"], epi=EPI_LN, gamma=lw["n2w"], beta=lw["n2b"], residual=x2d)
+    return ops.linear(h, lw["w2_16"] if h16 else lw["w2"], epi=EPI_LN, gamma=lw["n2w"], beta=lw["n2b"], residual=x2d, out=out)
 
 
-def loftr_layer(lw: dict, x: torch.Tensor, src: torch.Tensor, heads: int) -> torch.Tensor:
-    """LoFTR encoder layer with linear attention; x [n,L,C], src [n,S,C] -> [n,L,C]."""
+def loftr_layer(lw: dict, x: torch.Tensor, src: torch.Tensor, heads: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LoFTR encoder layer with linear attention; x [n,L,C], src [n,S,C] -> [n,L,C] (written into `out` if given)."""
     n, l, c = x.shape
     s = src.shape[1]
     d = c // heads
@@ -307,7 +308,7 @@ def loftr_layer(lw: dict, x: torch.Tensor, src: torch.Tensor, heads: int) -> tor
         kv = ops.linear(src.reshape(n * s, c), lw["wkv"], epi=EPI_ELU1, act_cols=c, out_f16=a16)
         k, v, ldq, ldk = kv, kv[:, c:], c, 2 * c
     msg = ops.linattn(q, ldq, k, ldk, v, ldk, n, l, s, heads, d)
-    return _post_attention(lw, x2d, msg, EPI_RELU).view(n, l, c)
+    return _post_attention(lw, x2d, msg, EPI_RELU, None if out is None else out.view(n * l, c)).view(n, l, c)
 
 
 def coarse_transformer(pw: PackedWeights, x0: torch.Tensor, x1: torch.Tensor, names, heads: int):
@@ -325,14 +326,15 @@ def coarse_transformer(pw: PackedWeights, x0: torch.Tensor, x1: torch.Tensor, na
             else:
                 x0 = loftr_layer(lw, x0, x0, heads)
                 x1 = loftr_layer(lw, x1, x1, heads)
+        elif same:                                    # both results land in the halves of one fresh 2n-sample buffer
+            Xn = torch.empty_like(X)
+            y0 = loftr_layer(lw, x0, x1, heads, out=Xn[:n])
+            loftr_layer(lw, x1, y0, heads, out=Xn[n:])         # sees the UPDATED feat0 (transformer.py:99-100)
+            X = Xn
+            x0, x1 = X[:n], X[n:]
         else:
             y0 = loftr_layer(lw, x0, x1, heads)
-            y1 = loftr_layer(lw, x1, y0, heads)       # sees the UPDATED feat0 (transformer.py:99-100)
-            if same:
-                X = torch.cat([y0, y1], 0)
-                x0, x1 = X[:n], X[n:]
-            else:
-                x0, x1 = y0, y1
+            x0, x1 = y0, loftr_layer(lw, x1, y0, heads)
     return x0, x1
 
 
@@ -522,7 +524,8 @@ def fine_stage(pw: PackedWeights, fine0: torch.Tensor, fine1: torch.Tensor, g0: 
     cf = fine0.shape[-1]
     stride = hw0_f[0] // hw0_c[0]
     # fine_preprocess.py:41-72.  merge_feat(cat[win, ctx]) = win Wa^T + (ctx Wb^T + b)
-    win = torch.empty((2 * m, ww, cf), device=dev, dtype=torch.float32)
+    w16 = ops.act16() and fine0.dtype == torch.bfloat16 and cf % 64 == 0      # bf16 map -> fp16 windows -> fp16-operand merge
+    win = torch.empty((2 * m, ww, cf), device=dev, dtype=torch.float16 if w16 else torch.float32)
     ops.fine_gather(fine0, b_ids, i_ids, hw0_c[1], stride, window, out=win[:m])
     ops.fine_gather(fine1, b_ids, j_ids, hw1_c[1], stride, window, out=win[m:])
     ctx = torch.empty((2 * m, g0.shape[-1]), device=dev)
@@ -530,7 +533,8 @@ def fine_stage(pw: PackedWeights, fine0: torch.Tensor, fine1: torch.Tensor, g0: 
     ops.gather_rows(g1, b_ids, j_ids, out=ctx[m:])
     cw = ops.linear(ctx, pw.fp["wd"], bias=pw.fp["bd"])                          # down_proj            [2m, 128]
     cterm = ops.linear(cw, pw.fp["wb"], bias=pw.fp["bm"])                        # coarse half of merge [2m, 128]
-    X = ops.linear(win.view(2 * m * ww, cf), pw.fp["wa"], rowbias=cterm, rowbias_group=ww).view(2 * m, ww, cf)
+    X = ops.linear(win.view(2 * m * ww, cf), pw.fp["wa16"] if w16 else pw.fp["wa"], rowbias=cterm,
+                   rowbias_group=ww).view(2 * m, ww, cf)
     pre = X
     f0, f1 = X[:m], X[m:]
     for lw, name in zip(pw.fine, names):

@@ -133,7 +133,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, a2: Optional[torch.Tensor] = None, 
     fp16 (kind::f16 MMA, tensor-core path only).  out_f16: fp16 result (lean epilogue: no LN / residual / row bias)."""
     in_f16 = a.dtype == torch.float16
     if in_f16 or out_f16:
-        return _linear_mixed(a, w, a2, epi, act_cols, bias, rowbias, rowbias_group, gamma, beta, residual, in_f16, out_f16)
+        return _linear_mixed(a, w, a2, epi, act_cols, bias, rowbias, rowbias_group, gamma, beta, residual, in_f16, out_f16, out)
     _chk(a); _chk(w)
     m, k1 = a.shape
     n = w.shape[0]
@@ -151,7 +151,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, a2: Optional[torch.Tensor] = None, 
     return y
 
 
-def _linear_mixed(a, w, a2, epi, act_cols, bias, rowbias, rowbias_group, gamma, beta, residual, in_f16, out_f16):
+def _linear_mixed(a, w, a2, epi, act_cols, bias, rowbias, rowbias_group, gamma, beta, residual, in_f16, out_f16, out=None):
     dt = torch.float16 if in_f16 else torch.float32
     _chk(a, dt); _chk(w, dt)
     if (_LINEAR_IMPL != "tf32"):
@@ -165,7 +165,10 @@ def _linear_mixed(a, w, a2, epi, act_cols, bias, rowbias, rowbias_group, gamma, 
         assert a2.is_contiguous() and a2.shape[0] == m
     if residual is not None:
         assert residual.is_contiguous() and residual.shape == (m, n) and residual.dtype == torch.float32
-    y = torch.empty((m, n), device=a.device, dtype=torch.float16 if out_f16 else torch.float32)
+    ydt = torch.float16 if out_f16 else torch.float32
+    if out is not None:
+        assert out.shape == (m, n) and out.dtype == ydt and out.is_contiguous()
+    y = out if out is not None else torch.empty((m, n), device=a.device, dtype=ydt)
     _call("gf_linear_mixed", a.data_ptr(), _ptr(a2), w.data_ptr(), y.data_ptr(), int(in_f16), int(out_f16), m, n, k1, k2,
           epi, act_cols, _ptr(bias), _ptr(rowbias), rowbias_group, _ptr(gamma), _ptr(beta), _ptr(residual), None,
           _stream(), tag=f"[{n}x{k1 + k2}{'h' if in_f16 else ''}{'>h' if out_f16 else ''}]")
@@ -438,7 +441,11 @@ def fine_gather(fine_nhwc: torch.Tensor, b_ids, tok_ids, wc: int, stride: int, w
     m = b_ids.shape[0]
     if out is None:
         out = torch.empty((m, window * window, c), device=fine_nhwc.device, dtype=torch.float32)
-    fn = "gf_fine_gather_bf16" if fine_nhwc.dtype == torch.bfloat16 else "gf_fine_gather"
+    if out.dtype == torch.float16:
+        assert fine_nhwc.dtype == torch.bfloat16
+        fn = "gf_fine_gather_bf16_f16"
+    else:
+        fn = "gf_fine_gather_bf16" if fine_nhwc.dtype == torch.bfloat16 else "gf_fine_gather"
     _call(fn, fine_nhwc.data_ptr(), hf, wf, c, b_ids.data_ptr(), tok_ids.data_ptr(), m, wc, stride,
               window, out.data_ptr(), _stream())
     return out

@@ -240,6 +240,9 @@ int gf_fine_gather(const float* fine_nhwc, int hf, int wf, int c, const int64_t*
 /* same, reading a bf16 NHWC fine map (native output of the tcgen05 backbone) */
 int gf_fine_gather_bf16(const void* fine_nhwc, int hf, int wf, int c, const int64_t* b_ids, const int64_t* tok_ids,
                         int64_t m, int wc, int stride, int window, float* out, gf_stream_t stream);
+/* same, windows written as fp16 (exact for bf16 inputs in fp16 range): A operand of the fp16 merge_feat GEMM */
+int gf_fine_gather_bf16_f16(const void* fine_nhwc, int hf, int wf, int c, const int64_t* b_ids, const int64_t* tok_ids,
+                            int64_t m, int wc, int stride, int window, void* out, gf_stream_t stream);
 /* rows out[m,:] = feat[b_ids[m], tok_ids[m], :] */
 int gf_gather_rows(const float* feat, int64_t l, int c, const int64_t* b_ids, const int64_t* tok_ids, int64_t m,
                    float* out, gf_stream_t stream);
