@@ -59,13 +59,16 @@ def workload_config(args, extra=None):
 
 # ------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """SM clock / throttle-reason samples during the timed region, through NVML in-process (nvidia_ml_py): one light
-    query every 100 ms.  (A looping `nvidia-smi` subprocess takes the driver lock for whole milliseconds per poll and
-    showed up as sporadic 50-100 ms stalls of the kernel-launching threads.)"""
+    """SM clock / throttle-reason samples under the bench load, through NVML in-process (nvidia_ml_py).
+    Every query goes through the driver's GPU lock and, about once in a hundred calls, stalled the kernel-launching
+    threads for ~100 ms (a looping `nvidia-smi` subprocess was worse): with 100 ms polling one timed loop in six lost a
+    whole step to it, without any polling none in 15 runs did.  So the timed loops are sampled sparsely (every 300 ms,
+    2-3 samples each) and the same load is run once more, untimed, with dense sampling; all samples are reported."""
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         self.index, self.samples, self.first, self.stop_flag, self.thread, self.h = index, [], 0, False, None, None
+        self.interval, self.timed_samples = 0.3, 0
 
     def start(self):
         try:
@@ -91,7 +94,7 @@ class ClockSampler:
                 self.samples.append((mhz, mask))
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(self.interval)
 
     def mark(self):
         """Samples from here on belong to the timed region."""
@@ -105,7 +108,7 @@ class ClockSampler:
         use = self.samples[self.first:] or self.samples
         reasons = sorted({nm for _, mask in use for nm, bit in self.REASONS if mask & bit})
         return {"sm_mhz": float(np.median([m for m, _ in use])) if use else None, "sm_max_mhz": self.max_mhz,
-                "samples": len(use), "reasons": reasons}
+                "samples": len(use), "samples_inside_timed_loops": self.timed_samples, "reasons": reasons}
 
 
 # ------------------------------------------------------------------------------------------- reference arm / CPU baseline
@@ -181,7 +184,10 @@ def run_ours(args):
     from geoformer_b200.pipeline import MatchPipeline
     pipe = MatchPipeline(model, depth=args.depth, device=device)
 
+    done_t = []                    # host completion time of every batch (GF_BENCH_TRACE=1 prints the gaps to stderr)
+
     def counts_only(d):            # keep only what the report needs (frees the big per-batch tensors early)
+        done_t.append(time.perf_counter())
         return {"b_ids": d["b_ids"].shape[0], "mkpts0_f": d["mkpts0_f"].shape[0]}
 
     def to_host(d):                # what match_pairs() reads back (geoformer.py:53-54,73)
@@ -215,14 +221,27 @@ def run_ours(args):
         return ms, outs, _lib.launch_count() - l0
 
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("GF_BENCH_NO_CLOCKS"):
         sampler.start()
     run_resident(args.warmup)
     run_e2e(args.warmup)
-    run_resident(args.warmup)          # both paths have their buffers in the caching allocator before anything is timed
+    # Settle pass (untimed, on top of the W warm-up steps): ~1.5 s of the same load.  The board reaches its power cap
+    # about a second into sustained load; the clock step-down that follows cost one timed loop in three a 100-300 ms
+    # stall when it fell inside it (0 of 7 runs with the settle pass, also 0 of 15 without NVML polling).
+    settle = max(args.warmup, int(os.environ.get('GF_BENCH_PREWARM', '40')))
+    run_resident(settle)
     sampler.mark()
+    done_t.clear()
     ms, outs, launches = timed(run_resident, args.steps)
+    if os.environ.get("GF_BENCH_TRACE") and rank == 0:
+        print("value loop, ms between batch completions:", " ".join(f"{1e3 * (b - a):.0f}" for a, b in zip(done_t, done_t[1:])),
+              file=sys.stderr)
     ms_e2e, outs_e2e, _ = timed(run_e2e, args.steps)
+    if rank == 0 and sampler.h is not None:      # same load once more, untimed, densely sampled (see ClockSampler)
+        sampler.timed_samples = len(sampler.samples) - sampler.first
+        sampler.interval = 0.04
+        run_resident(max(4, args.steps // 2))
+        sampler.interval = 0.3
     # dominant-kernel timing, live in this run: the two tcgen05 passes of the conf-matrix kernel (statistics pass and
     # confidence pass; each launch contracts the full n x L x S x C problem), CUDA events on the launching stream
     L_ = (H // 8) * (W // 8)
@@ -340,7 +359,8 @@ def run_ours(args):
                      else f"tf32 projections/attention, split-f16 similarity, {args.backbone} backbone",
             "data": "synthetic",
             "config": workload_config(args, {"matches_coarse_per_pair": mc, "matches_fine_per_pair": mf,
-                                             "batches_in_flight": args.depth, "ransac": args.ransac, "exchange_ms_per_batch_gather": exchange_ms,
+                                             "batches_in_flight": args.depth, "ransac": args.ransac,
+                                             "untimed_steps_before_timing": f"{args.warmup} warm-up (resident) + {args.warmup} warm-up (host inputs) + {settle} power-cap settle", "exchange_ms_per_batch_gather": exchange_ms,
                                              "gathered_matches": gathered,
                                              "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective"}),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * args.batch * H * W * 4, "d2h_bytes_per_step": d2h},
