@@ -125,12 +125,18 @@ def make_pairs(n: int, h: int, w: int, regime: str = "dense", seed0: int = 0):
     """``n`` synthetic pairs -> (image0 [n,1,h,w], image1 [n,1,h,w]).
 
     regimes (SURVEY.md §8d): 'dense' image1 == image0 (M_c ~ 0.79 L, the heavy case);
-    'shift' image1 = roll(image0, (8a, 8b)) (valid translation homography, few hundred matches)."""
+    'shift' image1 = roll(image0, (8a, 8b)) (valid translation homography, few hundred matches);
+    'mixed' sample i: i % 3 == 0 dense, == 1 an UNRELATED image (a handful of noise matches: the no-homography /
+    garbage-homography branches of geo_module.py:45-94 inside one batch), == 2 shift."""
     im0 = torch.cat([make_image(h, w, seed0 + i) for i in range(n)], 0)
+    shift = lambda i: torch.roll(im0[i], (8 * (1 + i % 2), 8 * (2 - i % 2)), (1, 2))
     if regime == "dense":
         im1 = im0.clone()
     elif regime == "shift":
-        im1 = torch.stack([torch.roll(im0[i], (8 * (1 + i % 2), 8 * (2 - i % 2)), (1, 2)) for i in range(n)], 0)
+        im1 = torch.stack([shift(i) for i in range(n)], 0)
+    elif regime == "mixed":
+        im1 = torch.stack([im0[i].clone() if i % 3 == 0 else (make_image(h, w, seed0 + 1000 + i)[0] if i % 3 == 1 else shift(i))
+                           for i in range(n)], 0)
     else:
         raise ValueError(regime)
     return im0, im1

@@ -94,7 +94,7 @@ def npify(d):
     return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
 
 
-def small_case(name, h, w, regime, n, seed0, randomize_norm, coarse_thr=0.0, fine_thr=0.1):
+def small_case(name, h, w, regime, n, seed0, randomize_norm, coarse_thr=0.0, fine_thr=0.1, slim=False):
     sd = synth.make_state_dict(seed=7, randomize_norm=randomize_norm)
     model = build_reference(sd, coarse_thr, fine_thr)
     im0, im1 = synth.make_pairs(n, h, w, regime, seed0)
@@ -119,8 +119,14 @@ def small_case(name, h, w, regime, n, seed0, randomize_norm, coarse_thr=0.0, fin
     if "loftr_fine" in cap:
         a, b = cap["loftr_fine"][0]
         out.update(fine_out0=a[:16], fine_out1=b[:16])
+    if slim:            # match lists + geo features only (keeps the fixture small)
+        for k in ("cnn_c", "fine_sub", "coarse0", "coarse1", "dect_conf", "conf", "fine_matrix", "fine_in0", "fine_in1",
+                  "fine_out0", "fine_out1"):
+            out.pop(k, None)
+        first = cap["coarse_matching"][0] if "coarse_matching" in cap else None
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **npify(out))
-    print(name, "M_c", len(data["b_ids"]), "M_f", len(data["mkpts0_f"]))
+    print(name, "M_c", len(data["b_ids"]), "M_f", len(data["mkpts0_f"]),
+          "per sample", np.bincount(np.asarray(data["b_ids"]), minlength=n).tolist())
 
 
 def full_case(name, h, w, regime, seed0, coarse_thr=0.0):
@@ -181,7 +187,11 @@ def eval_and_ingest_case():
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if "--only-mixed" in sys.argv:
+        small_case("small_mixed", 96, 128, "mixed", 3, 30, True, slim=True)     # dense + unrelated (noise matches) + shift in one batch
+        sys.exit(0)
     if "--only-eval" not in sys.argv:
+        small_case("small_mixed", 96, 128, "mixed", 3, 30, True, slim=True)
         small_case("small_dense", 96, 128, "dense", 2, 0, True)
         small_case("small_shift", 96, 128, "shift", 1, 10, True)
         small_case("small_rect_thr", 64, 96, "dense", 1, 20, False, coarse_thr=0.2)   # zero-match corner

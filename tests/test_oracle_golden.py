@@ -64,6 +64,19 @@ def test_small_cases_stagewise(golden_dir, name):
         assert out["mkpts0_f"].shape == (0, 2) and out["fine_matrix"].shape == (0, 25, 25)
 
 
+def test_mixed_batch_match_lists(golden_dir):
+    """One batch holding a dense pair, an UNRELATED pair (noise matches -> RANSAC on garbage, windows mostly out of
+    bounds) and a shifted pair: the per-sample branches of geo_module.py:45-94 side by side.  The oracle must reproduce
+    the reference's integer outputs exactly (slim fixture: match lists + geo features)."""
+    g = _load(golden_dir, "small_mixed")
+    out, cap = _run(g, 7)
+    assert np.bincount(g["b_ids"], minlength=3).min() > 8            # every sample takes the RANSAC branch
+    _close(cap["geo0"], g["geo0"]); _close(cap["geo1"], g["geo1"])
+    for k in ("b_ids", "i_ids", "j_ids", "m_bids", "mkpts0_c", "mkpts1_c", "mkpts0_f", "mkpts1_f"):
+        assert np.array_equal(out[k].numpy(), g[k]), k
+    _close(out["mconf"], g["mconf"], 1e-3)
+
+
 def test_full_size_dense_pair(golden_dir):
     """480x640 single pair, dense regime: the reference's final match list is reproduced exactly."""
     g = _load(golden_dir, "full_dense_480x640")
