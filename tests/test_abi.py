@@ -76,3 +76,26 @@ def test_product_does_not_import_oracle():
     code = ("import sys; sys.path.insert(0, %r); import geoformer_b200.model.full_model, geoformer_b200.pipeline, "
             "geoformer_b200.dist; assert not any(m.startswith('oracle') for m in sys.modules), 'oracle imported'") % ROOT
     subprocess.run([sys.executable, "-c", code], check=True)
+
+
+def test_header_is_valid_c_and_links_from_a_c_host(tmp_path):
+    """The boundary is a C ABI: include/geoformer_b200.h must compile as plain C99 (no C++-isms, no torch types) and a C
+    host must link against the shared library and call into it (gf_abi_version needs no GPU)."""
+    import shutil
+    import subprocess
+    from geoformer_b200 import build
+    if shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("gcc not available")
+    lib = build.build()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "host.c"
+    src.write_text('#include "geoformer_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { printf("%d %s\\n", gf_abi_version(), gf_last_error()); return gf_abi_version() == 1 ? 0 : 1; }\n')
+    exe = tmp_path / "host"
+    inc = os.path.join(root, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)], check=True)
+    subprocess.run(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", os.path.dirname(lib),
+                    "-l:" + os.path.basename(lib), "-Wl,-rpath," + os.path.dirname(lib)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out[0] == "1"
