@@ -71,8 +71,8 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return copysignf(t, x);
 }
 
-// FULL = false: lean epilogue (scale, bias, activation) with the TMEM loads software-pipelined one chunk ahead;
-// FULL = true : + row-group bias, LayerNorm, residual (staged through shared memory).
+// FULL = false: lean epilogue (scale, bias, row-group bias, activation) with the TMEM loads software-pipelined one chunk
+//                ahead; FULL = true : + LayerNorm, residual (staged through shared memory).
 // CL = 2 (opt-in, env GF_CLUSTER2): two CTAs of a cluster work on vertically adjacent M tiles of the same N tile and
 // share the B operand: each CTA TMA-loads half of every B box and multicasts it into both shared memories, cutting
 // the per-SM L2 -> smem operand traffic from (A + B) to (A + B/2) per k-block.  Measured on B200: no gain (the
@@ -288,17 +288,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) if (gc + j < p.N) v[j] += __ldg(p.bias + gc + j);
           }
         }
-        if constexpr (FULL) {
-          if (rb && row_ok) {
-            if (full) {
+        if (rb && row_ok) {        // per-row-group bias (fine merge_feat: one coarse-context row per 25-token window)
+          if (full) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(rb + gc) + j);
-                v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-              }
-            } else {
-              for (int j = 0; j < 32; ++j) if (gc + j < p.N) v[j] += __ldg(rb + gc + j);
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(rb + gc) + j);
+              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
             }
+          } else {
+            for (int j = 0; j < 32; ++j) if (gc + j < p.N) v[j] += __ldg(rb + gc + j);
           }
         }
         if (p.epi & GF_EPI_RELU) {
@@ -521,9 +519,9 @@ static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& ta2, const CU
 template <int KIND, int BN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& ty,
                        const GemmParams& p, cudaStream_t stream, bool out16 = false) {
-  const bool full = (p.epi & GF_EPI_LN) || p.residual != nullptr || p.rowbias != nullptr || !p.tma_store;
+  const bool full = (p.epi & GF_EPI_LN) || p.residual != nullptr || !p.tma_store;
   if (out16) {
-    if (full) return gf_set_error(GF_ERR_ARG, "fp16 output is available with the lean epilogue only (no LN / residual / row bias)");
+    if (full) return gf_set_error(GF_ERR_ARG, "fp16 output is available with the lean epilogue only (no LN / residual)");
     if constexpr (KIND == 0) return launch_gemm_t<KIND, BN, false, 1, true>(ta, ta2, tb, ty, p, stream);
     else return gf_set_error(GF_ERR_ARG, "fp16 output needs fp32 (tf32) operands");
   }
