@@ -133,6 +133,11 @@ class GeoFormer(nn.Module):
     @torch.no_grad()
     def forward(self, data: Dict[str, torch.Tensor]):
         img0, img1 = data["image0"], data["image1"]
+        if data.get("mask0") is not None or data.get("mask1") is not None:
+            # padding masks only exist in the MegaDepth TRAINING collation (optional); ignoring them silently
+            # would change the result, so refuse
+            raise NotImplementedError("geoformer_b200.GeoFormer: padding masks (mask0/mask1) are not supported; "
+                                      "the inference wrappers never pass them")
         if not img0.is_cuda:
             raise RuntimeError("geoformer_b200.GeoFormer runs on CUDA (sm_100a) only; there is no CPU fallback")
         pw = self._weights(img0.device)

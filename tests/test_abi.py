@@ -71,6 +71,16 @@ def test_no_cpu_fallback():
         ops.similarity(torch.zeros(1, 8, 256), torch.zeros(1, 8, 256), 0.1)
 
 
+def test_padding_masks_are_refused_not_ignored():
+    from geoformer_b200.model.full_model import GeoFormer
+    from geoformer_b200.model.geo_config import default_cfg as geo_cfg
+    from geoformer_b200.model.loftr_src.loftr.utils.cvpr_ds_config import default_cfg
+    m = GeoFormer(copy.deepcopy(default_cfg), dict(geo_cfg)).eval()
+    x = torch.zeros(1, 1, 32, 32)
+    with pytest.raises(NotImplementedError):
+        m({"image0": x, "image1": x, "mask0": torch.ones(1, 4, 4, dtype=torch.bool)})
+
+
 def test_product_does_not_import_oracle():
     import subprocess, sys
     code = ("import sys; sys.path.insert(0, %r); import geoformer_b200.model.full_model, geoformer_b200.pipeline, "
