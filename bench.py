@@ -355,8 +355,8 @@ def run_ours(args):
                  "traffic": fl_bytes * (2.826 / 2.867), "tensor_pipe_active_pct_ncu": 28.8}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32 projections/attention, split-f16 similarity, bf16 backbone" if args.backbone == "bf16"
-                     else f"tf32 projections/attention, split-f16 similarity, {args.backbone} backbone",
+            "dtype": ("tf32 / fp16 tensor-core operands with fp32 accumulation (fp32 residual stream, fp16 intermediates), "
+                      f"split-fp16 similarity, {args.backbone} backbone"),
             "data": "synthetic",
             "config": workload_config(args, {"matches_coarse_per_pair": mc, "matches_fine_per_pair": mf,
                                              "batches_in_flight": args.depth, "ransac": args.ransac,
