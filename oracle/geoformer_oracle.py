@@ -120,10 +120,18 @@ def add_pe_flatten(fmap: torch.Tensor) -> torch.Tensor:
 # LoFTR encoder layer + linear attention
 # model/loftr_src/loftr/loftr_module/transformer.py:37-60, linear_attention.py:21-51
 # ----------------------------------------------------------------------------
-def linear_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
-    """q [N,L,H,D], k/v [N,S,H,D] -> [N,L,H,D] (linear_attention.py:33-51, unmasked)."""
+def linear_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, eps: float = 1e-6,
+                     q_mask: Optional[torch.Tensor] = None, kv_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [N,L,H,D], k/v [N,S,H,D] -> [N,L,H,D] (linear_attention.py:33-51).  Optional padding masks q_mask [N,L],
+    kv_mask [N,S] zero the feature-mapped Q / K and the values of padded tokens (lines 37-43); the normaliser
+    v_length stays the full S."""
     Q = F.elu(q) + 1
     K = F.elu(k) + 1
+    if q_mask is not None:
+        Q = Q * q_mask[:, :, None, None]
+    if kv_mask is not None:
+        K = K * kv_mask[:, :, None, None]
+        v = v * kv_mask[:, :, None, None]
     s_len = v.size(1)
     v = v / s_len
     KV = torch.einsum("nshd,nshv->nhdv", K, v)
@@ -149,7 +157,7 @@ def softmax_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
 
 def encoder_layer(P: Params, pre: str, x: torch.Tensor, src: torch.Tensor, nhead: int,
                   attention: str = "linear", act: str = "relu",
-                  kv_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  kv_mask: Optional[torch.Tensor] = None, q_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """One LoFTR-style layer.  ``act``: 'relu' for LoFTR (transformer.py:27-31),
     'tanh' for the geo transformer (model/geo_transformer/transformer.py:29-33)."""
     n, _, c = x.shape
@@ -158,7 +166,7 @@ def encoder_layer(P: Params, pre: str, x: torch.Tensor, src: torch.Tensor, nhead
     k = F.linear(src, P[pre + ".k_proj.weight"]).view(n, -1, nhead, d)
     v = F.linear(src, P[pre + ".v_proj.weight"]).view(n, -1, nhead, d)
     if attention == "linear":
-        m = linear_attention(q, k, v)
+        m = linear_attention(q, k, v, q_mask=q_mask, kv_mask=kv_mask)
     else:
         m = softmax_attention(q, k, v, kv_mask)
     m = F.linear(m.view(n, -1, c), P[pre + ".merge.weight"])
@@ -171,28 +179,33 @@ def encoder_layer(P: Params, pre: str, x: torch.Tensor, src: torch.Tensor, nhead
 
 
 def local_feature_transformer(P: Params, pre: str, f0: torch.Tensor, f1: torch.Tensor,
-                              layer_names, nhead: int) -> Tuple[torch.Tensor, torch.Tensor]:
+                              layer_names, nhead: int, mask0: Optional[torch.Tensor] = None,
+                              mask1: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """loftr_module/transformer.py:82-104.  NB: the cross update of f1 sees the
-    *already updated* f0 (lines 99-100)."""
+    *already updated* f0 (lines 99-100).  mask0/mask1 [N,L]/[N,S]: optional padding masks (training collation)."""
     for i, name in enumerate(layer_names):
         lp = f"{pre}.layers.{i}"
         if name == "self":
-            f0 = encoder_layer(P, lp, f0, f0, nhead)
-            f1 = encoder_layer(P, lp, f1, f1, nhead)
+            f0 = encoder_layer(P, lp, f0, f0, nhead, q_mask=mask0, kv_mask=mask0)
+            f1 = encoder_layer(P, lp, f1, f1, nhead, q_mask=mask1, kv_mask=mask1)
         else:
-            f0 = encoder_layer(P, lp, f0, f1, nhead)
-            f1 = encoder_layer(P, lp, f1, f0, nhead)
+            f0 = encoder_layer(P, lp, f0, f1, nhead, q_mask=mask0, kv_mask=mask1)
+            f1 = encoder_layer(P, lp, f1, f0, nhead, q_mask=mask1, kv_mask=mask0)
     return f0, f1
 
 
 # ----------------------------------------------------------------------------
 # coarse matching: model/loftr_src/loftr/utils/coarse_matching.py:90-212
 # ----------------------------------------------------------------------------
-def dual_softmax_conf(f0: torch.Tensor, f1: torch.Tensor, temperature: float) -> torch.Tensor:
-    """conf [N,L,S] (coarse_matching.py:110-125; fine_matching2.py:52-60)."""
+def dual_softmax_conf(f0: torch.Tensor, f1: torch.Tensor, temperature: float, mask0: Optional[torch.Tensor] = None,
+                      mask1: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """conf [N,L,S] (coarse_matching.py:110-125; fine_matching2.py:52-60).  With padding masks the logits of padded
+    rows / columns are filled with -1e9 before the two softmaxes (coarse_matching.py:120-124, INF = 1e9)."""
     c = f0.shape[-1]
     a, b = f0 / c ** 0.5, f1 / c ** 0.5
     sim = torch.einsum("nlc,nsc->nls", a, b) / temperature
+    if mask0 is not None:
+        sim = sim.masked_fill(~(mask0[..., None] * mask1[:, None]).bool(), -1e9)
     return F.softmax(sim, 1) * F.softmax(sim, 2)
 
 
@@ -415,8 +428,15 @@ def fine_match(conf: torch.Tensor, thr: float, mkpts0_c, mkpts1_c, b_ids, hw0_i,
 # full forward: model/full_model.py:39-123
 # ----------------------------------------------------------------------------
 def forward(P: Params, image0: torch.Tensor, image1: torch.Tensor, cfg: Optional[dict] = None,
-            capture: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+            capture: Optional[dict] = None, mask0: Optional[torch.Tensor] = None,
+            mask1: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """full_model.py:39-123.  mask0/mask1 [N,h_c,w_c] bool: the optional padding masks of the MegaDepth training
+    collation (full_model.py:80-84); they reach the coarse transformer and both coarse-matching calls only (border
+    masking with padding is a no-op at border_rm == 0, coarse_matching.py:54-56).  The product refuses masks."""
     cfg = {**DEFAULT_CFG, **(cfg or {})}
+    mc0 = None if mask0 is None else mask0.flatten(-2)
+    mc1 = None if mask1 is None else mask1.flatten(-2)
+    assert (mc0 is None) == (mc1 is None) and (mc0 is None or cfg["border_rm"] == 0)
     cap = capture if capture is not None else {}
     n = image0.shape[0]
     hw0_i, hw1_i = tuple(image0.shape[2:]), tuple(image1.shape[2:])
@@ -431,10 +451,10 @@ def forward(P: Params, image0: torch.Tensor, image1: torch.Tensor, cfg: Optional
 
     x0, x1 = add_pe_flatten(c0), add_pe_flatten(c1)
     cap.update(pe0=x0, pe1=x1)
-    t0, t1 = local_feature_transformer(P, "loftr_coarse", x0, x1, cfg["coarse_layers"], cfg["coarse_nhead"])
+    t0, t1 = local_feature_transformer(P, "loftr_coarse", x0, x1, cfg["coarse_layers"], cfg["coarse_nhead"], mc0, mc1)
     cap.update(coarse0=t0, coarse1=t1)
 
-    conf1 = dual_softmax_conf(t0, t1, cfg["coarse_temperature"])
+    conf1 = dual_softmax_conf(t0, t1, cfg["coarse_temperature"], mc0, mc1)
     m1 = coarse_match(conf1, cfg["coarse_thr"], hw0_i, hw0_c, hw1_c, cfg["border_rm"])
     cap.update(conf_first=conf1, first=m1)
 
@@ -442,7 +462,7 @@ def forward(P: Params, image0: torch.Tensor, image1: torch.Tensor, cfg: Optional
     g0, g1 = geo_transformer(P, x0, x1, geo, hw0_c, hw1_c, cfg)   # geo module's own PE == same table
     cap.update(geo=geo, geo0=g0, geo1=g1)
 
-    conf2 = dual_softmax_conf(g0, g1, cfg["coarse_temperature"])
+    conf2 = dual_softmax_conf(g0, g1, cfg["coarse_temperature"], mc0, mc1)
     m2 = coarse_match(conf2, cfg["coarse_thr"], hw0_i, hw0_c, hw1_c, cfg["border_rm"])
     cap.update(conf_second=conf2)
 

@@ -16,6 +16,7 @@ import types
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
@@ -72,7 +73,7 @@ def build_reference(sd, coarse_thr, fine_thr=0.1):
     return model
 
 
-def run_reference(model, im0, im1):
+def run_reference(model, im0, im1, masks=None):
     cap = {}
     hooks = []
 
@@ -84,7 +85,10 @@ def run_reference(model, im0, im1):
     for nm in ("backbone", "loftr_coarse", "geo_module", "fine_preprocess", "loftr_fine"):
         hooks.append(getattr(model, nm).register_forward_hook(grab(nm)))
     with torch.no_grad():
-        data = model({"image0": im0.clone(), "image1": im1.clone()})
+        inp = {"image0": im0.clone(), "image1": im1.clone()}
+        if masks is not None:
+            inp.update(mask0=masks[0].clone(), mask1=masks[1].clone())
+        data = model(inp)
     for h in hooks:
         h.remove()
     return data, cap
@@ -127,6 +131,32 @@ def small_case(name, h, w, regime, n, seed0, randomize_norm, coarse_thr=0.0, fin
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **npify(out))
     print(name, "M_c", len(data["b_ids"]), "M_f", len(data["mkpts0_f"]),
           "per sample", np.bincount(np.asarray(data["b_ids"]), minlength=n).tolist())
+
+
+def padded_masks(n, hc, wc):
+    """Valid regions of zero-padded images at coarse resolution (MegaDepth collation, datasets/megadepth.py:121-128)."""
+    m0, m1 = torch.zeros(n, hc, wc, dtype=torch.bool), torch.zeros(n, hc, wc, dtype=torch.bool)
+    for b in range(n):
+        m0[b, :hc - 2 - b, :wc - 3] = True
+        m1[b, :hc - 1, :wc - 4 - b] = True
+    return m0, m1
+
+
+def masked_case(name, h, w, n, seed0):
+    """Optional padding-mask path (oracle only; the product refuses masks): images are zero outside the valid region."""
+    sd = synth.make_state_dict(seed=7, randomize_norm=True)
+    model = build_reference(sd, 0.0)
+    im0, im1 = synth.make_pairs(n, h, w, "dense", seed0)
+    m0, m1 = padded_masks(n, h // 8, w // 8)
+    im0 = im0 * F.interpolate(m0[:, None].float(), scale_factor=8, mode="nearest")
+    im1 = im1 * F.interpolate(m1[:, None].float(), scale_factor=8, mode="nearest")
+    data, cap = run_reference(model, im0, im1, (m0, m1))
+    c0, c1 = cap["loftr_coarse"][0]
+    out = dict(meta=np.array([h, w, n, seed0, 1]), coarse0=c0, coarse1=c1,
+               b_ids=data["b_ids"], i_ids=data["i_ids"], j_ids=data["j_ids"],
+               mkpts0_f=data["mkpts0_f"], mkpts1_f=data["mkpts1_f"], mconf=data["mconf"], m_bids=data["m_bids"])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **npify(out))
+    print(name, "M_c", len(data["b_ids"]), "M_f", len(data["mkpts0_f"]))
 
 
 def full_case(name, h, w, regime, seed0, coarse_thr=0.0):
@@ -187,10 +217,14 @@ def eval_and_ingest_case():
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if "--only-masked" in sys.argv:
+        masked_case("small_masked", 96, 128, 2, 40)
+        sys.exit(0)
     if "--only-mixed" in sys.argv:
         small_case("small_mixed", 96, 128, "mixed", 3, 30, True, slim=True)     # dense + unrelated (noise matches) + shift in one batch
         sys.exit(0)
     if "--only-eval" not in sys.argv:
+        masked_case("small_masked", 96, 128, 2, 40)
         small_case("small_mixed", 96, 128, "mixed", 3, 30, True, slim=True)
         small_case("small_dense", 96, 128, "dense", 2, 0, True)
         small_case("small_shift", 96, 128, "shift", 1, 10, True)

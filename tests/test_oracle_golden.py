@@ -77,6 +77,32 @@ def test_mixed_batch_match_lists(golden_dir):
     _close(out["mconf"], g["mconf"], 1e-3)
 
 
+def test_masked_path_oracle_matches_reference(golden_dir):
+    """Optional padding masks (MegaDepth training collation; the product refuses them): the oracle's masked linear
+    attention and -1e9 logit fill reproduce the reference run (coarse features, integer match lists)."""
+    import torch.nn.functional as Fn
+    g = _load(golden_dir, "small_masked")
+    h, w, n, seed0, rnd = [int(v) for v in g["meta"]]
+    P = synth.make_state_dict(seed=7, randomize_norm=bool(rnd))
+    im0, im1 = synth.make_pairs(n, h, w, "dense", seed0)
+    hc, wc = h // 8, w // 8
+    m0, m1 = torch.zeros(n, hc, wc, dtype=torch.bool), torch.zeros(n, hc, wc, dtype=torch.bool)
+    for b in range(n):                                   # same valid regions as make_golden.padded_masks
+        m0[b, :hc - 2 - b, :wc - 3] = True
+        m1[b, :hc - 1, :wc - 4 - b] = True
+    im0 = im0 * Fn.interpolate(m0[:, None].float(), scale_factor=8, mode="nearest")
+    im1 = im1 * Fn.interpolate(m1[:, None].float(), scale_factor=8, mode="nearest")
+    cap = {}
+    with torch.no_grad():
+        out = O.forward(P, im0, im1, dict(coarse_thr=0.0), capture=cap, mask0=m0, mask1=m1)
+    _close(cap["coarse0"], g["coarse0"]); _close(cap["coarse1"], g["coarse1"])
+    for k in ("b_ids", "i_ids", "j_ids", "m_bids", "mkpts0_f", "mkpts1_f"):
+        assert np.array_equal(out[k].numpy(), g[k]), k
+    _close(out["mconf"], g["mconf"], 1e-3)
+    # (with coarse_thr = 0 the reference itself keeps matches on padded tokens: fully masked rows / columns have a
+    # uniform softmax, every entry ties for the mutual maximum and conf = 1/(L*S) > 0 — the real threshold removes them)
+
+
 def test_full_size_dense_pair(golden_dir):
     """480x640 single pair, dense regime: the reference's final match list is reproduced exactly."""
     g = _load(golden_dir, "full_dense_480x640")
