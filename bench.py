@@ -182,7 +182,7 @@ def run_ours(args):
     dev = [(a.to(device), b.to(device)) for a, b in host]
 
     from geoformer_b200.pipeline import MatchPipeline
-    pipe = MatchPipeline(model, depth=args.depth, device=device)
+    pipe = MatchPipeline(model, depth=args.depth, device=device, freeze_gc=True)
 
     done_t = []                    # host completion time of every batch (GF_BENCH_TRACE=1 prints the gaps to stderr)
 

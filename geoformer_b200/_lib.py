@@ -25,6 +25,8 @@ SIGNATURES = {
     "gf_conv_bf16": (I, [P, P, P, P, P, I, I, I, I, I, I, I, I, I, P]),
     "gf_stem_conv7x7_bf16": (I, [P, P, P, P, I, I, I, P]),
     "gf_upsample_add_bf16": (I, [P, P, P, I, I, I, I, I, I, P]),
+    "gf_conv_ref": (I, [P, P, P, P, P, I, I, I, I, I, I, I, I, P]),
+    "gf_upsample_add_ref": (I, [P, P, P, I, I, I, I, I, I, P]),
     "gf_add_posenc": (I, [P, P, P, I, L, I, P]),
     "gf_linattn_partial_floats": (L, [I, I, I, I]),
     "gf_linear_mixed": (I, [P, P, P, P, I, I, L, I, I, I, I, I, P, P, I, P, P, P, P, P]),

@@ -16,6 +16,23 @@ int gf_set_error(int code, const char* msg);
 
 static inline int gf_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Opt-in to > 48 KB of dynamic shared memory.  The attribute belongs to the (function, DEVICE) pair, so it is tracked per
+// device of the calling thread (one bit per device ordinal), not once per process.  Use at launch sites:
+//   GF_SMEM_OPTIN(kernel, bytes);     // returns GF_ERR_LAUNCH from the enclosing function on failure
+#include <atomic>
+#define GF_SMEM_OPTIN(kernel, bytes)                                                                         \
+  do {                                                                                                       \
+    static std::atomic<uint64_t> done__{0};                                                                  \
+    int dev__ = 0;                                                                                           \
+    cudaGetDevice(&dev__);                                                                                   \
+    const uint64_t bit__ = 1ull << (dev__ & 63);                                                             \
+    if (!(done__.load(std::memory_order_acquire) & bit__)) {                                                 \
+      if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)) != cudaSuccess) \
+        return gf_set_error(GF_ERR_LAUNCH, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");        \
+      done__.fetch_or(bit__, std::memory_order_release);                                                     \
+    }                                                                                                        \
+  } while (0)
+
 namespace gf {
 
 // TMA descriptor helpers (gemm_tc.cu).  K-major operand map: dims {k, rows, batches}, box {128 B, box_rows, 1},

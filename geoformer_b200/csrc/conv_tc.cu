@@ -377,13 +377,8 @@ template <int BN, int MT = 1>
 static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const ConvParams& p,
                        cudaStream_t stream) {
   using Cfg = ConvCfg<BN, MT>;
-  static bool attr = false;
   auto kern = conv3x3_tc_kernel<BN, MT>;
-  if (!attr) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem) != cudaSuccess)
-      return gf_set_error(GF_ERR_LAUNCH, "cudaFuncSetAttribute(conv smem) failed");
-    attr = true;
-  }
+  GF_SMEM_OPTIN(kern, Cfg::kSmem);
   const int tiles = p.batch * p.tiles_x * p.tiles_y;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, 192, Cfg::kSmem, stream>>>(tx, tw, ty, p);

@@ -317,8 +317,7 @@ extern "C" int gf_fine_match(const float* f0, const float* f1, int64_t m, int ww
   if (m == 0) return GF_OK;
   if (ww == 25 && c == 128) {
     constexpr int kSmem = 8 * (2 * 25 * 36 + 25 * 27 + 1) * 4;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(fine_match_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem); attr = true; }
+    GF_SMEM_OPTIN(fine_match_warp_kernel, kSmem);
     fine_match_warp_kernel<<<(unsigned)((m + 7) / 8), 256, kSmem, STREAM>>>(f0, f1, m, temperature, thr, sel, fi, fj, fconf, fine_matrix);
     g_launches++;
     GF_CHECK_LAUNCH();

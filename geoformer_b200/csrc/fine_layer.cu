@@ -439,12 +439,7 @@ extern "C" int gf_fine_layer(const float* x, const float* src, const void* wpack
   p.y = y; p.gamma1 = gamma1; p.beta1 = beta1; p.gamma2 = gamma2; p.beta2 = beta2;
   p.rows = rows; p.tiles = (int)((windows + fl::WIN - 1) / fl::WIN); p.cross = (src != x) ? 1 : 0;
   { const char* dbg = getenv("GF_FL_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(fl::fine_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fl::SMEM_BYTES) != cudaSuccess)
-      return gf_set_error(GF_ERR_LAUNCH, "cudaFuncSetAttribute(smem) failed");
-    attr_set = true;
-  }
+  GF_SMEM_OPTIN(fl::fine_layer_kernel, fl::SMEM_BYTES);
   const int grid = p.tiles < num_sms() ? p.tiles : num_sms();
   fl::fine_layer_kernel<<<grid, 320, fl::SMEM_BYTES, (cudaStream_t)stream>>>(tx, ts, tw, ty, p);
   g_launches++;

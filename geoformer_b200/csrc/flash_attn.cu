@@ -310,12 +310,7 @@ extern "C" int gf_geo_self_attention_tc(const void* q16, int ldq, const void* kg
   if ((rc = make_tmap(&tk, kg, 2, dim, s_pad, (int64_t)heads * n, dim, (int64_t)s_pad * dim, fa::kBK))) return rc;
   if ((rc = make_tmap(&tv, vt, 2, s_pad, dim, (int64_t)heads * n, s_pad, (int64_t)dim * s_pad, fa::kD))) return rc;
   if ((rc = make_out_tmap(&to, out, c, l, n, c, (int64_t)l * c))) return rc;
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(geo_flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::kSmem) != cudaSuccess)
-      return gf_set_error(GF_ERR_LAUNCH, "cudaFuncSetAttribute(flash smem) failed");
-    attr = true;
-  }
+  GF_SMEM_OPTIN(geo_flash_attn_kernel, fa::kSmem);
   geo_flash_attn_kernel<<<dim3(gf_cdiv(l, fa::kBQ), heads, n), fa::kThreads, fa::kSmem, (cudaStream_t)stream>>>(
       tq, tk, tv, to, out, anchor_cnt, n, l, heads, 1.f / sqrtf((float)dim));
   g_launches++;

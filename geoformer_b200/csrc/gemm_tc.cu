@@ -430,7 +430,8 @@ int init_driver(int device) {
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return gf_set_error(GF_ERR_LAUNCH, "cudaGetDeviceProperties failed");
   if (prop.major != 10) return gf_set_error(GF_ERR_DEVICE, "libgeoformer_sm100 needs an sm_100 (B200) device");
   g_num_sms = prop.multiProcessorCount;
-  if (cudaSetDevice(device) != cudaSuccess) return gf_set_error(GF_ERR_LAUNCH, "cudaSetDevice failed");
+  // the caller's current device is left as it is: every launch goes to the device of the stream it is given, and the
+  // per-device kernel attributes are set lazily at the launch sites (GF_SMEM_OPTIN)
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr)
@@ -490,13 +491,8 @@ template <int KIND, int BN, bool FULL, int CL, bool OUT16 = false>
 static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& ty,
                          const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
   auto kern = gemm_tc_kernel<KIND, BN, FULL, CL, OUT16>;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
-      return gf_set_error(GF_ERR_LAUNCH, "cudaFuncSetAttribute(smem) failed");
-    attr_set = true;
-  }
+  GF_SMEM_OPTIN(kern, Cfg::kSmemBytes);
   const int64_t groups = (int64_t)p.batches * gf_cdiv(gf_cdiv(p.M, kBM), CL) * p.tiles_n;
   if (groups == 0) return GF_OK;
   const int64_t max_groups = g_num_sms / CL;

@@ -413,8 +413,7 @@ extern "C" int gf_geo_self_attention(const float* q, int ldq, const float* k, in
                                      const int* anchor_cnt, int anchor_cap, gf_stream_t stream) {
   if (n <= 0 || l <= 0 || heads <= 0 || dim != 64) return gf_set_error(GF_ERR_ARG, "gf_geo_self_attention: dim must be 64");
   const size_t smem = (size_t)(kSA * kSA + 3 * kSA * kSAPad) * sizeof(float);
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(geo_self_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  GF_SMEM_OPTIN(geo_self_attention_kernel, smem);
   geo_self_attention_kernel<<<dim3(gf_cdiv(l, kSA), heads, n), 256, smem, STREAM>>>(
       q, ldq, k, ldk, v, ldv, out, l, heads, anchor_idx, anchor_cnt, anchor_cap, 1.f / sqrtf((float)dim));
   g_launches++;

@@ -533,8 +533,7 @@ static int linattn_reduce_impl(const T* K, int ldk, const T* V, int ldv, int n, 
     return gf_set_error(GF_ERR_ARG, "gf_linattn_reduce: dim must be 32, heads <= 32, 16-byte aligned rows");
   const int nchunks = gf_cdiv(s, kChunk);
   const size_t smem = (size_t)2 * 32 * heads * dim * sizeof(float);
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(linattn_partial_kernel<32, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+  GF_SMEM_OPTIN((linattn_partial_kernel<32, T>), 96 * 1024);
   if (smem > 96 * 1024) return gf_set_error(GF_ERR_ARG, "gf_linattn_reduce: shared memory");
   linattn_partial_kernel<32, T><<<dim3(nchunks, n), 32 * heads, smem, STREAM>>>(K, ldk, V, ldv, s, heads, 1.f / (float)s, partial);
   linattn_finalize_kernel<<<dim3(gf_cdiv(dim * dim + dim, 128), n * heads), 128, 0, STREAM>>>(partial, nchunks, heads, dim, KV, Ksum);
@@ -573,8 +572,7 @@ extern "C" int gf_linattn_reduce_f16(const void* K, int ldk, const void* V, int 
     chunk_tokens = chunk_tokens < kChunkMma ? kChunkMma : (chunk_tokens > 512 ? 512 : chunk_tokens);
     const int nchunks = gf_cdiv(s, chunk_tokens);
     constexpr int kSmem = 2 * 2 * 32 * kPitch;
-    static bool attr16 = false;
-    if (!attr16) { cudaFuncSetAttribute(linattn_partial_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem); attr16 = true; }
+    GF_SMEM_OPTIN(linattn_partial_mma_kernel, kSmem);
     linattn_partial_mma_kernel<<<dim3(nchunks, n), 256, kSmem, STREAM>>>((const __half*)K, ldk, (const __half*)V, ldv, s,
                                                                         chunk_tokens, 1.f / (float)s, partial);
     linattn_finalize_kernel<<<dim3(gf_cdiv(dim * dim + dim, 128), n * heads), 128, 0, STREAM>>>(partial, nchunks, heads, dim, KV, Ksum);
@@ -600,8 +598,7 @@ extern "C" int gf_linattn_window_f16(const void* Q, int ldq, const void* K, int 
     return gf_set_error(GF_ERR_ARG, "gf_linattn_window_f16: needs 25-token windows, 8 heads of dim 16");
   if (n_windows == 0) return GF_OK;
   const size_t smem = (size_t)(3 * 25 * 128 + 128) * sizeof(float);
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(linattn_window16_kernel<16, 25>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+  GF_SMEM_OPTIN((linattn_window16_kernel<16, 25>), 96 * 1024);
   linattn_window16_kernel<16, 25><<<(unsigned)n_windows, 128, smem, STREAM>>>((const __half*)Q, ldq, (const __half*)K, ldk,
                                                                             (const __half*)V, ldv, (__half*)out);
   g_launches++;
@@ -616,12 +613,8 @@ extern "C" int gf_linattn_window(const float* Q, int ldq, const float* K, int ld
     return gf_set_error(GF_ERR_ARG, "gf_linattn_window: dim must be 16");
   if (n_windows == 0) return GF_OK;
   const size_t smem = (size_t)(3 * tokens * c + c) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(linattn_window_kernel<16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(linattn_window_kernel<16, 25>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr = true;
-  }
+  GF_SMEM_OPTIN((linattn_window_kernel<16, 0>), 96 * 1024);
+  GF_SMEM_OPTIN((linattn_window_kernel<16, 25>), 96 * 1024);
   if (smem > 96 * 1024) return gf_set_error(GF_ERR_ARG, "gf_linattn_window: shared memory");
   if (tokens == 25) linattn_window_kernel<16, 25><<<(unsigned)n_windows, c, smem, STREAM>>>(Q, ldq, K, ldk, V, ldv, out, tokens, heads);
   else              linattn_window_kernel<16, 0><<<(unsigned)n_windows, c, smem, STREAM>>>(Q, ldq, K, ldk, V, ldv, out, tokens, heads);

@@ -322,13 +322,8 @@ static int coarse_match_fused_impl(const void* a3, const void* b3, int n, int l,
   int rc;
   if ((rc = make_tmap(&ta, a3, 2, c3, l, n, c3, (int64_t)l * c3, sf::kBM))) return rc;
   if ((rc = make_tmap(&tb, b3, 2, c3, s, n, c3, (int64_t)s * c3, sf::kBN))) return rc;
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(sim_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sf::kSmem) != cudaSuccess ||
-        cudaFuncSetAttribute(sim_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sf::kSmem) != cudaSuccess)
-      return gf_set_error(GF_ERR_LAUNCH, "cudaFuncSetAttribute(sim_fused smem) failed");
-    attr = true;
-  }
+  GF_SMEM_OPTIN(sim_fused_kernel<0>, sf::kSmem);
+  GF_SMEM_OPTIN(sim_fused_kernel<1>, sf::kSmem);
   SimFusedParams p{};
   p.n = n; p.l = l; p.s = s; p.kblocks = c3 / 64; p.tiles_m = tiles_m; p.tiles_n = tiles_n;
   p.scale2 = out_scale * 1.4426950408889634f;

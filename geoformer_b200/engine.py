@@ -1,20 +1,21 @@
 """Host-side orchestration of the GeoFormer hot path on one B200.
 
-Follows the stage order of the reference ``model/full_model.py:39-123``; every stage except the
-CNN backbone (cuDNN through torch for now) and the host RANSAC
-(``cv2.findHomography``, geo_module.py:48, kept for parity by construction) runs in hand-written
-sm_100a kernels reached through the C ABI (``geoformer_b200.ops``).
+Follows the stage order of the reference ``model/full_model.py:39-123``; every stage except the host RANSAC
+(``cv2.findHomography``, geo_module.py:48, kept for parity by construction; ``model.ransac = "gpu"`` moves it to
+csrc/ransac.cu) runs in hand-written sm_100a kernels reached through the C ABI (``geoformer_b200.ops``).  No cuDNN /
+cuBLAS call exists in this package: the backbone is csrc/conv_tc.cu (bf16, product) or csrc/conv_ref.cu (fp32 FFMA,
+accurate mode for the golden-match parity tests).
 """
 from __future__ import annotations
 
 import math
 import os
+import threading
 from concurrent.futures import ThreadPoolExecutor
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 
 from . import ops
 from .ops import EPI_ELU1, EPI_LN, EPI_RELU, EPI_TANH
@@ -111,9 +112,16 @@ class PackedWeights:
                     n2w=f32(sd[p + "norm2.weight"]), n2b=f32(sd[p + "norm2.bias"])))
             return layers
 
-        self.coarse = enc("loftr_coarse", 8)
-        self.geo = enc("geo_module.des_transformer", 4)
-        self.fine = enc("loftr_fine", 2)
+        def count(prefix: str) -> int:
+            idx = {int(k[len(prefix) + 8:].split(".")[0]) for k in sd if k.startswith(prefix + ".layers.")}
+            assert idx == set(range(len(idx))), f"{prefix}: non-contiguous layer indices {sorted(idx)}"
+            return len(idx)
+
+        # layer counts come from the state dict (== the config's layer_names; GeoFormer.__init__ builds the modules
+        # from the config and forward() asserts the lengths agree), not from hard-coded 8 / 4 / 2
+        self.coarse = enc("loftr_coarse", count("loftr_coarse"))
+        self.geo = enc("geo_module.des_transformer", count("geo_module.des_transformer"))
+        self.fine = enc("loftr_fine", count("loftr_fine"))
         for i, lw in enumerate(self.fine):
             p = f"loftr_fine.layers.{i}."
             if tuple(sd[p + "q_proj.weight"].shape) == (128, 128):
@@ -125,131 +133,112 @@ class PackedWeights:
                        wa=f32(wm[:, :cf]), wa16=f16(wm[:, :cf]), wb=f32(wm[:, cf:]),
                        bm=f32(sd["fine_preprocess.merge_feat.bias"]))
 
-        # backbone: BN folded, channels-last, tensor-core dtype (cuDNN through torch).  Channel counts that
-        # are not a multiple of `cpad_to` (the 196-wide stage) are zero-padded in the weights: padded output
-        # channels stay exactly 0 through ReLU / residual adds and padded input channels multiply zeros, so the
-        # result is unchanged while cuDNN keeps its aligned tensor-core kernels (no nhwcAddPadding passes).
-        cpad_to = int(os.environ.get("GF_BACKBONE_CPAD", "8"))
+        # backbone: BN folded into weights + bias.  bf16 (product): tap-major K-major packs for the tcgen05 implicit GEMM
+        # (csrc/conv_tc.cu); the 196-wide stage is zero-padded to 200 channels (16-byte rows for TMA): padded output
+        # channels stay exactly 0 through ReLU / residual adds and padded input channels multiply zero weights.
+        # fp32 (accurate mode): [taps][cin][cout] fp32 packs for the FFMA reference kernels (csrc/conv_ref.cu).
+        cpad_to = 8
         bsd = {k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")}
 
         def padc(c):
             return c if (c % cpad_to == 0 or c == 1) else (c + cpad_to - 1) // cpad_to * cpad_to
 
-        def conv(name, bn=None, pad_out=True):
+        def folded(name, bn=None):
             w = sd["backbone." + name + ".weight"]
-            b = None
-            if bn is not None:
-                w, b = _fold_bn(w, bsd, bn)
-            co, ci = w.shape[:2]
-            cop, cip = (padc(co) if pad_out else co), padc(ci)
-            if (cop, cip) != (co, ci):
-                wp = torch.zeros((cop, cip) + tuple(w.shape[2:]), dtype=w.dtype)
-                wp[:co, :ci] = w
-                w = wp
-                if b is not None:
-                    bp = torch.zeros(cop, dtype=b.dtype)
-                    bp[:co] = b
-                    b = bp
-            w = w.detach().to(device=device, dtype=backbone_dtype).contiguous(memory_format=torch.channels_last)
-            b = None if b is None else b.to(device=device, dtype=backbone_dtype)
-            return w, b
+            return _fold_bn(w, bsd, bn) if bn is not None else (w.float(), None)
 
-        bb = {"conv1": conv("conv1", "bn1")}
+        names = [("conv1", "bn1")]
         for li in (1, 2, 3):
             for bi in (0, 1):
                 p = f"layer{li}.{bi}"
-                bb[p + ".conv1"] = conv(p + ".conv1", p + ".bn1")
-                bb[p + ".conv2"] = conv(p + ".conv2", p + ".bn2")
+                names += [(p + ".conv1", p + ".bn1"), (p + ".conv2", p + ".bn2")]
                 if li > 1 and bi == 0:
-                    bb[p + ".down"] = conv(p + ".downsample.0", p + ".downsample.1")
-        bb["layer3_outconv"] = conv("layer3_outconv")
-        bb["layer2_outconv"] = conv("layer2_outconv")
-        bb["layer2_outconv2.0"] = conv("layer2_outconv2.0", "layer2_outconv2.1")
-        bb["layer2_outconv2.3"] = conv("layer2_outconv2.3")
-        bb["layer1_outconv"] = conv("layer1_outconv")
-        bb["layer1_outconv2.0"] = conv("layer1_outconv2.0", "layer1_outconv2.1")
-        bb["layer1_outconv2.3"] = conv("layer1_outconv2.3")
-        self.bb = bb
-        # tcgen05 implicit-GEMM path (bf16 only): tap-major packed weights for every 3x3 / stride-1 conv
-        self.bb_tc = None
-        if backbone_dtype == torch.bfloat16 and os.environ.get("GF_CONV", "tc") == "tc":
-            def tc(name, bn=None):
-                w = sd["backbone." + name + ".weight"]
-                b = None
-                if bn is not None:
-                    w, b = _fold_bn(w, bsd, bn)
-                return pack_conv3x3(w.float(), b, padc(w.shape[1]), padc(w.shape[0]), device)
+                    names.append((p + ".downsample.0", p + ".downsample.1"))
+        names += [("layer3_outconv", None), ("layer2_outconv", None), ("layer1_outconv", None),
+                  ("layer2_outconv2.0", "layer2_outconv2.1"), ("layer2_outconv2.3", None),
+                  ("layer1_outconv2.0", "layer1_outconv2.1"), ("layer1_outconv2.3", None)]
+        key = lambda name: name.replace(".downsample.0", ".down")
+        self.bb_tc = self.bb_ref = None
+        if backbone_dtype == torch.bfloat16:
             t = {}
-            for li in (1, 2, 3):
-                for bi in (0, 1):
-                    p = f"layer{li}.{bi}"
-                    t[p + ".conv1"] = tc(p + ".conv1", p + ".bn1")            # stride 2 in the entry block of layer 2 / 3
-                    t[p + ".conv2"] = tc(p + ".conv2", p + ".bn2")
-                    if li > 1 and bi == 0:
-                        t[p + ".down"] = tc(p + ".downsample.0", p + ".downsample.1")   # 1x1 / stride 2
-            for name in ("layer3_outconv", "layer2_outconv", "layer1_outconv"):        # 1x1 FPN laterals
-                t[name] = tc(name)
-            t["layer2_outconv2.0"] = tc("layer2_outconv2.0", "layer2_outconv2.1")
-            t["layer2_outconv2.3"] = tc("layer2_outconv2.3")
-            t["layer1_outconv2.0"] = tc("layer1_outconv2.0", "layer1_outconv2.1")
-            t["layer1_outconv2.3"] = tc("layer1_outconv2.3")
-            # stem: BN-folded 7x7 weights as [49 taps][128 channels]
-            w7, b7 = _fold_bn(sd["backbone.conv1.weight"], bsd, "bn1")
+            for name, bn in names[1:]:
+                w, b = folded(name, bn)
+                t[key(name)] = pack_conv3x3(w, b, padc(w.shape[1]), padc(w.shape[0]), device)
+            w7, b7 = folded("conv1", "bn1")                       # stem: [49 taps][128 channels]
             assert w7.shape == (128, 1, 7, 7)
             t["stem"] = (w7.reshape(128, 49).t().contiguous().to(device), b7.float().to(device))
             self.bb_tc = t
+        elif backbone_dtype == torch.float32:
+            r = {}
+            for name, bn in names:
+                w, b = folded(name, bn)
+                co, ci, kh, kw = w.shape
+                r[key(name)] = (w.permute(2, 3, 1, 0).reshape(kh * kw, ci, co).contiguous().to(device),
+                                None if b is None else b.to(device))
+            self.bb_ref = r
+        else:
+            raise ValueError(f"backbone dtype must be bfloat16 (product) or float32 (accurate), got {backbone_dtype}")
         self._pe: Dict[Tuple[int, int, int], torch.Tensor] = {}
+        self._pe_lock = threading.Lock()
 
     def pos_table(self, c: int, h: int, w: int) -> torch.Tensor:
         """[h*w, c] sinusoidal table in token-major layout.  Bug-compatible with the reference
         (position_encoding.py:28: ``-ln(1e4) / d_model // 2`` == -1.0, i.e. div_term[k] = exp(-2k))."""
         key = (c, h, w)
-        if key not in self._pe:
+        t = self._pe.get(key)
+        if t is not None:
+            return t
+        with self._pe_lock:                 # workers of MatchPipeline share this cache: build once, publish when complete
+            if key in self._pe:
+                return self._pe[key]
             ypos = torch.ones(h, w).cumsum(0).float().unsqueeze(0)
             xpos = torch.ones(h, w).cumsum(1).float().unsqueeze(0)
             div = torch.exp(torch.arange(0, c // 2, 2).float() * (-math.log(10000.0) / c // 2))[:, None, None]
             pe = torch.zeros(c, h, w)
             pe[0::4] = torch.sin(xpos * div); pe[1::4] = torch.cos(xpos * div)
             pe[2::4] = torch.sin(ypos * div); pe[3::4] = torch.cos(ypos * div)
-            self._pe[key] = pe.permute(1, 2, 0).reshape(h * w, c).contiguous().to(self.device)
-        return self._pe[key]
+            t = pe.permute(1, 2, 0).reshape(h * w, c).contiguous().to(self.device)      # pageable source: synchronous copy
+            torch.cuda.current_stream(self.device).synchronize()
+            self._pe[key] = t
+        return t
 
 
 # --------------------------------------------------------------------------------------------
-# backbone (resnet_fpn.py:100-118) — cuDNN, channels-last, BN folded
+# backbone (resnet_fpn.py:100-118)
 # --------------------------------------------------------------------------------------------
 def backbone_forward(pw: PackedWeights, img: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """[B,1,H,W] fp32 -> coarse NHWC [B,H/8,W/8,256] fp32, fine NHWC [B,H/2,W/2,128] fp32 (both contiguous)."""
-    if pw.bb_tc is not None:
-        return backbone_forward_tc(pw, img)
-    bb = pw.bb
-    x = img.to(pw.backbone_dtype).contiguous(memory_format=torch.channels_last)
+    """[B,1,H,W] fp32 -> coarse NHWC [B,H/8,W/8,256] fp32, fine NHWC [B,H/2,W/2,128] (bf16 in product mode, fp32 in
+    accurate mode); both contiguous."""
+    return backbone_forward_tc(pw, img) if pw.bb_tc is not None else backbone_forward_ref(pw, img)
 
-    def cv(name, t, stride=1, pad=1):
-        w, b = bb[name]
-        return F.conv2d(t, w, b, stride, pad)
 
-    def block(p, t, stride):
-        y = F.relu_(cv(p + ".conv1", t, stride))
-        y = cv(p + ".conv2", y)
-        if (p + ".down") in bb:
-            t = cv(p + ".down", t, stride, 0)
-        return F.relu_(y.add_(t))
+def backbone_forward_ref(pw: PackedWeights, img: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Accurate mode: the same network on the fp32 FFMA kernels of csrc/conv_ref.cu (NHWC fp32 throughout)."""
+    r = pw.bb_ref
 
-    x0 = F.relu_(cv("conv1", x, 2, 3))
-    x1 = block("layer1.1", block("layer1.0", x0, 1), 1)
-    x2 = block("layer2.1", block("layer2.0", x1, 2), 1)
-    x3 = block("layer3.1", block("layer3.0", x2, 2), 1)
-    x3o = cv("layer3_outconv", x3, 1, 0)
-    x2o = cv("layer2_outconv", x2, 1, 0)
-    x2o = x2o + F.interpolate(x3o, size=x2o.shape[2:], mode="bilinear", align_corners=True)
-    x2o = cv("layer2_outconv2.3", F.leaky_relu_(cv("layer2_outconv2.0", x2o), 0.01))
-    x1o = cv("layer1_outconv", x1, 1, 0)
-    x1o = x1o + F.interpolate(x2o, size=x1o.shape[2:], mode="bilinear", align_corners=True)
-    x1o = cv("layer1_outconv2.3", F.leaky_relu_(cv("layer1_outconv2.0", x1o), 0.01))
-    coarse = x3o.permute(0, 2, 3, 1).float().contiguous()
-    fine = x1o.permute(0, 2, 3, 1).float().contiguous()
-    return coarse, fine
+    def conv(name, t, act, residual=None, stride=1):
+        wt, b = r[name]
+        return ops.conv_ref(t, wt, b, residual, act, stride)
+
+    def block(p, a):
+        if (p + ".down") in r:
+            y = conv(p + ".conv1", a, 1, stride=2)
+            a = conv(p + ".down", a, 0, stride=2)
+        else:
+            y = conv(p + ".conv1", a, 1)
+        return conv(p + ".conv2", y, 1, residual=a)
+
+    b, _, h, w = img.shape
+    x0 = conv("conv1", img.contiguous().view(b, h, w, 1), 1, stride=2)        # [B,1,H,W] == NHWC with one channel
+    x1 = block("layer1.1", block("layer1.0", x0))
+    x2 = block("layer2.1", block("layer2.0", x1))
+    x3 = block("layer3.1", block("layer3.0", x2))
+    x3o = conv("layer3_outconv", x3, 0)
+    x2o = ops.upsample_add_ref(conv("layer2_outconv", x2, 0), x3o)
+    x2o = conv("layer2_outconv2.3", conv("layer2_outconv2.0", x2o, 2), 0)
+    x1o = ops.upsample_add_ref(conv("layer1_outconv", x1, 0), x2o)
+    x1o = conv("layer1_outconv2.3", conv("layer1_outconv2.0", x1o, 2), 0)
+    return x3o, x1o
 
 
 def backbone_forward_tc(pw: PackedWeights, img: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:

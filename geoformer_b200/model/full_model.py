@@ -9,13 +9,14 @@ There is no CPU path: calling ``forward`` with CPU tensors raises.
 from __future__ import annotations
 
 import os
+import threading
 from typing import Dict, Optional
 
 import torch
 import torch.nn as nn
 
-from .. import engine, ops
-from .geo_config import default_cfg
+from geoformer_b200 import engine, ops      # absolute: this file is also importable as top-level `model.full_model`
+from .geo_config import default_cfg         # relative: the wrapper mutates the `default_cfg` of whichever name it imported
 
 
 def _conv(cin, cout, k):
@@ -83,7 +84,8 @@ class _GeoModule(nn.Module):
         self.des_transformer = _Encoder(d, n_layers, nn.Tanh, final_norm=True)
 
 
-_BACKBONE_DTYPES = {"bf16": torch.bfloat16, "fp16": torch.float16, "tf32": torch.float32, "fp32": torch.float32}
+# "bf16": tcgen05 implicit-GEMM backbone (product); "fp32": FFMA reference kernels (accurate mode for parity runs)
+_BACKBONE_DTYPES = {"bf16": torch.bfloat16, "fp32": torch.float32}
 
 
 class GeoFormer(nn.Module):
@@ -106,6 +108,10 @@ class GeoFormer(nn.Module):
         self.materialize = False       # also return conf_matrix / dect_conf_matrix / fine_matrix (training-side keys)
         self.capture = False           # keep per-stage tensors in data['_stages'] (tests)
         self._packed: Optional[engine.PackedWeights] = None
+        self._pack_lock = threading.Lock()
+        if loftr_config["coarse"].get("temp_bug_fix", False):
+            # position_encoding.py:26-28: only the (default) bug-compatible table is implemented
+            raise NotImplementedError("geoformer_b200.GeoFormer: coarse.temp_bug_fix=True is not supported")
 
     # ---- parameter bookkeeping -----------------------------------------------------------------
     def load_state_dict(self, state_dict, *args, **kwargs):
@@ -120,14 +126,26 @@ class GeoFormer(nn.Module):
         return super()._apply(fn, *a, **kw)
 
     def _weights(self, device) -> engine.PackedWeights:
-        if self._packed is None or self._packed.device != device:
-            ops.ensure_init(device)
-            prec = self.backbone_precision
-            torch.backends.cudnn.allow_tf32 = prec != "fp32"
-            torch.backends.cudnn.benchmark = True
-            self._packed = engine.PackedWeights({k: v for k, v in self.state_dict().items()}, device,
-                                                _BACKBONE_DTYPES[prec])
-        return self._packed
+        """Kernel-ready weights, packed once per device.  Thread-safe: MatchPipeline's workers call forward concurrently
+        on their own streams, so packing happens under a lock and the packing stream is drained before the result is
+        published (the H2D copies and casts are ordered on the packing stream only)."""
+        pw = self._packed
+        if pw is not None and pw.device == device:
+            return pw
+        with self._pack_lock:
+            if self._packed is None or self._packed.device != device:
+                if self.backbone_precision not in _BACKBONE_DTYPES:
+                    raise ValueError(f"backbone_precision must be one of {sorted(_BACKBONE_DTYPES)}")
+                ops.ensure_init(device)
+                pw = engine.PackedWeights({k: v for k, v in self.state_dict().items()}, device,
+                                          _BACKBONE_DTYPES[self.backbone_precision])
+                cfg, gcfg = self.config, self.geo_cfg
+                for got, names, what in ((pw.coarse, cfg["coarse"]["layer_names"], "coarse"),
+                                         (pw.fine, cfg["fine"]["layer_names"], "fine"), (pw.geo, gcfg["layer_names"], "geo")):
+                    assert len(got) == len(names), f"{what}: {len(got)} layers in the state dict, {len(names)} in the config"
+                torch.cuda.current_stream(device).synchronize()
+                self._packed = pw
+            return self._packed
 
     # ---- forward ---------------------------------------------------------------------------------
     @torch.no_grad()
@@ -138,8 +156,18 @@ class GeoFormer(nn.Module):
             # would change the result, so refuse
             raise NotImplementedError("geoformer_b200.GeoFormer: padding masks (mask0/mask1) are not supported; "
                                       "the inference wrappers never pass them")
+        for k in ("scale0", "scale1", "dataset_name"):
+            # scale0/scale1 rescale mkpts*_c / the geo windows / mkpts*_f (coarse_matching.py:194, geo_module.py:39-42,
+            # fine_matching2.py:96-115); dataset_name forces a match during training (coarse_matching.py:182).  Both
+            # only exist in the training collations; ignoring them would silently change the result.
+            if data.get(k) is not None:
+                raise NotImplementedError(f"geoformer_b200.GeoFormer: data[{k!r}] is not supported (training-only key)")
         if not img0.is_cuda:
             raise RuntimeError("geoformer_b200.GeoFormer runs on CUDA (sm_100a) only; there is no CPU fallback")
+        with torch.cuda.device(img0.device):       # kernels launch on the tensors' device and its current stream
+            return self._forward(data, img0, img1)
+
+    def _forward(self, data, img0, img1):
         pw = self._weights(img0.device)
         cfg, gcfg = self.config, self.geo_cfg
         n = img0.shape[0]

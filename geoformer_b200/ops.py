@@ -218,6 +218,35 @@ def upsample_add(lateral: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def conv_ref(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], residual: Optional[torch.Tensor] = None,
+             act: int = 0, stride: int = 1) -> torch.Tensor:
+    """fp32 FFMA convolution (accurate mode): x NHWC fp32 [b,h,w,cin]; wt [k*k, cin, cout] fp32; pad = k // 2."""
+    _chk(x); _chk(wt)
+    assert x.is_contiguous() and wt.is_contiguous()
+    b, h, w, cin = x.shape
+    taps, cin_w, cout = wt.shape
+    k = {1: 1, 9: 3, 49: 7}[taps]
+    assert cin_w == cin
+    pad = k // 2
+    y = torch.empty((b, (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1, cout), device=x.device)
+    if residual is not None:
+        assert residual.shape == y.shape and residual.is_contiguous() and residual.dtype == torch.float32
+    _call("gf_conv_ref", x.data_ptr(), wt.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), b, h, w, cin, cout, k,
+          stride, act, _stream(), tag=f"[{cin}->{cout}@{h}x{w}k{k}s{stride}]")
+    return y
+
+
+def upsample_add_ref(lateral: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+    """fp32 version of upsample_add (accurate mode)."""
+    _chk(lateral); _chk(src)
+    assert lateral.is_contiguous() and src.is_contiguous()
+    b, h, w, c = lateral.shape
+    out = torch.empty_like(lateral)
+    _call("gf_upsample_add_ref", lateral.data_ptr(), src.data_ptr(), out.data_ptr(), b, h, w, src.shape[1], src.shape[2],
+          c, _stream())
+    return out
+
+
 def add_posenc(x: torch.Tensor, pe: torch.Tensor) -> torch.Tensor:
     n, l, c = x.shape
     assert x.is_contiguous() and pe.is_contiguous() and pe.shape == (l, c)

@@ -16,8 +16,11 @@ import torch
 
 
 class MatchPipeline:
-    def __init__(self, model, depth: int = 2, device: Optional[torch.device] = None):
+    def __init__(self, model, depth: int = 2, device: Optional[torch.device] = None, freeze_gc: bool = False):
+        """freeze_gc: move the objects alive at the first run() to the permanent GC generation (gc.freeze()) — a
+        process-wide side effect, hence opt-in; bench.py uses it (see run())."""
         self.model = model
+        self.freeze_gc = freeze_gc
         self.depth = max(1, int(depth))
         self.device = device or next(model.parameters()).device
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.depth)]
@@ -41,7 +44,9 @@ class MatchPipeline:
         main = torch.cuda.current_stream(self.device)
         for s in self.streams:
             s.wait_stream(main)
-        if not self._frozen:
+        with torch.cuda.device(self.device):
+            self.model._weights(self.device)          # pack once, before the workers start (they would race to do it)
+        if self.freeze_gc and not self._frozen:
             # a full (generation-2) collection walks every tracked object of the process (model, torch, cv2 ...) while
             # holding the GIL: measured as 200+ ms stalls of ALL launch threads.  Moving what is alive now to the
             # permanent generation keeps later collections proportional to the garbage the pipeline itself creates.

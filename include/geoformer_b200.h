@@ -41,7 +41,9 @@ typedef void* gf_stream_t;
 
 int gf_abi_version(void);
 const char* gf_last_error(void);
-/* Binds the calling thread's current device; verifies sm_100; resolves the TMA descriptor encoder. */
+/* Verifies that `device` is sm_100 and resolves the TMA descriptor encoder.  Does NOT change the calling thread's
+ * current device: every launch goes to the current device of the calling thread, which must own `stream` and the
+ * buffers (per-device kernel attributes are set lazily on first launch per device). */
 int gf_init(int device);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t gf_launch_count(void);
@@ -90,6 +92,15 @@ int gf_stem_conv7x7_bf16(const float* img, const float* wperm, const float* bias
 /* FPN top-down merge (resnet_fpn.py:108-115): out = lateral + bilinear(src -> h x w, align_corners=True); NHWC bf16 */
 int gf_upsample_add_bf16(const void* lateral, const void* src, void* out, int batch, int h, int w, int hs, int ws,
                          int c, gf_stream_t stream);
+/* fp32 FFMA versions of the backbone operators for the accurate mode (golden-match parity runs): the same layers
+ * (resnet_fpn.py:15-40, 58-118) on NHWC fp32, any channel count (the 1-channel 7x7 stem included).
+ *   gf_conv_ref: ksize 1 / 3 / 7 (pad = ksize / 2), stride 1 / 2; x [b,h,w,cin]; wt [ksize*ksize][cin][cout] fp32 (BN
+ *   folded); bias fp32 [cout] or null; residual / y [b,ho,wo,cout] with ho = (h + 2 pad - ksize) / stride + 1;
+ *   act as gf_conv_bf16.  gf_upsample_add_ref: as gf_upsample_add_bf16 on fp32. */
+int gf_conv_ref(const float* x, const float* wt, const float* bias, const float* residual, float* y, int batch, int h,
+                int w, int cin, int cout, int ksize, int stride, int act, gf_stream_t stream);
+int gf_upsample_add_ref(const float* lateral, const float* src, float* out, int batch, int h, int w, int hs, int ws,
+                        int c, gf_stream_t stream);
 
 /* out[n,l,c] = x[n,l,c] + pe[l,c]  (position_encoding.py:42 on the NHWC-flattened coarse map) */
 int gf_add_posenc(const float* x, const float* pe, float* out, int n, int64_t l, int c, gf_stream_t stream);

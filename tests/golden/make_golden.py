@@ -179,6 +179,66 @@ def full_case(name, h, w, regime, seed0, coarse_thr=0.0):
     print(name, "M_c", len(data["b_ids"]), "M_f", len(data["mkpts0_f"]))
 
 
+def textured_image_u8(h, w, seed):
+    """Smooth multi-octave texture as uint8 (stored inside the fixture: bicubic interpolation is not bit-reproducible
+    across CPUs, the stored bytes are)."""
+    g = torch.Generator().manual_seed(seed)
+    acc = torch.zeros(1, 1, h, w)
+    for k, amp in ((4, 1.0), (8, 0.8), (16, 0.6), (32, 0.5), (64, 0.35), (128, 0.25)):
+        z = torch.rand(1, 1, max(2, h // (512 // k) + 2), max(2, w // (512 // k) + 2), generator=g)
+        acc += amp * F.interpolate(z, size=(h, w), mode="bicubic", align_corners=True)
+    acc = (acc - acc.min()) / (acc.max() - acc.min())
+    return (acc[0, 0].numpy() * 255).round().astype(np.uint8)
+
+
+def full_stage_case(name, h, w, regime, seed0, wseed, randomize_norm, tok_stride=24):
+    """Full-size (480x640) case with stage features for the PRODUCT-mode parity tests: match lists in full, features
+    subsampled (every `tok_stride`-th token; every 4th x 5th coarse cell of the CNN map) to keep the fixture ~1 MB.
+    regime 'shift' uses synth.make_pairs (rebuilt on the GPU box); 'warp' stores its uint8 images in the fixture:
+    image1 = cv2.warpPerspective(image0, H_gt)."""
+    import cv2
+    sd = synth.make_state_dict(seed=wseed, randomize_norm=randomize_norm)
+    model = build_reference(sd, 0.0)
+    extra = {}
+    if regime == "warp":
+        im0u = textured_image_u8(h, w, seed0)
+        src = np.float32([[0, 0], [w - 1, 0], [w - 1, h - 1], [0, h - 1]])
+        dst = src + np.float32([[12, 7], [-9, 10], [-14, -8], [10, -11]])
+        h_gt = cv2.getPerspectiveTransform(src, dst)
+        im1u = cv2.warpPerspective(im0u, h_gt, (w, h), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT)
+        im0 = torch.from_numpy(im0u).float().div(255)[None, None]
+        im1 = torch.from_numpy(im1u).float().div(255)[None, None]
+        extra.update(image0_u8=im0u, image1_u8=im1u, h_gt=h_gt)
+    else:
+        im0, im1 = synth.make_pairs(1, h, w, regime, seed0)
+    first = {}
+    orig = model.coarse_matching.forward
+    calls = []
+
+    def spy(f0, f1, data, **kw):                       # first-pass match list (overwritten by the second call)
+        r = orig(f0, f1, data, **kw)
+        calls.append({k: data[k].clone() for k in ("b_ids", "i_ids", "j_ids", "mconf")})
+        return r
+    model.coarse_matching.forward = spy
+    data, cap = run_reference(model, im0, im1)
+    fc, _ = cap["backbone"][0]
+    c0, c1 = cap["loftr_coarse"][0]
+    g0, g1 = cap["geo_module"][0]
+    out = dict(
+        meta=np.array([h, w, 1, seed0, int(randomize_norm)]), wseed=np.array(wseed), regime=np.array(regime),
+        tok_stride=np.array(tok_stride),
+        cnn_c_sub=fc[:, :, ::4, ::5], coarse0_sub=c0[0, ::tok_stride], coarse1_sub=c1[0, ::tok_stride],
+        geo0_sub=g0[0, ::tok_stride], geo1_sub=g1[0, ::tok_stride],
+        first_i=calls[0]["i_ids"].to(torch.int32), first_j=calls[0]["j_ids"].to(torch.int32), first_conf=calls[0]["mconf"],
+        i_ids=data["i_ids"].to(torch.int32), j_ids=data["j_ids"].to(torch.int32), mconf_c=calls[1]["mconf"],
+        mkpts0_f=data["mkpts0_f"].to(torch.int16), mkpts1_f=data["mkpts1_f"].to(torch.int16), mconf=data["mconf"],
+        dect_conf_max=data["dect_conf_matrix"].max(), conf_max=data["conf_matrix"].max(), **extra)
+    assert torch.equal(data["mkpts0_f"].to(torch.int16).float(), data["mkpts0_f"])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **npify(out))
+    print(name, "first", len(calls[0]["i_ids"]), "M_c", len(data["b_ids"]), "M_f", len(data["mkpts0_f"]),
+          "dect max", float(data["dect_conf_matrix"].max()), os.path.getsize(os.path.join(HERE, name + ".npz")) // 1024, "KB")
+
+
 def eval_and_ingest_case():
     """Golden vectors for the 'next' rows: downstream evaluation helpers (hpatches_helper.cal_error_auc /
     cal_reproj_dists, fire_helper.compute_auc) and the image ingest (data_io.resize_im + cv2.resize + to_tensor)."""
@@ -220,6 +280,11 @@ if __name__ == "__main__":
     if "--only-masked" in sys.argv:
         masked_case("small_masked", 96, 128, 2, 40)
         sys.exit(0)
+    if "--only-stage" in sys.argv:
+        full_stage_case("full_shift_480x640", 480, 640, "shift", 10, 0, False)            # flat confidences (default norms)
+        full_stage_case("full_shift_rn_480x640", 480, 640, "shift", 10, 7, True)          # peaky confidences
+        full_stage_case("full_warp_rn_480x640", 480, 640, "warp", 3, 7, True)             # cv2.warpPerspective pair
+        sys.exit(0)
     if "--only-mixed" in sys.argv:
         small_case("small_mixed", 96, 128, "mixed", 3, 30, True, slim=True)     # dense + unrelated (noise matches) + shift in one batch
         sys.exit(0)
@@ -231,4 +296,7 @@ if __name__ == "__main__":
         small_case("small_rect_thr", 64, 96, "dense", 1, 20, False, coarse_thr=0.2)   # zero-match corner
     if "--only-eval" not in sys.argv:
         full_case("full_dense_480x640", 480, 640, "dense", 0)
+        full_stage_case("full_shift_480x640", 480, 640, "shift", 10, 0, False)
+        full_stage_case("full_shift_rn_480x640", 480, 640, "shift", 10, 7, True)
+        full_stage_case("full_warp_rn_480x640", 480, 640, "warp", 3, 7, True)
     eval_and_ingest_case()

@@ -176,27 +176,29 @@ def test_full_size_dense_pair_corner_error(golden_dir):
     assert abs(e_gpu - e_ref) <= 0.1, (e_gpu, e_ref)
 
 
-def test_backbone_tcgen05_vs_cudnn_and_fp32():
-    """The tcgen05 implicit-GEMM backbone (bf16) against cuDNN bf16 and cuDNN fp32 on the same folded weights:
-    bf16 storage of 20 chained conv layers gives ~1e-2 relative differences; both bf16 paths must sit at the same
-    distance from the fp32 result."""
+def test_backbone_fp32_reference_kernels_and_tcgen05_vs_oracle():
+    """Both backbones of this library against the CPU oracle (resnet_fpn.py restated with F.conv2d / BatchNorm):
+    the fp32 FFMA kernels (accurate mode) to fp32 round-off, the bf16 tcgen05 implicit-GEMM path (product) within the
+    bf16 storage error of ~20 chained layers (3e-2 of the feature range, measured ~1e-2)."""
     from geoformer_b200 import engine, ops
     dev = torch.device("cuda:0")
     ops.ensure_init(dev)
     sd = synth.make_state_dict(7, True)
-    img = torch.cat(synth.make_pairs(2, 96, 128, "dense", 3), 0).to(dev)
-    torch.backends.cudnn.allow_tf32 = False
-    ref_c, ref_f = engine.backbone_forward(engine.PackedWeights(sd, dev, torch.float32), img)
-    os.environ["GF_CONV"] = "cudnn"
-    cd_c, cd_f = engine.backbone_forward(engine.PackedWeights(sd, dev, torch.bfloat16), img)
-    os.environ["GF_CONV"] = "tc"
+    img = torch.cat(synth.make_pairs(2, 96, 128, "dense", 3), 0)
+    with torch.no_grad():
+        want_c, want_f = O.backbone(sd, img)                                  # NCHW fp32
+    want_c, want_f = want_c.permute(0, 2, 3, 1), want_f.permute(0, 2, 3, 1)
+    rel = lambda a, b: ((a.float().cpu() - b).abs().max() / b.abs().max()).item()
+    ref_c, ref_f = engine.backbone_forward(engine.PackedWeights(sd, dev, torch.float32), img.to(dev))
+    assert ref_c.shape == want_c.shape and ref_f.shape == want_f.shape and ref_f.dtype == torch.float32
+    assert rel(ref_c, want_c) <= 2e-5 and rel(ref_f, want_f) <= 2e-5, (rel(ref_c, want_c), rel(ref_f, want_f))
     pw = engine.PackedWeights(sd, dev, torch.bfloat16)
-    assert pw.bb_tc is not None
-    tc_c, tc_f = engine.backbone_forward(pw, img)
-    rel = lambda a, b: ((a - b).abs().max() / b.abs().max()).item()
-    assert tc_c.shape == ref_c.shape and tc_f.shape == ref_f.shape
-    e_tc, e_cd = max(rel(tc_c, ref_c), rel(tc_f, ref_f)), max(rel(cd_c, ref_c), rel(cd_f, ref_f))
-    assert e_tc <= 3e-2 and e_tc <= 2.0 * e_cd + 5e-3, (e_tc, e_cd)
+    assert pw.bb_tc is not None and pw.bb_ref is None
+    tc_c, tc_f = engine.backbone_forward(pw, img.to(dev))
+    assert tc_c.shape == want_c.shape and tc_f.shape == want_f.shape and tc_f.dtype == torch.bfloat16
+    e_c, e_f = rel(tc_c, want_c), rel(tc_f, want_f)
+    print("bf16 tcgen05 backbone vs fp32 oracle: coarse", e_c, "fine", e_f)
+    assert e_c <= 3e-2 and e_f <= 3e-2, (e_c, e_f)
 
 
 @pytest.mark.parametrize("hw", [(768, 768), (840, 840)])

@@ -10,6 +10,7 @@ import torch
 
 from geoformer_b200 import synth
 from oracle import geoformer_oracle as O
+from tests.util import stage_case_inputs
 
 
 def _load(golden_dir, name):
@@ -116,6 +117,29 @@ def test_full_size_dense_pair(golden_dir):
     _close(cap["coarse0"][0, :4, :8], g["coarse0_head"]); _close(cap["geo0"][0, :4, :8], g["geo0_head"])
     # outputs are even integer pixel coordinates
     assert (out["mkpts0_f"] % 2 == 0).all()
+
+
+@pytest.mark.parametrize("name", ["full_shift_480x640", "full_shift_rn_480x640", "full_warp_rn_480x640"])
+def test_full_size_stage_cases(golden_dir, name):
+    """480x640 pairs with a NON-identity geometry (translation by (16, 8) px; cv2.warpPerspective pair), flat and peaky
+    confidence regimes: the oracle reproduces the reference's first-pass and final match lists exactly and its
+    (subsampled) stage features to fp32 round-off.  These fixtures pin the product-mode GPU tests."""
+    g = _load(golden_dir, name)
+    P, im0, im1 = stage_case_inputs(g)
+    cap = {}
+    with torch.no_grad():
+        out = O.forward(P, im0, im1, dict(coarse_thr=0.0), capture=cap)
+    ts = int(g["tok_stride"])
+    _close(torch.cat([cap["cnn_c0"], cap["cnn_c1"]], 0)[:, :, ::4, ::5], g["cnn_c_sub"])
+    _close(cap["coarse0"][0, ::ts], g["coarse0_sub"]); _close(cap["coarse1"][0, ::ts], g["coarse1_sub"])
+    _close(cap["geo0"][0, ::ts], g["geo0_sub"]); _close(cap["geo1"][0, ::ts], g["geo1_sub"])
+    assert np.array_equal(out["first_i_ids"].numpy().astype(np.int32), g["first_i"])
+    assert np.array_equal(out["first_j_ids"].numpy().astype(np.int32), g["first_j"])
+    assert np.array_equal(out["i_ids"].numpy().astype(np.int32), g["i_ids"])
+    assert np.array_equal(out["j_ids"].numpy().astype(np.int32), g["j_ids"])
+    assert np.array_equal(out["mkpts0_f"].numpy().astype(np.int16), g["mkpts0_f"])
+    assert np.array_equal(out["mkpts1_f"].numpy().astype(np.int16), g["mkpts1_f"])
+    _close(out["mconf"], g["mconf"], 1e-3)
 
 
 def test_position_encoding_bug_compat():
