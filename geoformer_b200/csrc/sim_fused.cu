@@ -10,9 +10,15 @@
 //   then mnn_from_best_kernel applies threshold / border / mutual check on vectors.
 // Nothing of size L x S touches HBM: per call the kernels read the packed operands (2 x n*L*3C fp16) and write
 // O(n*(L+S)*tiles) partials, so the similarity contraction is tensor-bound instead of bound by a 1.5 GB fp32 store.
-// Tie caveat (documented in DESIGN.md): among exactly equal row maxima the smallest j is taken BEFORE the column check,
-// whereas the reference takes the first j that also passes it; the materialised path (gf_mnn_select) keeps the
-// reference order bit-exactly and is what the parity tests of the MNN semantics use.
+//
+// Exact tie semantics.  The reference's match of row i is the FIRST j with conf_ij == rowmax_i AND conf_ij == colmax_j AND
+// the border test (coarse_matching.py:176-188: mask.max(dim=2) returns the first True).  Pass 1 keeps (rowmax_i, smallest
+// j attaining it); that j is the reference's answer unless the row maximum is attained more than once and the smallest
+// such j fails the column / border test.  Pass 1 therefore also raises a per-row tie flag (an equal value seen inside the
+// thread's chunk scan, or an equal confidence returned by the 64-bit atomicMax when column tiles merge).  Rows that are
+// flagged AND rejected are re-scanned exactly by pass 2 (MODE 2: the same tile recomputed bit-identically, every j tested
+// against rowmax_i / colmax_j / border, smallest j kept with atomicMin).  Pass 2 exits at once when no row needs it
+// (the normal case: a few microseconds) and only visits the 128-row blocks that contain such rows.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -38,6 +44,11 @@ struct SimFusedParams {
   float2* rowp; float2* colp;   // pass 0 outputs
   const float* row_m2; const float* row_inv; const float* col_m2; const float* col_inv;   // pass 1 inputs
   unsigned long long* row_best; unsigned* col_best;                                        // pass 1 outputs
+  int* row_tie;                 // pass 1 output: row maximum attained more than once (may be a stale over-approximation)
+  // pass 2 (exact re-scan of tied + rejected rows)
+  const int* rescan_cnt;        // [n * tiles_m + 1]: flagged rows per 128-row block; last entry = total
+  int* rescan_j;                // [n * l]: INT_MAX for rows to re-scan (atomicMin target), -2 otherwise
+  int border, h0c, w0c, h1c, w1c;
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -60,6 +71,14 @@ sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.n * p.tiles_m * p.tiles_n;
+  if constexpr (MODE == 2) {
+    if (p.rescan_cnt[p.n * p.tiles_m] == 0) return;        // nothing to re-scan (uniform over the grid)
+  }
+  // MODE 2 visits only the 128-row blocks that hold a row to re-scan (all three roles skip the same tiles)
+  auto skip_tile = [&](int t) -> bool {
+    if constexpr (MODE == 2) return p.rescan_cnt[t / p.tiles_n] == 0;
+    else return false;
+  };
 
   if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmB); }
   if (warp == 1) {
@@ -80,6 +99,7 @@ sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        if (skip_tile(t)) continue;
         const int n_blk = t % p.tiles_n, rest = t / p.tiles_n;
         const int m_blk = rest % p.tiles_m, batch = rest / p.tiles_m;
         for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -98,6 +118,7 @@ sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        if (skip_tile(t)) continue;
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kBN;
@@ -121,6 +142,7 @@ sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* box = staging + (warp - 2) * 4096;          // this warp's 32 x 32 fp32 transpose box (128B-swizzled rows)
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      if (skip_tile(t)) continue;
       const int n_blk = t % p.tiles_n, rest = t / p.tiles_n;
       const int m_blk = rest % p.tiles_m, batch = rest / p.tiles_m;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
@@ -133,8 +155,18 @@ sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float rm = -INFINITY, rsum = 0.f;                  // MODE 0: running row (max, sum)
       float r_m2 = 0.f, r_inv = 0.f;                     // MODE 1: final row stats
       float best = 0.f; int best_j = 0;
-      if constexpr (MODE == 1) {
+      bool tied = false;                                 // MODE 1: the running row maximum was seen more than once
+      unsigned want_bits = 0u; int min_j = 0x7fffffff;   // MODE 2: row maximum to look for (0 = row not re-scanned), first hit
+      bool row_border_ok = true;
+      if constexpr (MODE >= 1) {
         if (row_ok) { r_m2 = p.row_m2[(int64_t)batch * p.l + row]; r_inv = p.row_inv[(int64_t)batch * p.l + row]; }
+      }
+      if constexpr (MODE == 2) {
+        if (row_ok && p.rescan_j[(int64_t)batch * p.l + row] != -2) want_bits = (unsigned)(p.row_best[(int64_t)batch * p.l + row] >> 32);
+        if (p.border > 0) {
+          const int r0 = row / p.w0c, c0 = row % p.w0c;
+          row_border_ok = r0 >= p.border && r0 < p.h0c - p.border && c0 >= p.border && c0 < p.w0c - p.border;
+        }
       }
       float v[32];
       if (nch > 0) ptx::tmem_ld_32x32(t_row, v);
@@ -143,9 +175,19 @@ sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::tmem_ld_wait();
         const int gc = col0 + ci * 32;
         const bool full = gc + 32 <= p.s;
-        float c_m2 = 0.f, c_inv = 0.f;                   // MODE 1: stats of column gc + lane
-        if constexpr (MODE == 1) {
+        float c_m2 = 0.f, c_inv = 0.f;                   // MODE 1 / 2: stats of column gc + lane
+        unsigned c_best = 0u;                            // MODE 2: column maximum of column gc + lane (0 if its border test fails)
+        if constexpr (MODE >= 1) {
           if (gc + lane < p.s) { c_m2 = p.col_m2[(int64_t)batch * p.s + gc + lane]; c_inv = p.col_inv[(int64_t)batch * p.s + gc + lane]; }
+        }
+        if constexpr (MODE == 2) {
+          if (gc + lane < p.s) {
+            c_best = p.col_best[(int64_t)batch * p.s + gc + lane];
+            if (p.border > 0) {
+              const int r1 = (gc + lane) / p.w1c, c1 = (gc + lane) % p.w1c;
+              if (!(r1 >= p.border && r1 < p.h1c - p.border && c1 >= p.border && c1 < p.w1c - p.border)) c_best = 0u;
+            }
+          }
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= p.scale2;
@@ -170,15 +212,28 @@ sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = -INFINITY;      // rows beyond L must not enter the column statistics
           }
-        } else {
+        } else if constexpr (MODE == 1) {
           // ---- conf = softmax_row * softmax_col with one exponential: 2^(2x - rmax - cmax_j) * rinv * cinv_j
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float cmj = __shfl_sync(0xffffffffu, c_m2, j), cij = __shfl_sync(0xffffffffu, c_inv, j);
             const float cf = row_ok ? ex2f(fmaf(2.f, v[j], -r_m2 - cmj)) * (r_inv * cij) : 0.f;   // -inf logits -> 0
             v[j] = cf;
+            tied = (cf == best) ? true : ((cf > best) ? false : tied);
             if (cf > best) { best = cf; best_j = gc + j; }     // strict >: the first j wins inside this row
           }
+        } else {
+          // ---- exact re-scan: the same expression as pass 1 (bit-identical), every j tested against both maxima
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float cmj = __shfl_sync(0xffffffffu, c_m2, j), cij = __shfl_sync(0xffffffffu, c_inv, j);
+            const unsigned cbj = __shfl_sync(0xffffffffu, c_best, j);
+            const float cf = row_ok ? ex2f(fmaf(2.f, v[j], -r_m2 - cmj)) * (r_inv * cij) : 0.f;
+            const unsigned bits = __float_as_uint(cf);
+            if (want_bits != 0u && bits == want_bits && bits == cbj && row_border_ok && gc + j < min_j) min_j = gc + j;
+          }
+          if (ci + 1 < nch) ptx::tmem_ld_32x32(t_row + (ci + 1) * 32, v);
+          continue;
         }
         // ---- transpose through the swizzled box: lane <- column (gc + lane) over the warp's 32 rows
 #pragma unroll
@@ -211,9 +266,15 @@ sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (row_ok) {
         if constexpr (MODE == 0) {
           p.rowp[((int64_t)batch * p.l + row) * (p.tiles_n * 2) + n_blk * 2 + half] = make_float2(rm, rsum);
-        } else if (best > 0.f) {
-          const unsigned long long key = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)best_j);
-          atomicMax(&p.row_best[(int64_t)batch * p.l + row], key);
+        } else if constexpr (MODE == 1) {
+          if (best > 0.f) {
+            const unsigned long long key = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)best_j);
+            const unsigned long long old = atomicMax(&p.row_best[(int64_t)batch * p.l + row], key);
+            // an equal confidence already stored by another column tile == a tie across tiles
+            if (tied || (unsigned)(old >> 32) == __float_as_uint(best)) p.row_tie[(int64_t)batch * p.l + row] = 1;
+          }
+        } else if (min_j != 0x7fffffff) {
+          atomicMin(&p.rescan_j[(int64_t)batch * p.l + row], min_j);
         }
       }
       ptx::tc_fence_before();
@@ -245,10 +306,12 @@ __global__ void merge_stats2_kernel(const float2* __restrict__ in, int64_t elems
   out_inv[e] = 1.f / sum;
 }
 
-// threshold + border + mutual check on the per-row / per-column bests (coarse_matching.py:161-188)
+// threshold + border + mutual check on the per-row / per-column bests (coarse_matching.py:161-188).  Rows whose maximum
+// is tied and whose smallest-j candidate is rejected are queued for the exact re-scan (see the header comment).
 __global__ void mnn_from_best_kernel(const unsigned long long* __restrict__ row_best, const unsigned* __restrict__ col_best,
-                                     int n, int l, int s, float thr, int border, int h0c, int w0c, int h1c, int w1c,
-                                     int* __restrict__ match_j, float* __restrict__ match_conf) {
+                                     const int* __restrict__ row_tie, int n, int l, int s, float thr, int border, int h0c,
+                                     int w0c, int h1c, int w1c, int tiles_m, int* __restrict__ match_j,
+                                     float* __restrict__ match_conf, int* __restrict__ rescan_j, int* __restrict__ rescan_cnt) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)n * l) return;
   const int b = (int)(idx / l), i = (int)(idx - (int64_t)b * l);
@@ -256,7 +319,8 @@ __global__ void mnn_from_best_kernel(const unsigned long long* __restrict__ row_
   const unsigned cbits = (unsigned)(key >> 32);
   const int j = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
   const float conf = __uint_as_float(cbits);
-  bool ok = key != 0ull && conf > thr && j >= 0 && j < s && col_best[(int64_t)b * s + j] == cbits;
+  const bool cand = key != 0ull && conf > thr && j >= 0 && j < s;
+  bool ok = cand && col_best[(int64_t)b * s + j] == cbits;
   if (ok && border > 0) {
     const int r0 = i / w0c, c0 = i % w0c, r1 = j / w1c, c1 = j % w1c;
     ok = r0 >= border && r0 < h0c - border && c0 >= border && c0 < w0c - border &&
@@ -264,6 +328,22 @@ __global__ void mnn_from_best_kernel(const unsigned long long* __restrict__ row_
   }
   match_j[idx] = ok ? j : -1;
   match_conf[idx] = ok ? conf : 0.f;
+  const bool rescan = cand && !ok && row_tie[idx] != 0;
+  rescan_j[idx] = rescan ? 0x7fffffff : -2;
+  if (rescan) { atomicAdd(&rescan_cnt[b * tiles_m + i / sf::kBM], 1); atomicAdd(&rescan_cnt[n * tiles_m], 1); }
+}
+
+// after pass 2: re-scanned rows take the first j that passed every test (or stay unmatched)
+__global__ void mnn_apply_rescan_kernel(const unsigned long long* __restrict__ row_best, const int* __restrict__ rescan_j,
+                                        const int* __restrict__ rescan_cnt, int64_t rows, int total_idx,
+                                        int* __restrict__ match_j, float* __restrict__ match_conf) {
+  if (rescan_cnt[total_idx] == 0) return;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows) return;
+  const int j = rescan_j[idx];
+  if (j == -2 || j == 0x7fffffff) return;
+  match_j[idx] = j;
+  match_conf[idx] = __uint_as_float((unsigned)(row_best[idx] >> 32));
 }
 
 }  // namespace gf
@@ -279,6 +359,7 @@ extern "C" int64_t gf_coarse_match_fused_workspace_bytes(int n, int l, int s) {
   b += align_up((int64_t)n * tiles_m * 4 * s * 8, 256);        // colp
   b += 2 * align_up((int64_t)n * l * 4, 256) + 2 * align_up((int64_t)n * s * 4, 256);   // row/col m2 + inv
   b += align_up((int64_t)n * l * 8, 256) + align_up((int64_t)n * s * 4, 256);           // row_best, col_best
+  b += 2 * align_up((int64_t)n * l * 4, 256) + align_up(((int64_t)n * tiles_m + 1) * 4, 256);   // row_tie, rescan_j, rescan_cnt
   return b;
 }
 
@@ -316,19 +397,27 @@ static int coarse_match_fused_impl(const void* a3, const void* b3, int n, int l,
   float* row_inv = (float*)w; w += align_up((int64_t)n * l * 4, 256);
   float* col_m2 = (float*)w; w += align_up((int64_t)n * s * 4, 256);
   float* col_inv = (float*)w; w += align_up((int64_t)n * s * 4, 256);
+  // [row_best | col_best | row_tie | rescan_cnt] are contiguous: one memset clears them
+  uint8_t* zero0 = w;
   unsigned long long* row_best = (unsigned long long*)w; w += align_up((int64_t)n * l * 8, 256);
-  unsigned* col_best = (unsigned*)w;
+  unsigned* col_best = (unsigned*)w; w += align_up((int64_t)n * s * 4, 256);
+  int* row_tie = (int*)w; w += align_up((int64_t)n * l * 4, 256);
+  int* rescan_cnt = (int*)w; w += align_up(((int64_t)n * tiles_m + 1) * 4, 256);
+  const size_t zero_bytes = (size_t)(w - zero0);
+  int* rescan_j = (int*)w;
   CUtensorMap ta, tb;
   int rc;
   if ((rc = make_tmap(&ta, a3, 2, c3, l, n, c3, (int64_t)l * c3, sf::kBM))) return rc;
   if ((rc = make_tmap(&tb, b3, 2, c3, s, n, c3, (int64_t)s * c3, sf::kBN))) return rc;
   GF_SMEM_OPTIN(sim_fused_kernel<0>, sf::kSmem);
   GF_SMEM_OPTIN(sim_fused_kernel<1>, sf::kSmem);
+  GF_SMEM_OPTIN(sim_fused_kernel<2>, sf::kSmem);
   SimFusedParams p{};
   p.n = n; p.l = l; p.s = s; p.kblocks = c3 / 64; p.tiles_m = tiles_m; p.tiles_n = tiles_n;
   p.scale2 = out_scale * 1.4426950408889634f;
   p.rowp = rowp; p.colp = colp; p.row_m2 = row_m2; p.row_inv = row_inv; p.col_m2 = col_m2; p.col_inv = col_inv;
-  p.row_best = row_best; p.col_best = col_best;
+  p.row_best = row_best; p.col_best = col_best; p.row_tie = row_tie; p.rescan_cnt = rescan_cnt; p.rescan_j = rescan_j;
+  p.border = border; p.h0c = h0c; p.w0c = w0c; p.h1c = h1c; p.w1c = w1c;
   const int64_t tiles = (int64_t)n * tiles_m * tiles_n;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   if (only_pass == 0) { sim_fused_kernel<0><<<grid, sf::kThreads, sf::kSmem, st>>>(ta, tb, p); g_launches++; GF_CHECK_LAUNCH(); return GF_OK; }
@@ -338,12 +427,15 @@ static int coarse_match_fused_impl(const void* a3, const void* b3, int n, int l,
                                                                    row_m2, row_inv);
   merge_stats2_kernel<<<gf_cdiv((int64_t)n * s, 256), 256, 0, st>>>(colp, (int64_t)n * s, tiles_m * 4, 1, s, s,
                                                                    (int64_t)tiles_m * 4 * s, col_m2, col_inv);
-  cudaMemsetAsync(row_best, 0, (size_t)n * l * 8, st);
-  cudaMemsetAsync(col_best, 0, (size_t)n * s * 4, st);
+  cudaMemsetAsync(zero0, 0, zero_bytes, st);
   sim_fused_kernel<1><<<grid, sf::kThreads, sf::kSmem, st>>>(ta, tb, p);
-  mnn_from_best_kernel<<<gf_cdiv((int64_t)n * l, 256), 256, 0, st>>>(row_best, col_best, n, l, s, thr, border, h0c, w0c, h1c, w1c,
-                                                                    match_j, match_conf);
-  g_launches += 5;
+  mnn_from_best_kernel<<<gf_cdiv((int64_t)n * l, 256), 256, 0, st>>>(row_best, col_best, row_tie, n, l, s, thr, border, h0c, w0c,
+                                                                    h1c, w1c, tiles_m, match_j, match_conf, rescan_j, rescan_cnt);
+  // exact tie handling: both kernels return at once unless a tied row maximum was rejected (see the header comment)
+  sim_fused_kernel<2><<<grid, sf::kThreads, sf::kSmem, st>>>(ta, tb, p);
+  mnn_apply_rescan_kernel<<<gf_cdiv((int64_t)n * l, 256), 256, 0, st>>>(row_best, rescan_j, rescan_cnt, (int64_t)n * l, n * tiles_m,
+                                                                       match_j, match_conf);
+  g_launches += 7;
   GF_CHECK_LAUNCH();
   return GF_OK;
 }

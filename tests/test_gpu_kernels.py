@@ -563,6 +563,46 @@ def test_fused_coarse_matching_equals_materialised(ops, golden_dir, shape, thr):
         assert torch.equal(a, torch.stack([want["b_ids"], want["i_ids"], want["j_ids"]], 1))
 
 
+@pytest.mark.parametrize("border,thr", [(0, 0.0), (2, 0.0), (2, 1e-4), (1, 0.0)])
+def test_fused_coarse_matching_exact_ties_and_border(ops, border, thr):
+    """Reference tie order in the PRODUCT matcher (coarse_matching.py:176-188: first j with conf == row max AND conf ==
+    column max AND inside the border).  Duplicated rows of f1 give exactly equal logits, hence exactly equal confidences,
+    in two columns; the earlier copy sits in the border strip, so with border > 0 the reference takes the LATER copy while
+    the smallest-j candidate of pass 1 is rejected -> the exact re-scan (sim_fused_kernel<2>) must recover it.
+    Duplicated rows of f0 (two rows sharing a column maximum) are in the mix too.  Bit-exact (b, i, j) vs the CPU
+    oracle and vs the materialised kernels; L != S; batch 2."""
+    n, hw0, hw1 = 2, (12, 16), (11, 19)
+    l, s = hw0[0] * hw0[1], hw1[0] * hw1[1]
+    f0, f1 = _feat(n, l, 256, 41, rms=1.0, offset=0.3), _feat(n, s, 256, 42, rms=1.0, offset=0.3)
+    w0, w1 = hw0[1], hw1[1]
+    pairs = []                                                  # (i, j_border, j_inside): f0[i] looks like both copies
+    for k, (i, ja, jb) in enumerate([(3 * w0 + 4, 0 * w1 + 5, 4 * w1 + 7), (5 * w0 + 9, 3 * w1 + 0, 6 * w1 + 11),
+                                     (7 * w0 + 6, 1 * w1 + 18, 8 * w1 + 3), (8 * w0 + 8, 5 * w1 + 5, 9 * w1 + 9)]):
+        for b in range(n):
+            f1[b, jb] = f1[b, ja]                               # exact duplicate -> identical columns of the logit matrix
+            f0[b, i] = 3.0 * f1[b, ja]                          # strongly aligned: (i, ja) and (i, jb) are mutual maxima
+        pairs.append((i, ja, jb))
+    f0[:, 2 * w0 + 3] = f0[:, 2 * w0 + 2]                       # duplicated query rows
+    f0[1, 6 * w0 + 1] = f0[1, 3 * w0 + 4]                       # a second row tied on the same (duplicated) columns
+    conf = O.dual_softmax_conf(f0, f1, 0.1)
+    want = O.coarse_match(conf, thr, (hw0[0] * 8, hw0[1] * 8), hw0, hw1, border)
+    want_l = torch.stack([want["b_ids"], want["i_ids"], want["j_ids"]], 1)
+    for i, ja, jb in pairs[:3]:                                 # the constructed rows really tie and really match
+        assert conf[0, i, ja] == conf[0, i, jb] == conf[0, i].max()
+        hit = want_l[(want_l[:, 0] == 0) & (want_l[:, 1] == i)]
+        assert hit.shape[0] == 1 and int(hit[0, 2]) == (ja if border == 0 else jb)      # ja lies in the border strip
+    fused, counts = ops.coarse_match_fused(dev(f0), dev(f1), 0.1, thr, border, hw0, hw1, 8.0)
+    got = _match_lists(fused)
+    assert torch.equal(got, want_l), (got.shape, want_l.shape)
+    assert torch.equal(fused["mkpts1_c"].cpu(), want["mkpts1_c"]) and torch.equal(fused["mkpts0_c"].cpu(), want["mkpts0_c"])
+    sim = ops.similarity(dev(f0), dev(f1), 0.1)
+    cf, crmax, ccmax = ops.dual_softmax_(sim)
+    mat, counts2 = ops.mutual_nearest(cf, crmax, ccmax, thr, border, hw0, hw1, 8.0)
+    assert torch.equal(got, _match_lists(mat)) and counts.tolist() == counts2.tolist()
+    rel = ((fused["mconf"].cpu() - want["mconf"]).abs() / want["mconf"].abs().clamp(min=1e-30)).max().item()
+    assert rel <= 2e-3, rel
+
+
 def test_stem_conv7x7(ops):
     """Stem 7x7/s2 conv + folded BN + ReLU (FFMA kernel, fp32 image -> NHWC bf16) vs F.conv2d; odd sizes hit the
     partial-tile and zero-padding paths.  Tolerance = bf16 output rounding."""
