@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--regime", default="dense", choices=["dense", "shift"])
-    ap.add_argument("--backbone", default=os.environ.get("GF_BACKBONE", "bf16"))
+    ap.add_argument("--backbone", default=os.environ.get("GF_BACKBONE", "f16"))
     ap.add_argument("--ransac", default=os.environ.get("GF_RANSAC", "cv2"), choices=["cv2", "gpu"],
                     help="cv2 = host cv2.findHomography as the reference (default); gpu = csrc/ransac.cu (not bit-identical)")
     ap.add_argument("--depth", type=int, default=2, help="batches in flight (MatchPipeline); 1 = plain serial forward")

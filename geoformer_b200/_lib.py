@@ -21,10 +21,10 @@ SIGNATURES = {
     "gf_launch_count": (L, []),
     "gf_linear_tf32": (I, [P, P, P, P, L, I, I, I, I, I, P, P, I, P, P, P, P, P]),
     "gf_linear_ref": (I, [P, P, P, P, L, I, I, I, I, I, P, P, I, P, P, P, P, P]),
-    "gf_conv3x3_bf16": (I, [P, P, P, P, P, I, I, I, I, I, I, I, P]),
-    "gf_conv_bf16": (I, [P, P, P, P, P, I, I, I, I, I, I, I, I, I, P]),
-    "gf_stem_conv7x7_bf16": (I, [P, P, P, P, I, I, I, P]),
-    "gf_upsample_add_bf16": (I, [P, P, P, I, I, I, I, I, I, P]),
+    "gf_conv3x3_f16": (I, [P, P, P, P, P, I, I, I, I, I, I, I, P]),
+    "gf_conv_f16": (I, [P, P, P, P, P, I, I, I, I, I, I, I, I, I, P]),
+    "gf_stem_conv7x7_f16": (I, [P, P, P, P, I, I, I, P]),
+    "gf_upsample_add_f16": (I, [P, P, P, I, I, I, I, I, I, P]),
     "gf_conv_ref": (I, [P, P, P, P, P, I, I, I, I, I, I, I, I, P]),
     "gf_upsample_add_ref": (I, [P, P, P, I, I, I, I, I, I, P]),
     "gf_add_posenc": (I, [P, P, P, I, L, I, P]),
@@ -61,8 +61,8 @@ SIGNATURES = {
     "gf_geo_cross_attention_f16": (I, [P, I, P, I, P, I, P, I, I, I, I, I, P, I, P]),
     "gf_select_rows": (I, [P, P, P, I, L, I, P]),
     "gf_fine_gather": (I, [P, I, I, I, P, P, L, I, I, I, P, P]),
-    "gf_fine_gather_bf16": (I, [P, I, I, I, P, P, L, I, I, I, P, P]),
-    "gf_fine_gather_bf16_f16": (I, [P, I, I, I, P, P, L, I, I, I, P, P]),
+    "gf_fine_gather_f16": (I, [P, I, I, I, P, P, L, I, I, I, P, P]),
+    "gf_fine_gather_f16_f16": (I, [P, I, I, I, P, P, L, I, I, I, P, P]),
     "gf_gather_rows": (I, [P, L, I, P, P, L, P, P]),
     "gf_fine_match": (I, [P, P, L, I, I, F, F, P, P, P, P, P, P]),
     "gf_resize_gray_u8": (I, [P, I, I, P, I, I, P]),

@@ -1,5 +1,8 @@
 // 3x3 (pad 1) and 1x1 convolutions, stride 1 or 2, as a tcgen05 implicit GEMM (backbone: resnet_fpn.py:32-40, 70-82, 100-118;
-// SURVEY.md §8f rank 1).  NHWC bf16 activations, BN folded into weights + bias.
+// SURVEY.md §8f rank 1).  NHWC fp16 activations (fp32 accumulation in TMEM), BN folded into weights + bias.  fp16, not
+// bf16: same tensor-core rate, 8x smaller storage rounding (2^-11 vs 2^-8) through ~20 chained layers - measured on the
+// 480x640 reference goldens the bf16 backbone alone cost 10-40 % of the final match-set identity, fp16 costs ~1-3 %
+// (profiles/r02_parity_precision_probe.txt).  Outputs saturate at +-65504 instead of overflowing to inf.
 //
 //   Y[b,y,x,co] = act( bias[co] + sum_{dy,dx,ci} X[b,y+dy-1,x+dx-1,ci] * W[co,dy,dx,ci]  (+ R[b,y,x,co]) )
 //
@@ -8,21 +11,21 @@
 // {64 ch, 16 px, 8 rows, 1} at (cb*64, x0+dx-1, y0+dy-1, b); TMA zero-fills the padding halo and the channel tail,
 // and lands the box as 128 rows x 128 B with the 128B swizzle == a K-major UMMA operand.
 // Same warp-specialised persistent structure as gemm_tc.cu (TMA producer / single-thread MMA issuer / 4 epilogue
-// warps, double-buffered TMEM accumulator); epilogue fuses bias, residual add, ReLU / LeakyReLU, bf16 pack and
+// warps, double-buffered TMEM accumulator); epilogue fuses bias, residual add, ReLU / LeakyReLU, fp16 pack and
 // writes 4-D TMA boxes {64 ch, 16 px, 2 rows}.
 #include "common.cuh"
 #include "ptx.cuh"
 
 #include <atomic>
 #include <cstdlib>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace gf {
 extern std::atomic<int64_t> g_launches;
 
 struct ConvParams {
   const float* bias;                 // [cout_p] fp32
-  const __nv_bfloat16* residual;     // NHWC [b,h,w,cout_p] or null
+  const __half* residual;            // NHWC [b,h,w,cout_p] or null
   int batch, h, w, cout_p;
   int kbc;                           // 64-channel k-blocks per tap
   int last_k;                        // MMAs (16 channels each) that carry real channels in the last k-block of a tap
@@ -51,8 +54,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
       : "memory");
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  // saturating: a value beyond fp16's range becomes +-65504, never inf (which would turn into NaN downstream)
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  __half2 t = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
@@ -115,7 +121,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc(1 /*bf16*/, 128, BN);
+      constexpr uint32_t idesc = ptx::umma_idesc(0 /*f16*/, 128, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -200,7 +206,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const uint32_t w4[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[q]);
+              const __half2 h2 = *reinterpret_cast<const __half2*>(&w4[q]);
               v[8 * j + 2 * q] += __low2float(h2);
               v[8 * j + 2 * q + 1] += __high2float(h2);
             }
@@ -216,8 +222,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           uint4 o;
-          o.x = pack_bf16(v[8 * j], v[8 * j + 1]); o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-          o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+          o.x = pack_f16(v[8 * j], v[8 * j + 1]); o.y = pack_f16(v[8 * j + 2], v[8 * j + 3]);
+          o.z = pack_f16(v[8 * j + 4], v[8 * j + 5]); o.w = pack_f16(v[8 * j + 6], v[8 * j + 7]);
           *reinterpret_cast<uint4*>(myrow + ((j ^ (lane & 7)) << 4)) = o;
         }
         ptx::fence_proxy_async();
@@ -244,8 +250,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 }
 
 // out = lateral + bilinear_upsample(src -> (h, w), align_corners=True)   (FPN top-down merge, resnet_fpn.py:108-115)
-// NHWC bf16; one thread per 8 channels (16 B).
-__global__ void upsample_add_bf16_kernel(const uint4* __restrict__ lateral, const uint4* __restrict__ src,
+// NHWC fp16; one thread per 8 channels (16 B).
+__global__ void upsample_add_f16_kernel(const uint4* __restrict__ lateral, const uint4* __restrict__ src,
                                          uint4* __restrict__ out, int b, int h, int w, int hs, int ws, int c8,
                                          float ry, float rx) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -270,19 +276,19 @@ __global__ void upsample_add_bf16_kernel(const uint4* __restrict__ lateral, cons
   uint32_t o[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(&aw[q]), b2 = *reinterpret_cast<const __nv_bfloat162*>(&bw[q]);
-    const __nv_bfloat162 c2 = *reinterpret_cast<const __nv_bfloat162*>(&cw[q]), d2 = *reinterpret_cast<const __nv_bfloat162*>(&dw[q]);
-    const __nv_bfloat162 l2 = *reinterpret_cast<const __nv_bfloat162*>(&lw[q]);
+    const __half2 a2 = *reinterpret_cast<const __half2*>(&aw[q]), b2 = *reinterpret_cast<const __half2*>(&bw[q]);
+    const __half2 c2 = *reinterpret_cast<const __half2*>(&cw[q]), d2 = *reinterpret_cast<const __half2*>(&dw[q]);
+    const __half2 l2 = *reinterpret_cast<const __half2*>(&lw[q]);
     const float lo = __low2float(l2) + w00 * __low2float(a2) + w01 * __low2float(b2) + w10 * __low2float(c2) + w11 * __low2float(d2);
     const float hi = __high2float(l2) + w00 * __high2float(a2) + w01 * __high2float(b2) + w10 * __high2float(c2) + w11 * __high2float(d2);
-    o[q] = pack_bf16(lo, hi);
+    o[q] = pack_f16(lo, hi);
   }
   out[idx] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // ---------------------------------------------------------------------------------------------
 // Stem: 7x7 / stride 2 / pad 3 convolution of the 1-channel image + folded BN + ReLU (resnet_fpn.py:58-60,102),
-// fp32 image in, NHWC bf16 out.  C_in = 1 makes this a 49-tap FFMA kernel (no tensor-core shape): CTA = 8 x 32
+// fp32 image in, NHWC fp16 out.  C_in = 1 makes this a 49-tap FFMA kernel (no tensor-core shape): CTA = 8 x 32
 // output pixels x 128 channels, thread = 8 consecutive pixels x 16 channels (128 accumulators), input patch and
 // weights in shared memory; per kernel row 21 input LDS + 28 weight LDS.128 feed 896 FFMA.
 // Weights: [49 taps][128 channels] fp32 (natural channel order); thread (cg, j) reads the float4 of channels
@@ -290,7 +296,7 @@ __global__ void upsample_add_bf16_kernel(const uint4* __restrict__ lateral, cons
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 stem_conv7x7_kernel(const float* __restrict__ img, const float* __restrict__ wperm, const float* __restrict__ bias,
-                    __nv_bfloat16* __restrict__ out, int h, int w, int ho, int wo) {
+                    __half* __restrict__ out, int h, int w, int ho, int wo) {
   __shared__ float patch[21][72];
   __shared__ __align__(16) float ws[49 * 128];
   const int b = blockIdx.z;
@@ -342,8 +348,8 @@ stem_conv7x7_kernel(const float* __restrict__ img, const float* __restrict__ wpe
         const int ox = ox0 + pcol + i;
         if (ox < wo) {
           uint2 o;
-          o.x = pack_bf16(fmaxf(acc[i][4 * j] + b4.x, 0.f), fmaxf(acc[i][4 * j + 1] + b4.y, 0.f));
-          o.y = pack_bf16(fmaxf(acc[i][4 * j + 2] + b4.z, 0.f), fmaxf(acc[i][4 * j + 3] + b4.w, 0.f));
+          o.x = pack_f16(fmaxf(acc[i][4 * j] + b4.x, 0.f), fmaxf(acc[i][4 * j + 1] + b4.y, 0.f));
+          o.y = pack_f16(fmaxf(acc[i][4 * j + 2] + b4.z, 0.f), fmaxf(acc[i][4 * j + 3] + b4.w, 0.f));
           *reinterpret_cast<uint2*>(out + (((int64_t)b * ho + oy) * wo + ox) * 128 + j * 32 + cg * 4) = o;
         }
       }
@@ -356,7 +362,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_fn();
 
-// NHWC bf16 map: dims {C, W, H, B}; box {64, box_w, box_h, 1}; 128B swizzle; OOB -> 0 on load, clipped on store
+// NHWC fp16 map: dims {C, W, H, B}; box {64, box_w, box_h, 1}; 128B swizzle; OOB -> 0 on load, clipped on store
 // `stride` > 1: W and H are traversed with that element stride; the box then spans box_w*stride x box_h*stride source
 // elements and delivers box_w x box_h of them (cuTensorMapEncodeTiled: ceil(boxDim / elementStride) per dimension).
 static int make_nhwc_tmap(CUtensorMap* m, const void* base, int c, int w, int h, int b, int box_w, int box_h, int stride = 1) {
@@ -366,7 +372,7 @@ static int make_nhwc_tmap(CUtensorMap* m, const void* base, int c, int w, int h,
   cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)c * 2 * w, (cuuint64_t)c * 2 * w * h};
   cuuint32_t box[4] = {64, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return gf_set_error(GF_ERR_DRIVER, "cuTensorMapEncodeTiled(nhwc) failed");
@@ -391,15 +397,15 @@ static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const CUten
 
 using namespace gf;
 
-// x NHWC bf16 [b,h,w,cin_p]; wt bf16 [cout_p][taps][cin_k] (taps = ksize^2, cin_k = cin_p rounded up to 64, zero padded);
-// bias fp32 [cout_p]; residual / y NHWC bf16 [b,ho,wo,cout_p], ho = (h - 1) / stride + 1.  ksize 3 (pad 1) or 1 (pad 0),
+// x NHWC fp16 [b,h,w,cin_p]; wt fp16 [cout_p][taps][cin_k] (taps = ksize^2, cin_k = cin_p rounded up to 64, zero padded);
+// bias fp32 [cout_p]; residual / y NHWC fp16 [b,ho,wo,cout_p], ho = (h - 1) / stride + 1.  ksize 3 (pad 1) or 1 (pad 0),
 // stride 1 or 2; cin_p, cout_p multiples of 8; cout_p <= 256.
-extern "C" int gf_conv_bf16(const void* x, const void* wt, const float* bias, const void* residual, void* y, int batch,
+extern "C" int gf_conv_f16(const void* x, const void* wt, const float* bias, const void* residual, void* y, int batch,
                             int h, int w, int cin_p, int cout_p, int cin_k, int ksize, int stride, int act,
                             gf_stream_t stream) {
   if (batch <= 0 || h <= 0 || w <= 0 || (cin_p % 8) || (cout_p % 8) || cout_p > 256 || (cin_k % 64) || cin_k < cin_p ||
       !(ksize == 1 || ksize == 3) || !(stride == 1 || stride == 2) || bias == nullptr)
-    return gf_set_error(GF_ERR_ARG, "gf_conv_bf16: channels % 8, cout <= 256, cin_k % 64 == 0, ksize in {1,3}, stride in {1,2}");
+    return gf_set_error(GF_ERR_ARG, "gf_conv_f16: channels % 8, cout <= 256, cin_k % 64 == 0, ksize in {1,3}, stride in {1,2}");
   const int taps = ksize * ksize;
   const int ho = (h - 1) / stride + 1, wo = (w - 1) / stride + 1;
   const int BN = cout_p <= 128 ? 128 : (cout_p <= 208 ? 208 : 256);
@@ -409,10 +415,10 @@ extern "C" int gf_conv_bf16(const void* x, const void* wt, const float* bias, co
   if ((rc = make_nhwc_tmap(&ty, y, cout_p, wo, ho, batch, 16, 2))) return rc;
   if ((rc = make_tmap(&tw, wt, 2, taps * (int64_t)cin_k, cout_p, 1, taps * (int64_t)cin_k, 0, BN))) return rc;
   ConvParams p{};
-  p.bias = bias; p.residual = (const __nv_bfloat16*)residual; p.batch = batch; p.h = ho; p.w = wo; p.cout_p = cout_p;
+  p.bias = bias; p.residual = (const __half*)residual; p.batch = batch; p.h = ho; p.w = wo; p.cout_p = cout_p;
   p.kbc = cin_k / 64; p.taps = taps; p.stride = stride; p.pad = ksize / 2;
   p.last_k = (cin_p - (p.kbc - 1) * 64 + 15) / 16;
-  if (p.last_k < 1 || p.last_k > 4) return gf_set_error(GF_ERR_ARG, "gf_conv_bf16: cin_k must be cin_p rounded up to 64");
+  if (p.last_k < 1 || p.last_k > 4) return gf_set_error(GF_ERR_ARG, "gf_conv_f16: cin_k must be cin_p rounded up to 64");
   p.tiles_x = gf_cdiv(wo, 16); p.tiles_y = gf_cdiv(ho, 8); p.act = act;
   if (BN == 128 && ho >= 32 && getenv("GF_CONV_MT1") == nullptr) {     // two stacked pixel tiles per weight box
     p.tiles_y = gf_cdiv(ho, 16);
@@ -423,30 +429,30 @@ extern "C" int gf_conv_bf16(const void* x, const void* wt, const float* bias, co
   return launch_conv<256>(tx, tw, ty, p, (cudaStream_t)stream);
 }
 
-extern "C" int gf_conv3x3_bf16(const void* x, const void* wt, const float* bias, const void* residual, void* y,
+extern "C" int gf_conv3x3_f16(const void* x, const void* wt, const float* bias, const void* residual, void* y,
                                int batch, int h, int w, int cin_p, int cout_p, int cin_k, int act, gf_stream_t stream) {
-  return gf_conv_bf16(x, wt, bias, residual, y, batch, h, w, cin_p, cout_p, cin_k, 3, 1, act, stream);
+  return gf_conv_f16(x, wt, bias, residual, y, batch, h, w, cin_p, cout_p, cin_k, 3, 1, act, stream);
 }
 
-extern "C" int gf_upsample_add_bf16(const void* lateral, const void* src, void* out, int batch, int h, int w, int hs,
+extern "C" int gf_upsample_add_f16(const void* lateral, const void* src, void* out, int batch, int h, int w, int hs,
                                     int ws, int c, gf_stream_t stream) {
-  if (batch <= 0 || h <= 1 || w <= 1 || hs <= 0 || ws <= 0 || (c % 8)) return gf_set_error(GF_ERR_ARG, "gf_upsample_add_bf16: bad shape");
+  if (batch <= 0 || h <= 1 || w <= 1 || hs <= 0 || ws <= 0 || (c % 8)) return gf_set_error(GF_ERR_ARG, "gf_upsample_add_f16: bad shape");
   const int64_t total = (int64_t)batch * h * w * (c / 8);
   const float ry = (float)(hs - 1) / (float)(h - 1), rx = (float)(ws - 1) / (float)(w - 1);
-  upsample_add_bf16_kernel<<<gf_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  upsample_add_f16_kernel<<<gf_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const uint4*)lateral, (const uint4*)src, (uint4*)out, batch, h, w, hs, ws, c / 8, ry, rx);
   g_launches++;
   GF_CHECK_LAUNCH();
   return GF_OK;
 }
 
-// img fp32 [b,1,h,w]; wperm fp32 [49 taps][128 channels]; bias fp32 [128]; out NHWC bf16 [b, ceil(h/2), ceil(w/2), 128].
-extern "C" int gf_stem_conv7x7_bf16(const float* img, const float* wperm, const float* bias, void* out, int batch, int h,
+// img fp32 [b,1,h,w]; wperm fp32 [49 taps][128 channels]; bias fp32 [128]; out NHWC fp16 [b, ceil(h/2), ceil(w/2), 128].
+extern "C" int gf_stem_conv7x7_f16(const float* img, const float* wperm, const float* bias, void* out, int batch, int h,
                                     int w, gf_stream_t stream) {
-  if (batch <= 0 || h <= 0 || w <= 0) return gf_set_error(GF_ERR_ARG, "gf_stem_conv7x7_bf16: bad shape");
+  if (batch <= 0 || h <= 0 || w <= 0) return gf_set_error(GF_ERR_ARG, "gf_stem_conv7x7_f16: bad shape");
   const int ho = (h + 6 - 7) / 2 + 1, wo = (w + 6 - 7) / 2 + 1;
   stem_conv7x7_kernel<<<dim3(gf_cdiv(wo, 32), gf_cdiv(ho, 8), batch), 256, 0, (cudaStream_t)stream>>>(
-      img, wperm, bias, (__nv_bfloat16*)out, h, w, ho, wo);
+      img, wperm, bias, (__half*)out, h, w, ho, wo);
   g_launches++;
   GF_CHECK_LAUNCH();
   return GF_OK;

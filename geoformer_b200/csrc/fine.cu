@@ -2,14 +2,13 @@
 #include "common.cuh"
 
 #include <atomic>
-#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 namespace gf {
 extern std::atomic<int64_t> g_launches;
 
-// same gather from a bf16 NHWC fine map (the tcgen05 backbone's native output): 8-byte loads; windows out as fp32, or as
-// fp16 (exact for bf16 values in fp16's range) when they feed the fp16-operand merge GEMM
+// same gather from an fp16 NHWC fine map (the tcgen05 backbone's native output): 8-byte loads; windows out as fp32, or as
+// fp16 (a copy) when they feed the fp16-operand merge GEMM
 __device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void store4(__half* p, float4 v) {
   const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
@@ -19,7 +18,7 @@ __device__ __forceinline__ void store4(__half* p, float4 v) {
 }
 
 template <typename TO>
-__global__ void fine_gather_bf16_kernel(const __nv_bfloat16* __restrict__ fine, int hf, int wf, int c,
+__global__ void fine_gather_f16_kernel(const __half* __restrict__ fine, int hf, int wf, int c,
                                         const int64_t* __restrict__ b_ids, const int64_t* __restrict__ tok_ids, int wc,
                                         int stride, int window, TO* __restrict__ out) {
   const int64_t m = blockIdx.x;
@@ -35,8 +34,8 @@ __global__ void fine_gather_bf16_kernel(const __nv_bfloat16* __restrict__ fine, 
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (py >= 0 && py < hf && px >= 0 && px < wf) {
       const uint2 raw = __ldg(reinterpret_cast<const uint2*>(fine + (((int64_t)b * hf + py) * wf + px) * c) + q);
-      const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
-      const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+      const __half2 lo = *reinterpret_cast<const __half2*>(&raw.x);
+      const __half2 hi = *reinterpret_cast<const __half2*>(&raw.y);
       v = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
     }
     store4(o + 4 * e, v);
@@ -287,24 +286,24 @@ extern "C" int gf_fine_gather(const float* fine_nhwc, int hf, int wf, int c, con
   return GF_OK;
 }
 
-extern "C" int gf_fine_gather_bf16(const void* fine_nhwc, int hf, int wf, int c, const int64_t* b_ids,
+extern "C" int gf_fine_gather_f16(const void* fine_nhwc, int hf, int wf, int c, const int64_t* b_ids,
                                    const int64_t* tok_ids, int64_t m, int wc, int stride, int window, float* out,
                                    gf_stream_t stream) {
-  if (m < 0 || c <= 0 || (c % 4) || window <= 0) return gf_set_error(GF_ERR_ARG, "gf_fine_gather_bf16: bad shape");
+  if (m < 0 || c <= 0 || (c % 4) || window <= 0) return gf_set_error(GF_ERR_ARG, "gf_fine_gather_f16: bad shape");
   if (m == 0) return GF_OK;
-  fine_gather_bf16_kernel<float><<<(unsigned)m, 128, 0, STREAM>>>((const __nv_bfloat16*)fine_nhwc, hf, wf, c, b_ids, tok_ids, wc,
+  fine_gather_f16_kernel<float><<<(unsigned)m, 128, 0, STREAM>>>((const __half*)fine_nhwc, hf, wf, c, b_ids, tok_ids, wc,
                                                                  stride, window, out);
   g_launches++;
   GF_CHECK_LAUNCH();
   return GF_OK;
 }
 
-extern "C" int gf_fine_gather_bf16_f16(const void* fine_nhwc, int hf, int wf, int c, const int64_t* b_ids,
+extern "C" int gf_fine_gather_f16_f16(const void* fine_nhwc, int hf, int wf, int c, const int64_t* b_ids,
                                        const int64_t* tok_ids, int64_t m, int wc, int stride, int window, void* out,
                                        gf_stream_t stream) {
-  if (m < 0 || c <= 0 || (c % 4) || window <= 0) return gf_set_error(GF_ERR_ARG, "gf_fine_gather_bf16_f16: bad shape");
+  if (m < 0 || c <= 0 || (c % 4) || window <= 0) return gf_set_error(GF_ERR_ARG, "gf_fine_gather_f16_f16: bad shape");
   if (m == 0) return GF_OK;
-  fine_gather_bf16_kernel<__half><<<(unsigned)m, 128, 0, STREAM>>>((const __nv_bfloat16*)fine_nhwc, hf, wf, c, b_ids, tok_ids, wc,
+  fine_gather_f16_kernel<__half><<<(unsigned)m, 128, 0, STREAM>>>((const __half*)fine_nhwc, hf, wf, c, b_ids, tok_ids, wc,
                                                                   stride, window, (__half*)out);
   g_launches++;
   GF_CHECK_LAUNCH();

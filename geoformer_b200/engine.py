@@ -3,7 +3,7 @@
 Follows the stage order of the reference ``model/full_model.py:39-123``; every stage except the host RANSAC
 (``cv2.findHomography``, geo_module.py:48, kept for parity by construction; ``model.ransac = "gpu"`` moves it to
 csrc/ransac.cu) runs in hand-written sm_100a kernels reached through the C ABI (``geoformer_b200.ops``).  No cuDNN /
-cuBLAS call exists in this package: the backbone is csrc/conv_tc.cu (bf16, product) or csrc/conv_ref.cu (fp32 FFMA,
+cuBLAS call exists in this package: the backbone is csrc/conv_tc.cu (fp16, product) or csrc/conv_ref.cu (fp32 FFMA,
 accurate mode for the golden-match parity tests).
 """
 from __future__ import annotations
@@ -53,8 +53,8 @@ def _fold_bn(w: torch.Tensor, sd: Dict[str, torch.Tensor], bn: str, eps: float =
 
 
 def pack_conv3x3(w: torch.Tensor, b: Optional[torch.Tensor], cin_p: int, cout_p: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
-    """[Cout,Cin,k,k] fp32 (+bias), k in {3, 1} -> tap-major K-major bf16 [cout_p, k*k, cin_k] and fp32 bias [cout_p]
-    for gf_conv_bf16 (cin_k = cin_p rounded up to a multiple of 64; all padding is zero)."""
+    """[Cout,Cin,k,k] fp32 (+bias), k in {3, 1} -> tap-major K-major fp16 [cout_p, k*k, cin_k] and fp32 bias [cout_p]
+    for gf_conv_f16 (cin_k = cin_p rounded up to a multiple of 64; all padding is zero)."""
     co, ci = w.shape[:2]
     taps = w.shape[2] * w.shape[3]
     cin_k = (cin_p + 63) // 64 * 64
@@ -63,7 +63,7 @@ def pack_conv3x3(w: torch.Tensor, b: Optional[torch.Tensor], cin_p: int, cout_p:
     bias = torch.zeros(cout_p, dtype=torch.float32)
     if b is not None:
         bias[:co] = b
-    return wt.to(device=device, dtype=torch.bfloat16).contiguous(), bias.to(device)
+    return wt.to(device=device, dtype=torch.float16).contiguous(), bias.to(device)
 
 
 def pack_fine_layer(wq, wk, wv, wm, w1, w2, device) -> torch.Tensor:
@@ -133,7 +133,7 @@ class PackedWeights:
                        wa=f32(wm[:, :cf]), wa16=f16(wm[:, :cf]), wb=f32(wm[:, cf:]),
                        bm=f32(sd["fine_preprocess.merge_feat.bias"]))
 
-        # backbone: BN folded into weights + bias.  bf16 (product): tap-major K-major packs for the tcgen05 implicit GEMM
+        # backbone: BN folded into weights + bias.  fp16 (product): tap-major K-major packs for the tcgen05 implicit GEMM
         # (csrc/conv_tc.cu); the 196-wide stage is zero-padded to 200 channels (16-byte rows for TMA): padded output
         # channels stay exactly 0 through ReLU / residual adds and padded input channels multiply zero weights.
         # fp32 (accurate mode): [taps][cin][cout] fp32 packs for the FFMA reference kernels (csrc/conv_ref.cu).
@@ -159,7 +159,7 @@ class PackedWeights:
                   ("layer1_outconv2.0", "layer1_outconv2.1"), ("layer1_outconv2.3", None)]
         key = lambda name: name.replace(".downsample.0", ".down")
         self.bb_tc = self.bb_ref = None
-        if backbone_dtype == torch.bfloat16:
+        if backbone_dtype == torch.float16:
             t = {}
             for name, bn in names[1:]:
                 w, b = folded(name, bn)
@@ -177,7 +177,7 @@ class PackedWeights:
                                 None if b is None else b.to(device))
             self.bb_ref = r
         else:
-            raise ValueError(f"backbone dtype must be bfloat16 (product) or float32 (accurate), got {backbone_dtype}")
+            raise ValueError(f"backbone dtype must be float16 (product) or float32 (accurate), got {backbone_dtype}")
         self._pe: Dict[Tuple[int, int, int], torch.Tensor] = {}
         self._pe_lock = threading.Lock()
 
@@ -207,7 +207,7 @@ class PackedWeights:
 # backbone (resnet_fpn.py:100-118)
 # --------------------------------------------------------------------------------------------
 def backbone_forward(pw: PackedWeights, img: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """[B,1,H,W] fp32 -> coarse NHWC [B,H/8,W/8,256] fp32, fine NHWC [B,H/2,W/2,128] (bf16 in product mode, fp32 in
+    """[B,1,H,W] fp32 -> coarse NHWC [B,H/8,W/8,256] fp32, fine NHWC [B,H/2,W/2,128] (fp16 in product mode, fp32 in
     accurate mode); both contiguous."""
     return backbone_forward_tc(pw, img) if pw.bb_tc is not None else backbone_forward_ref(pw, img)
 
@@ -244,7 +244,7 @@ def backbone_forward_ref(pw: PackedWeights, img: torch.Tensor) -> Tuple[torch.Te
 def backbone_forward_tc(pw: PackedWeights, img: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """Same network on this library's kernels only: every 3x3 and 1x1 convolution (stride 1 or 2) runs in the tcgen05
     implicit-GEMM kernel with BN, residual add and activation fused into its epilogue; the 7x7 stem is a register-
-    tiled FFMA kernel and the FPN upsample+add one fused kernel.  Activations are NHWC bf16 throughout."""
+    tiled FFMA kernel and the FPN upsample+add one fused kernel.  Activations are NHWC fp16 throughout."""
     tc = pw.bb_tc
 
     def conv(name, t, act, residual=None, stride=1):
@@ -268,7 +268,7 @@ def backbone_forward_tc(pw: PackedWeights, img: torch.Tensor) -> Tuple[torch.Ten
     x2o = conv("layer2_outconv2.3", conv("layer2_outconv2.0", x2o, 2), 0)
     x1o = ops.upsample_add(conv("layer1_outconv", x1, 0), x2o)
     x1o = conv("layer1_outconv2.3", conv("layer1_outconv2.0", x1o, 2), 0)
-    return x3o.float().contiguous(), x1o          # the fine map stays bf16 NHWC: fine_gather reads it directly
+    return x3o.float().contiguous(), x1o          # the fine map stays fp16 NHWC: fine_gather reads it directly
 
 
 # --------------------------------------------------------------------------------------------
@@ -513,7 +513,7 @@ def fine_stage(pw: PackedWeights, fine0: torch.Tensor, fine1: torch.Tensor, g0: 
     cf = fine0.shape[-1]
     stride = hw0_f[0] // hw0_c[0]
     # fine_preprocess.py:41-72.  merge_feat(cat[win, ctx]) = win Wa^T + (ctx Wb^T + b)
-    w16 = ops.act16() and fine0.dtype == torch.bfloat16 and cf % 64 == 0      # bf16 map -> fp16 windows -> fp16-operand merge
+    w16 = ops.act16() and fine0.dtype == torch.float16 and cf % 64 == 0      # fp16 map -> fp16 windows -> fp16-operand merge
     win = torch.empty((2 * m, ww, cf), device=dev, dtype=torch.float16 if w16 else torch.float32)
     ops.fine_gather(fine0, b_ids, i_ids, hw0_c[1], stride, window, out=win[:m])
     ops.fine_gather(fine1, b_ids, j_ids, hw1_c[1], stride, window, out=win[m:])

@@ -84,8 +84,8 @@ class _GeoModule(nn.Module):
         self.des_transformer = _Encoder(d, n_layers, nn.Tanh, final_norm=True)
 
 
-# "bf16": tcgen05 implicit-GEMM backbone (product); "fp32": FFMA reference kernels (accurate mode for parity runs)
-_BACKBONE_DTYPES = {"bf16": torch.bfloat16, "fp32": torch.float32}
+# "f16": tcgen05 implicit-GEMM backbone (product); "fp32": FFMA reference kernels (accurate mode for parity runs)
+_BACKBONE_DTYPES = {"f16": torch.float16, "fp32": torch.float32}
 
 
 class GeoFormer(nn.Module):
@@ -101,7 +101,7 @@ class GeoFormer(nn.Module):
         self.loftr_fine = _Encoder(df, len(loftr_config["fine"]["layer_names"]))
         self.geo_module = _GeoModule(dc, len(geoformer_cfg["layer_names"]))
         # engine options (not part of the reference surface)
-        self.backbone_precision = os.environ.get("GF_BACKBONE", "bf16")
+        self.backbone_precision = os.environ.get("GF_BACKBONE", "f16")
         # "cv2": host cv2.findHomography as the reference (geo_module.py:48); "gpu": csrc/ransac.cu (not bit-identical)
         self.ransac = os.environ.get("GF_RANSAC", "cv2")
         self.ransac_hyps = 1024

@@ -177,43 +177,43 @@ def _linear_mixed(a, w, a2, epi, act_cols, bias, rowbias, rowbias_group, gamma, 
 
 def conv3x3(x: torch.Tensor, wt: torch.Tensor, bias: torch.Tensor, residual: Optional[torch.Tensor] = None,
             act: int = 0) -> torch.Tensor:
-    """3x3/s1/p1 conv + folded BN (+ residual) + activation on NHWC bf16 (tcgen05 implicit GEMM).
-    x [b,h,w,cin_p]; wt [cout_p, 9, cin_k]; bias fp32 [cout_p]; returns [b,h,w,cout_p] bf16."""
+    """3x3/s1/p1 conv + folded BN (+ residual) + activation on NHWC fp16 (tcgen05 implicit GEMM).
+    x [b,h,w,cin_p]; wt [cout_p, 9, cin_k]; bias fp32 [cout_p]; returns [b,h,w,cout_p] fp16."""
     return conv(x, wt, bias, residual, act, 1)
 
 
 def conv(x: torch.Tensor, wt: torch.Tensor, bias: torch.Tensor, residual: Optional[torch.Tensor] = None,
          act: int = 0, stride: int = 1) -> torch.Tensor:
-    """3x3 (pad 1) or 1x1 (pad 0) conv, stride 1 or 2, + bias (+ residual) + activation on NHWC bf16.
-    wt [cout_p, taps, cin_k] with taps in {9, 1}; returns [b, (h-1)//stride+1, (w-1)//stride+1, cout_p] bf16."""
-    assert x.dtype == torch.bfloat16 and x.is_contiguous() and wt.dtype == torch.bfloat16 and wt.is_contiguous()
+    """3x3 (pad 1) or 1x1 (pad 0) conv, stride 1 or 2, + bias (+ residual) + activation on NHWC fp16.
+    wt [cout_p, taps, cin_k] with taps in {9, 1}; returns [b, (h-1)//stride+1, (w-1)//stride+1, cout_p] fp16."""
+    assert x.dtype == torch.float16 and x.is_contiguous() and wt.dtype == torch.float16 and wt.is_contiguous()
     b, h, w, cin_p = x.shape
     cout_p, taps, cin_k = wt.shape
     assert taps in (1, 9)
-    y = torch.empty((b, (h - 1) // stride + 1, (w - 1) // stride + 1, cout_p), device=x.device, dtype=torch.bfloat16)
+    y = torch.empty((b, (h - 1) // stride + 1, (w - 1) // stride + 1, cout_p), device=x.device, dtype=torch.float16)
     if residual is not None:
-        assert residual.shape == y.shape and residual.is_contiguous() and residual.dtype == torch.bfloat16
-    _call("gf_conv_bf16", x.data_ptr(), wt.data_ptr(), bias.data_ptr(), _ptr(residual), y.data_ptr(), b, h, w, cin_p,
+        assert residual.shape == y.shape and residual.is_contiguous() and residual.dtype == torch.float16
+    _call("gf_conv_f16", x.data_ptr(), wt.data_ptr(), bias.data_ptr(), _ptr(residual), y.data_ptr(), b, h, w, cin_p,
           cout_p, cin_k, 3 if taps == 9 else 1, stride, act, _stream(),
           tag=f"[{cin_p}->{cout_p}@{h}x{w}{'k1' if taps == 1 else ''}{'s2' if stride == 2 else ''}]")
     return y
 
 
 def stem_conv(img: torch.Tensor, wperm: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
-    """7x7/s2 stem + folded BN + ReLU: fp32 [b,1,h,w] -> NHWC bf16 [b,h/2,w/2,128]."""
+    """7x7/s2 stem + folded BN + ReLU: fp32 [b,1,h,w] -> NHWC fp16 [b,h/2,w/2,128]."""
     assert img.dtype == torch.float32 and img.is_contiguous() and img.shape[1] == 1
     b, _, h, w = img.shape
-    out = torch.empty((b, (h - 1) // 2 + 1, (w - 1) // 2 + 1, 128), device=img.device, dtype=torch.bfloat16)
-    _call("gf_stem_conv7x7_bf16", img.data_ptr(), wperm.data_ptr(), bias.data_ptr(), out.data_ptr(), b, h, w, _stream())
+    out = torch.empty((b, (h - 1) // 2 + 1, (w - 1) // 2 + 1, 128), device=img.device, dtype=torch.float16)
+    _call("gf_stem_conv7x7_f16", img.data_ptr(), wperm.data_ptr(), bias.data_ptr(), out.data_ptr(), b, h, w, _stream())
     return out
 
 
 def upsample_add(lateral: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
-    """lateral [b,h,w,c] + bilinear_upsample(src [b,hs,ws,c]) (align_corners=True), NHWC bf16."""
-    assert lateral.is_contiguous() and src.is_contiguous() and lateral.dtype == src.dtype == torch.bfloat16
+    """lateral [b,h,w,c] + bilinear_upsample(src [b,hs,ws,c]) (align_corners=True), NHWC fp16."""
+    assert lateral.is_contiguous() and src.is_contiguous() and lateral.dtype == src.dtype == torch.float16
     b, h, w, c = lateral.shape
     out = torch.empty_like(lateral)
-    _call("gf_upsample_add_bf16", lateral.data_ptr(), src.data_ptr(), out.data_ptr(), b, h, w, src.shape[1], src.shape[2],
+    _call("gf_upsample_add_f16", lateral.data_ptr(), src.data_ptr(), out.data_ptr(), b, h, w, src.shape[1], src.shape[2],
           c, _stream())
     return out
 
@@ -471,10 +471,10 @@ def fine_gather(fine_nhwc: torch.Tensor, b_ids, tok_ids, wc: int, stride: int, w
     if out is None:
         out = torch.empty((m, window * window, c), device=fine_nhwc.device, dtype=torch.float32)
     if out.dtype == torch.float16:
-        assert fine_nhwc.dtype == torch.bfloat16
-        fn = "gf_fine_gather_bf16_f16"
+        assert fine_nhwc.dtype == torch.float16
+        fn = "gf_fine_gather_f16_f16"
     else:
-        fn = "gf_fine_gather_bf16" if fine_nhwc.dtype == torch.bfloat16 else "gf_fine_gather"
+        fn = "gf_fine_gather_f16" if fine_nhwc.dtype == torch.float16 else "gf_fine_gather"
     _call(fn, fine_nhwc.data_ptr(), hf, wf, c, b_ids.data_ptr(), tok_ids.data_ptr(), m, wc, stride,
               window, out.data_ptr(), _stream())
     return out

@@ -74,29 +74,29 @@ int gf_linear_ref(const float* A, const float* A2, const float* W, float* Y, int
                   gf_stream_t stream);
 
 /* Backbone 3x3 / stride 1 / pad 1 convolution with folded BatchNorm (resnet_fpn.py:32-40,70-82) as a tcgen05
- * implicit GEMM over NHWC bf16:  y = act(conv(x, wt) + bias (+ residual)).
- *   x [b,h,w,cin_p] bf16; wt [cout_p][9][cin_k] bf16 (tap-major, cin_k = cin_p rounded up to 64, zero padded);
- *   bias fp32 [cout_p]; residual (optional) and y [b,h,w,cout_p] bf16.  act: 0 none, 1 ReLU, 2 LeakyReLU(0.01). */
-int gf_conv3x3_bf16(const void* x, const void* wt, const float* bias, const void* residual, void* y, int batch, int h,
+ * implicit GEMM over NHWC fp16 (fp32 accumulation; outputs saturate at +-65504):  y = act(conv(x, wt) + bias (+ residual)).
+ *   x [b,h,w,cin_p] fp16; wt [cout_p][9][cin_k] fp16 (tap-major, cin_k = cin_p rounded up to 64, zero padded);
+ *   bias fp32 [cout_p]; residual (optional) and y [b,h,w,cout_p] fp16.  act: 0 none, 1 ReLU, 2 LeakyReLU(0.01). */
+int gf_conv3x3_f16(const void* x, const void* wt, const float* bias, const void* residual, void* y, int batch, int h,
                     int w, int cin_p, int cout_p, int cin_k, int act, gf_stream_t stream);
 /* Generalisation used for the rest of the backbone: ksize 3 (pad 1) or 1 (pad 0), stride 1 or 2 (the stride-2 entry
  * convolutions and 1x1 downsample / FPN lateral convolutions of resnet_fpn.py:18-29, 62-82).  h, w are the INPUT sizes;
- * y is [batch, (h-1)/stride+1, (w-1)/stride+1, cout_p].  wt: [cout_p][ksize*ksize][cin_k] bf16. */
-int gf_conv_bf16(const void* x, const void* wt, const float* bias, const void* residual, void* y, int batch, int h, int w,
+ * y is [batch, (h-1)/stride+1, (w-1)/stride+1, cout_p].  wt: [cout_p][ksize*ksize][cin_k] fp16. */
+int gf_conv_f16(const void* x, const void* wt, const float* bias, const void* residual, void* y, int batch, int h, int w,
                  int cin_p, int cout_p, int cin_k, int ksize, int stride, int act, gf_stream_t stream);
 
 /* Backbone stem (resnet_fpn.py:58-60,102): 7x7 / stride 2 / pad 3 conv of the 1-channel fp32 image + folded BN +
- * ReLU -> NHWC bf16 [b, h/2, w/2, 128].  wperm = folded weights as [49 taps][128 channels] fp32. */
-int gf_stem_conv7x7_bf16(const float* img, const float* wperm, const float* bias, void* out, int batch, int h, int w,
+ * ReLU -> NHWC fp16 [b, h/2, w/2, 128].  wperm = folded weights as [49 taps][128 channels] fp32. */
+int gf_stem_conv7x7_f16(const float* img, const float* wperm, const float* bias, void* out, int batch, int h, int w,
                          gf_stream_t stream);
-/* FPN top-down merge (resnet_fpn.py:108-115): out = lateral + bilinear(src -> h x w, align_corners=True); NHWC bf16 */
-int gf_upsample_add_bf16(const void* lateral, const void* src, void* out, int batch, int h, int w, int hs, int ws,
+/* FPN top-down merge (resnet_fpn.py:108-115): out = lateral + bilinear(src -> h x w, align_corners=True); NHWC fp16 */
+int gf_upsample_add_f16(const void* lateral, const void* src, void* out, int batch, int h, int w, int hs, int ws,
                          int c, gf_stream_t stream);
 /* fp32 FFMA versions of the backbone operators for the accurate mode (golden-match parity runs): the same layers
  * (resnet_fpn.py:15-40, 58-118) on NHWC fp32, any channel count (the 1-channel 7x7 stem included).
  *   gf_conv_ref: ksize 1 / 3 / 7 (pad = ksize / 2), stride 1 / 2; x [b,h,w,cin]; wt [ksize*ksize][cin][cout] fp32 (BN
  *   folded); bias fp32 [cout] or null; residual / y [b,ho,wo,cout] with ho = (h + 2 pad - ksize) / stride + 1;
- *   act as gf_conv_bf16.  gf_upsample_add_ref: as gf_upsample_add_bf16 on fp32. */
+ *   act as gf_conv_f16.  gf_upsample_add_ref: as gf_upsample_add_f16 on fp32. */
 int gf_conv_ref(const float* x, const float* wt, const float* bias, const float* residual, float* y, int batch, int h,
                 int w, int cin, int cout, int ksize, int stride, int act, gf_stream_t stream);
 int gf_upsample_add_ref(const float* lateral, const float* src, float* out, int batch, int h, int w, int hs, int ws,
@@ -248,11 +248,11 @@ int gf_fine_layer(const float* x, const float* src, const void* wpack, const flo
 /* 5x5 (stride 4, pad 2) windows of the NHWC fine map around coarse tokens: out[m, w*w, c] */
 int gf_fine_gather(const float* fine_nhwc, int hf, int wf, int c, const int64_t* b_ids, const int64_t* tok_ids,
                    int64_t m, int wc, int stride, int window, float* out, gf_stream_t stream);
-/* same, reading a bf16 NHWC fine map (native output of the tcgen05 backbone) */
-int gf_fine_gather_bf16(const void* fine_nhwc, int hf, int wf, int c, const int64_t* b_ids, const int64_t* tok_ids,
+/* same, reading an fp16 NHWC fine map (native output of the tcgen05 backbone) */
+int gf_fine_gather_f16(const void* fine_nhwc, int hf, int wf, int c, const int64_t* b_ids, const int64_t* tok_ids,
                         int64_t m, int wc, int stride, int window, float* out, gf_stream_t stream);
-/* same, windows written as fp16 (exact for bf16 inputs in fp16 range): A operand of the fp16 merge_feat GEMM */
-int gf_fine_gather_bf16_f16(const void* fine_nhwc, int hf, int wf, int c, const int64_t* b_ids, const int64_t* tok_ids,
+/* same, windows written as fp16 (a copy): A operand of the fp16 merge_feat GEMM */
+int gf_fine_gather_f16_f16(const void* fine_nhwc, int hf, int wf, int c, const int64_t* b_ids, const int64_t* tok_ids,
                             int64_t m, int wc, int stride, int window, void* out, gf_stream_t stream);
 /* rows out[m,:] = feat[b_ids[m], tok_ids[m], :] */
 int gf_gather_rows(const float* feat, int64_t l, int c, const int64_t* b_ids, const int64_t* tok_ids, int64_t m,

@@ -75,7 +75,7 @@ def test_accurate_mode_matches_reference_golden(golden_dir, name):
 def test_mixed_batch_matches_reference_golden(golden_dir):
     """Dense + unrelated (noise matches, garbage homography) + shifted pair in ONE batch against the reference run:
     accurate mode (fp32 kernels) reproduces the reference's final match list of every sample exactly.  Product mode
-    (bf16 backbone, tf32 / fp16 operands) is a sanity bound here: on 12 x 16-token images with random weights the
+    (fp16 backbone, tf32 / fp16 operands) is a sanity bound here: on 12 x 16-token images with random weights the
     confidences are nearly flat (max ~3e-4), so mutual-nearest-neighbour decisions flip easily -> >= 60 % identical
     matches on the dense / shifted samples (measured 0.82 / 0.73) (the 480 x 640 product-mode bar is the 0.1 px corner error)."""
     g = _golden(golden_dir, "small_mixed")
@@ -83,7 +83,7 @@ def test_mixed_batch_matches_reference_golden(golden_dir):
     sd = synth.make_state_dict(7, bool(rnd))
     im0, im1 = synth.make_pairs(n, h, w, "mixed", seed0)
     want = {(int(b), *[int(v) for v in r]) for b, r in zip(g["m_bids"], np.concatenate([g["mkpts0_f"], g["mkpts1_f"]], 1))}
-    for mode, bar in ((dict(backbone="fp32", linear="ref", sim="ref"), 1.0), (dict(backbone="bf16", linear="tf32", sim="f16x3"), 0.6)):
+    for mode, bar in ((dict(backbone="fp32", linear="ref", sim="ref"), 1.0), (dict(backbone="f16", linear="tf32", sim="f16x3"), 0.6)):
         model = build_model(sd, 0.0, **mode)
         model.materialize = False
         d = model({"image0": im0.cuda(), "image1": im1.cuda()})
@@ -155,11 +155,11 @@ def test_rectangular_pair_and_batch_invariance():
 
 
 def test_full_size_dense_pair_corner_error(golden_dir):
-    """480x640 dense pair, product precision incl. bf16 backbone: downstream cv2.findHomography corner error
+    """480x640 dense pair, product precision incl. fp16 backbone: downstream cv2.findHomography corner error
     agrees with the reference run within 0.1 px (north star); match count within 10% of the reference's."""
     import cv2
     g = _golden(golden_dir, "full_dense_480x640")
-    model = build_model(synth.make_state_dict(0), 0.0, backbone="bf16", linear="tf32", sim="f16x3")
+    model = build_model(synth.make_state_dict(0), 0.0, backbone="f16", linear="tf32", sim="f16x3")
     model.materialize = False
     im0, im1 = synth.make_pairs(1, 480, 640, "dense", 0)
     data = model({"image0": im0.cuda(), "image1": im1.cuda()})
@@ -178,8 +178,8 @@ def test_full_size_dense_pair_corner_error(golden_dir):
 
 def test_backbone_fp32_reference_kernels_and_tcgen05_vs_oracle():
     """Both backbones of this library against the CPU oracle (resnet_fpn.py restated with F.conv2d / BatchNorm):
-    the fp32 FFMA kernels (accurate mode) to fp32 round-off, the bf16 tcgen05 implicit-GEMM path (product) within the
-    bf16 storage error of ~20 chained layers (3e-2 of the feature range, measured ~1e-2)."""
+    the fp32 FFMA kernels (accurate mode) to fp32 round-off, the fp16 tcgen05 implicit-GEMM path (product) within the
+    fp16 storage error of ~20 chained layers (3e-2 of the feature range, measured ~1e-2)."""
     from geoformer_b200 import engine, ops
     dev = torch.device("cuda:0")
     ops.ensure_init(dev)
@@ -192,12 +192,12 @@ def test_backbone_fp32_reference_kernels_and_tcgen05_vs_oracle():
     ref_c, ref_f = engine.backbone_forward(engine.PackedWeights(sd, dev, torch.float32), img.to(dev))
     assert ref_c.shape == want_c.shape and ref_f.shape == want_f.shape and ref_f.dtype == torch.float32
     assert rel(ref_c, want_c) <= 2e-5 and rel(ref_f, want_f) <= 2e-5, (rel(ref_c, want_c), rel(ref_f, want_f))
-    pw = engine.PackedWeights(sd, dev, torch.bfloat16)
+    pw = engine.PackedWeights(sd, dev, torch.float16)
     assert pw.bb_tc is not None and pw.bb_ref is None
     tc_c, tc_f = engine.backbone_forward(pw, img.to(dev))
-    assert tc_c.shape == want_c.shape and tc_f.shape == want_f.shape and tc_f.dtype == torch.bfloat16
+    assert tc_c.shape == want_c.shape and tc_f.shape == want_f.shape and tc_f.dtype == torch.float16
     e_c, e_f = rel(tc_c, want_c), rel(tc_f, want_f)
-    print("bf16 tcgen05 backbone vs fp32 oracle: coarse", e_c, "fine", e_f)
+    print("fp16 tcgen05 backbone vs fp32 oracle: coarse", e_c, "fine", e_f)
     assert e_c <= 3e-2 and e_f <= 3e-2, (e_c, e_f)
 
 
@@ -217,7 +217,7 @@ def test_fire_and_megadepth_shapes(hw):
     assert len(ref) > 50
     assert len(got & ref) >= 0.99 * len(ref), (len(got), len(ref), len(got & ref))
     # product precision on the same input: runs, finite, similar match count
-    model2 = build_model(sd, 0.0, backbone="bf16", linear="tf32", sim="f16x3")
+    model2 = build_model(sd, 0.0, backbone="f16", linear="tf32", sim="f16x3")
     model2.materialize = False
     d2 = model2({"image0": im0.cuda(), "image1": im1.cuda()})
     assert torch.isfinite(d2["mconf"]).all() and abs(d2["mkpts0_f"].shape[0] - len(ref)) <= 0.5 * len(ref) + 20

@@ -457,29 +457,29 @@ def test_fine_match_threshold_and_random(ops):
     (256, 196, 256, 200, False, 0), (196, 128, 200, 128, False, 0), (256, 256, 256, 256, False, 2),
 ])
 def test_conv3x3_tcgen05(ops, cin, cout, cin_p, cout_p, res, act):
-    """tcgen05 implicit-GEMM 3x3 conv (NHWC bf16, zero-padded channels, partial 8x16 tiles at the borders) vs
-    F.conv2d in fp32 on the same bf16-rounded operands.  Tolerance: bf16 output rounding (2^-8) on top of
-    fp32 accumulation -> 1e-2 of the output range."""
+    """tcgen05 implicit-GEMM 3x3 conv (NHWC fp16, zero-padded channels, partial 8x16 tiles at the borders) vs
+    F.conv2d in fp32 on the same fp16-rounded operands.  Tolerance: fp16 output rounding (2^-11) on top of
+    fp32 accumulation -> 1.5e-3 of the output range."""
     from geoformer_b200.engine import pack_conv3x3
     b, h, w = 2, 20, 40
-    x = rnd(b, cin, h, w, seed=1).bfloat16()
-    wgt = (rnd(cout, cin, 3, 3, seed=2) * (cin * 9) ** -0.5).bfloat16()
+    x = rnd(b, cin, h, w, seed=1).half()
+    wgt = (rnd(cout, cin, 3, 3, seed=2) * (cin * 9) ** -0.5).half()
     bias = rnd(cout, seed=3) * 0.1
-    r = rnd(b, cout, h, w, seed=4).bfloat16() if res else None
+    r = rnd(b, cout, h, w, seed=4).half() if res else None
     want = F.conv2d(x.float(), wgt.float(), bias, 1, 1)
     if res:
         want = want + r.float()
     want = F.relu(want) if act == 1 else (F.leaky_relu(want, 0.01) if act == 2 else want)
-    xp = torch.zeros(b, h, w, cin_p, dtype=torch.bfloat16); xp[..., :cin] = x.permute(0, 2, 3, 1)
+    xp = torch.zeros(b, h, w, cin_p, dtype=torch.float16); xp[..., :cin] = x.permute(0, 2, 3, 1)
     rp = None
     if res:
-        rp = torch.zeros(b, h, w, cout_p, dtype=torch.bfloat16); rp[..., :cout] = r.permute(0, 2, 3, 1)
+        rp = torch.zeros(b, h, w, cout_p, dtype=torch.float16); rp[..., :cout] = r.permute(0, 2, 3, 1)
     wt, bp = pack_conv3x3(wgt.float(), bias, cin_p, cout_p, "cuda")
     y = ops.conv3x3(dev(xp), wt, bp, None if rp is None else dev(rp), act).cpu().float()
     got = y[..., :cout].permute(0, 3, 1, 2)
     assert (y[..., cout:] == 0).all()                       # padded channels stay exactly zero
     err = (got - want).abs().max().item()
-    assert err <= 1e-2 * want.abs().max().item(), err
+    assert err <= 1.5e-3 * want.abs().max().item(), err
 
 
 @pytest.mark.parametrize("h,w,cin,cin_p,res", [(41, 40, 128, 128, True), (48, 17, 196, 200, False), (33, 64, 128, 128, False)])
@@ -488,18 +488,18 @@ def test_conv3x3_two_pixel_tiles_per_weight_box(ops, h, w, cin, cin_p, res):
     two accumulators); odd heights leave the second tile partially or completely outside the image."""
     from geoformer_b200.engine import pack_conv3x3
     b, cout = 2, 128
-    x = rnd(b, cin, h, w, seed=1).bfloat16()
-    wgt = (rnd(cout, cin, 3, 3, seed=2) * (cin * 9) ** -0.5).bfloat16()
+    x = rnd(b, cin, h, w, seed=1).half()
+    wgt = (rnd(cout, cin, 3, 3, seed=2) * (cin * 9) ** -0.5).half()
     bias = rnd(cout, seed=3) * 0.1
-    r = rnd(b, cout, h, w, seed=4).bfloat16() if res else None
+    r = rnd(b, cout, h, w, seed=4).half() if res else None
     want = F.conv2d(x.float(), wgt.float(), bias, 1, 1)
     want = F.relu(want + r.float()) if res else F.relu(want)
-    xp = torch.zeros(b, h, w, cin_p, dtype=torch.bfloat16); xp[..., :cin] = x.permute(0, 2, 3, 1)
+    xp = torch.zeros(b, h, w, cin_p, dtype=torch.float16); xp[..., :cin] = x.permute(0, 2, 3, 1)
     rp = dev(r.permute(0, 2, 3, 1)) if res else None
     wt, bp = pack_conv3x3(wgt.float(), bias, cin_p, cout, "cuda")
     got = ops.conv3x3(dev(xp), wt, bp, rp, 1).cpu().float().permute(0, 3, 1, 2)
     err = (got - want).abs().max().item()
-    assert err <= 1e-2 * want.abs().max().item(), err
+    assert err <= 1.5e-3 * want.abs().max().item(), err
 
 
 @pytest.mark.parametrize("cin,cout,cin_p,cout_p,ksize,stride,hw,act", [
@@ -512,22 +512,22 @@ def test_conv3x3_two_pixel_tiles_per_weight_box(ops, h, w, cin, cin_p, res):
 ])
 def test_conv_strided_and_1x1_tcgen05(ops, cin, cout, cin_p, cout_p, ksize, stride, hw, act):
     """The generalised implicit-GEMM conv (TMA element stride 2 on W/H for stride-2 layers; a single tap for 1x1)
-    vs F.conv2d in fp32 on the same bf16-rounded operands; same tolerance as the 3x3 / stride-1 test."""
+    vs F.conv2d in fp32 on the same fp16-rounded operands; same tolerance as the 3x3 / stride-1 test."""
     from geoformer_b200.engine import pack_conv3x3
     b, (h, w) = 2, hw
-    x = rnd(b, cin, h, w, seed=1).bfloat16()
-    wgt = (rnd(cout, cin, ksize, ksize, seed=2) * (cin * ksize * ksize) ** -0.5).bfloat16()
+    x = rnd(b, cin, h, w, seed=1).half()
+    wgt = (rnd(cout, cin, ksize, ksize, seed=2) * (cin * ksize * ksize) ** -0.5).half()
     bias = rnd(cout, seed=3) * 0.1
     want = F.conv2d(x.float(), wgt.float(), bias, stride, ksize // 2)
     want = F.relu(want) if act == 1 else want
-    xp = torch.zeros(b, h, w, cin_p, dtype=torch.bfloat16); xp[..., :cin] = x.permute(0, 2, 3, 1)
+    xp = torch.zeros(b, h, w, cin_p, dtype=torch.float16); xp[..., :cin] = x.permute(0, 2, 3, 1)
     wt, bp = pack_conv3x3(wgt.float(), bias, cin_p, cout_p, "cuda")
     y = ops.conv(dev(xp), wt, bp, None, act, stride).cpu().float()
     assert tuple(y.shape) == (b, want.shape[2], want.shape[3], cout_p)
     got = y[..., :cout].permute(0, 3, 1, 2)
     assert (y[..., cout:] == 0).all()
     err = (got - want).abs().max().item()
-    assert err <= 1e-2 * want.abs().max().item(), err
+    assert err <= 1.5e-3 * want.abs().max().item(), err
 
 
 # ------------------------------------------------------------------------------------------- fused coarse matching
@@ -604,8 +604,8 @@ def test_fused_coarse_matching_exact_ties_and_border(ops, border, thr):
 
 
 def test_stem_conv7x7(ops):
-    """Stem 7x7/s2 conv + folded BN + ReLU (FFMA kernel, fp32 image -> NHWC bf16) vs F.conv2d; odd sizes hit the
-    partial-tile and zero-padding paths.  Tolerance = bf16 output rounding."""
+    """Stem 7x7/s2 conv + folded BN + ReLU (FFMA kernel, fp32 image -> NHWC fp16) vs F.conv2d; odd sizes hit the
+    partial-tile and zero-padding paths.  Tolerance = fp16 output rounding."""
     b, h, w = 2, 70, 100
     img = torch.rand(b, 1, h, w, generator=torch.Generator().manual_seed(1))
     wgt = rnd(128, 1, 7, 7, seed=2) * 0.2
@@ -614,17 +614,17 @@ def test_stem_conv7x7(ops):
     wt7 = wgt.reshape(128, 49).t().contiguous()
     got = ops.stem_conv(dev(img), dev(wt7), dev(bias)).cpu().float().permute(0, 3, 1, 2)
     assert got.shape == want.shape
-    assert (got - want).abs().max().item() <= 6e-3 * want.abs().max().item()
+    assert (got - want).abs().max().item() <= 1e-3 * want.abs().max().item()
 
 
 def test_upsample_add(ops):
-    """FPN top-down merge: lateral + bilinear x2 (align_corners=True), NHWC bf16."""
+    """FPN top-down merge: lateral + bilinear x2 (align_corners=True), NHWC fp16."""
     b, hs, ws, c = 2, 15, 20, 200
-    lat = rnd(b, c, 2 * hs, 2 * ws, seed=1).bfloat16()
-    src = rnd(b, c, hs, ws, seed=2).bfloat16()
+    lat = rnd(b, c, 2 * hs, 2 * ws, seed=1).half()
+    src = rnd(b, c, hs, ws, seed=2).half()
     want = lat.float() + F.interpolate(src.float(), size=(2 * hs, 2 * ws), mode="bilinear", align_corners=True)
     got = ops.upsample_add(dev(lat.permute(0, 2, 3, 1)), dev(src.permute(0, 2, 3, 1))).cpu().float().permute(0, 3, 1, 2)
-    assert (got - want).abs().max().item() <= 1e-2 * want.abs().max().item()
+    assert (got - want).abs().max().item() <= 1.5e-3 * want.abs().max().item()
 
 
 # ------------------------------------------------------------------------------------------- fused fine layer

@@ -95,7 +95,7 @@ def test_forward_with_gpu_ransac_matches_cv2_mode():
     """Full forward with ransac='gpu' vs the default host cv2 mode on the same dense pairs: same set of samples get a
     homography, and the final fine matches overlap almost entirely (anchors / windows differ only at RANSAC's margin)."""
     from tests.test_gpu_forward import build_model, _match_set
-    model = build_model(synth.make_state_dict(0), 0.0, backbone="bf16", linear="tf32", sim="f16x3")
+    model = build_model(synth.make_state_dict(0), 0.0, backbone="f16", linear="tf32", sim="f16x3")
     model.materialize = False
     im0, im1 = synth.make_pairs(2, 240, 320, "dense", 0)
     d_cv = model({"image0": im0.cuda(), "image1": im1.cuda()})

@@ -42,10 +42,10 @@ def test_pack_conv_weights_tap_major_and_padding():
         w, b = _rnd(cout, cin, k, k, seed=7), _rnd(cout, seed=8)
         wt, bias = engine.pack_conv3x3(w, b, cin_p, cout_p, "cpu")
         cin_k = (cin_p + 63) // 64 * 64
-        assert wt.dtype == torch.bfloat16 and tuple(wt.shape) == (cout_p, k * k, cin_k) and tuple(bias.shape) == (cout_p,)
+        assert wt.dtype == torch.float16 and tuple(wt.shape) == (cout_p, k * k, cin_k) and tuple(bias.shape) == (cout_p,)
         for tap in range(k * k):
             dy, dx = divmod(tap, k)
-            assert torch.equal(wt[:cout, tap, :cin], w[:, :, dy, dx].bfloat16())
+            assert torch.equal(wt[:cout, tap, :cin], w[:, :, dy, dx].half())
         assert (wt[cout:] == 0).all() and (wt[:, :, cin:] == 0).all() and (bias[cout:] == 0).all()
         assert torch.equal(bias[:cout], b)
 

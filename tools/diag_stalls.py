@@ -9,7 +9,7 @@ depth = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 ransac = sys.argv[2] if len(sys.argv) > 2 else "cv2"
 nb = int(sys.argv[3]) if len(sys.argv) > 3 else 32
 dev = torch.device("cuda:0")
-model = bench.build_model(dev, "bf16", ransac)
+model = bench.build_model(dev, "f16", ransac)
 host = [synth.make_pairs(16, 480, 640, "dense", 100 * p) for p in range(2)]
 devb = [(a.to(dev), b.to(dev)) for a, b in host]
 rt = []

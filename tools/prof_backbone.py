@@ -10,7 +10,7 @@ sd = synth.make_state_dict(0)
 img = torch.rand(32, 1, 480, 640, device=dev)
 torch.backends.cudnn.benchmark = True
 ref = None
-for dt_name, dt in (("bf16", torch.bfloat16), ("fp16", torch.float16)):
+for dt_name, dt in (("f16", torch.float16), ("fp16", torch.float16)):
     for cpad in (1, 8, 16, 32, 64):
         os.environ["GF_BACKBONE_CPAD"] = str(cpad)
         pw = engine.PackedWeights(sd, dev, dt)

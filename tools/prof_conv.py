@@ -17,12 +17,12 @@ def timeit(fn, k=5):
 for (cin, cout, cp_in, cp_out, h, w) in [(128,128,128,128,240,320), (196,196,200,200,240,320), (196,128,200,128,240,320),
                                          (196,196,200,200,120,160), (256,256,256,256,120,160), (256,196,256,200,120,160), (256,256,256,256,60,80)]:
     b = 32
-    x = torch.randn(b, h, w, cp_in, device=dev).bfloat16()
+    x = torch.randn(b, h, w, cp_in, device=dev).half()
     wgt = torch.randn(cout, cin, 3, 3) * 0.03
     wt, bias = pack_conv3x3(wgt, torch.zeros(cout), cp_in, cp_out, dev)
     wc = torch.zeros(cp_out, cp_in, 3, 3); wc[:cout, :cin] = wgt
-    wc = wc.to(dev).bfloat16().contiguous(memory_format=torch.channels_last)
-    bc = torch.zeros(cp_out, device=dev).bfloat16()
+    wc = wc.to(dev).half().contiguous(memory_format=torch.channels_last)
+    bc = torch.zeros(cp_out, device=dev).half()
     xc = x.permute(0, 3, 1, 2)
     t_my = timeit(lambda: ops.conv3x3(x, wt, bias, None, 1))
     t_cd = timeit(lambda: F.relu_(F.conv2d(xc, wc, bc, 1, 1)))

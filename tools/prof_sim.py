@@ -8,7 +8,7 @@ dev = torch.device("cuda:0"); ops.ensure_init(dev)
 g = torch.Generator(device="cuda").manual_seed(0)
 f0 = torch.randn(16, 4800, 256, device=dev, generator=g) * 3 + 1.5
 f1 = torch.randn(16, 4800, 256, device=dev, generator=g) * 3 + 1.5
-x = torch.randn(32, 240, 320, 128, device=dev, generator=g).bfloat16()
+x = torch.randn(32, 240, 320, 128, device=dev, generator=g).half()
 wt, bias = pack_conv3x3(torch.randn(128, 128, 3, 3) * 0.03, torch.zeros(128), 128, 128, dev)
 a = torch.randn(153600, 256, device=dev, generator=g)
 w = torch.randn(512, 512, device=dev, generator=g) / 22
