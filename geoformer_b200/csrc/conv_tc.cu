@@ -10,7 +10,13 @@
 // The im2col never exists: for tap (dy,dx) and 64-channel block cb the A tile is ONE 4-D TMA box
 // {64 ch, 16 px, 8 rows, 1} at (cb*64, x0+dx-1, y0+dy-1, b); TMA zero-fills the padding halo and the channel tail,
 // and lands the box as 128 rows x 128 B with the 128B swizzle == a K-major UMMA operand.
-// Same warp-specialised persistent structure as gemm_tc.cu (TMA producer / single-thread MMA issuer / 4 epilogue
+// The kernel runs as 2-CTA thread-block clusters (r02): the two CTAs of a cluster work on neighbouring pixel tiles with the
+// SAME weights in lockstep; each loads half of every weight box and multicasts it into both CTAs' shared memory
+// (cp.async.bulk.tensor ... .multicast::cluster), which cuts the L2 -> SM operand traffic per CTA from A + B to A + B/2.
+// r01 measured the N >= 200 layers AT the L2 feed limit (102 B/clk/SM demanded, e.g. 29.4 GB per launch of the
+// 200 -> 200 @ 240x320 layer = 1.88 ms at ~16 TB/s while its MMA floor is 1.26 ms).  A stage is recycled when the MMAs of
+// BOTH CTAs have consumed it (tcgen05.commit ... .multicast::cluster on the empty barrier, count 2).
+// Same warp-specialised persistent structure as gemm_tc.cu (TMA producer / single-thread MMA issuer / 8 epilogue
 // warps, double-buffered TMEM accumulator); epilogue fuses bias, residual add, ReLU / LeakyReLU, fp16 pack and
 // writes 4-D TMA boxes {64 ch, 16 px, 2 rows}.
 #include "common.cuh"
@@ -29,6 +35,8 @@ struct ConvParams {
   int batch, h, w, cout_p;
   int kbc;                           // 64-channel k-blocks per tap
   int last_k;                        // MMAs (16 channels each) that carry real channels in the last k-block of a tap
+  int tail;                          // last_k == 1: the last k-block of a tap is loaded as a 32-byte-wide box (16 channels)
+                                     // through the *_t tensor maps instead of a mostly zero-filled 128-byte one
   int taps, stride, pad;             // 9 taps / pad 1 (3x3) or 1 tap / pad 0 (1x1); stride 1 or 2; h, w are OUTPUT sizes
   int tiles_x, tiles_y;
   int act;                           // 0 none, 1 relu, 2 leaky relu (0.01)
@@ -43,7 +51,7 @@ template <int BN, int MT = 1> struct ConvCfg {
   static constexpr int kStages = (BN <= 128) ? (MT == 2 ? 4 : 5) : 3;
   static constexpr int kAccStride = (BN <= 128) ? MT * 128 : 256;      // TMEM column offset of accumulator buffer 1
   static constexpr int kTmemCols = (BN <= 128 && MT == 1) ? 256 : 512;
-  static constexpr int kStaging = 4 * 2 * 4096;                   // per epilogue warp: 2 boxes of 32 px x 128 B
+  static constexpr int kStaging = 8 * 4096;                       // per epilogue warp: one box of 32 px x 128 B
   static constexpr int kSmem = kStages * kStage + kStaging + 1024 + 256;
 };
 
@@ -63,9 +71,10 @@ __device__ __forceinline__ uint32_t pack_f16(float a, float b) {
 }
 
 template <int BN, int MT = 1>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                  const __grid_constant__ CUtensorMap tmY, const ConvParams p) {
+                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmXt,
+                  const __grid_constant__ CUtensorMap tmWt, const ConvParams p) {
   using Cfg = ConvCfg<BN, MT>;
   static_assert(MT == 1 || BN <= 128, "two pixel tiles per step need 2 x 2 x BN TMEM columns");
   extern __shared__ uint8_t smem_raw[];
@@ -82,11 +91,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int total_tiles = p.batch * tiles_per_img;
   const int kblocks = p.taps * p.kbc;
 
-  if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmX); ptx::prefetch_tmap(&tmW); ptx::prefetch_tmap(&tmY); }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmX); ptx::prefetch_tmap(&tmW); ptx::prefetch_tmap(&tmY);
+    if (p.tail) { ptx::prefetch_tmap(&tmXt); ptx::prefetch_tmap(&tmWt); }
+  }
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < Cfg::kStages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
-      for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], 4); }
+      for (int i = 0; i < Cfg::kStages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 2); }   // 2: both CTAs' MMAs
+      for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], 8); }
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -94,69 +106,122 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
   ptx::tc_fence_before();
   __syncthreads();
+  ptx::cluster_sync();                     // the peer's barriers are initialised before anything is multicast into them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+  const int n_pairs = (total_tiles + 1) >> 1;
+  // tile of this CTA in iteration `pair`: 2 * pair + rank; the odd tail tile's partner recomputes the last tile (no store)
+  auto tile_of = [&](int pair, bool& ghost) -> int {
+    const int t = 2 * pair + (int)rank;
+    ghost = t >= total_tiles;
+    return ghost ? total_tiles - 1 : t;
+  };
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int pair = cluster_id; pair < n_pairs; pair += n_clusters) {
+        bool ghost;
+        const int t = tile_of(pair, ghost);
         const int b = t / tiles_per_img, r = t - b * tiles_per_img;
         const int y0 = (r / p.tiles_x) * (8 * MT), x0 = (r % p.tiles_x) * 16;
         for (int kb = 0; kb < kblocks; ++kb) {
           const int tap = kb / p.kbc, cb = kb - tap * p.kbc;
           const int dy = tap / 3, dx = tap - dy * 3;       // single-tap (1x1) convolutions: tap == 0, pad == 0
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);    // both CTAs have consumed this stage
           uint8_t* sa = smem + stage * Cfg::kStage;
-          ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStage);
+          if (p.tail && cb == p.kbc - 1) {
+            // channel tail (e.g. channels 192..199 of 200): 32-byte-wide boxes, a quarter of the bytes of a full k-block
+            ptx::mbar_expect_tx(&full_bar[stage], MT * 4096 + BN * 32);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+              ptx::tma_load_4d(sa + mt * 4096, &tmXt, &full_bar[stage], cb * 64, x0 * p.stride + dx - p.pad,
+                               (y0 + 8 * mt) * p.stride + dy - p.pad, b);
+            ptx::tma_load_3d_mcast(sa + Cfg::kStageA + rank * (BN / 2 * 32), &tmWt, &full_bar[stage], kb * 64,
+                                   (int)rank * (BN / 2), 0, (uint16_t)0x3);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStage);     // own A box(es) + BOTH halves of the weight box
           // the input map traverses W and H with element stride == conv stride: the box is 16 x 8 OUTPUT pixels
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt)
             ptx::tma_load_4d(sa + mt * 16384, &tmX, &full_bar[stage], cb * 64, x0 * p.stride + dx - p.pad,
                              (y0 + 8 * mt) * p.stride + dy - p.pad, b);
-          ptx::tma_load_3d(sa + Cfg::kStageA, &tmW, &full_bar[stage], kb * 64, 0, 0);
+          // this CTA's half of the weight box (rows [rank * BN/2, +BN/2)) lands in both CTAs of the cluster
+          ptx::tma_load_3d_mcast(sa + Cfg::kStageA + rank * (Cfg::kStageB / 2), &tmW, &full_bar[stage], kb * 64,
+                                 (int)rank * (BN / 2), 0, (uint16_t)0x3);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc(0 /*f16*/, 128, BN);
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // MMA issuer.  The WHOLE warp runs this loop converged and one elected lane issues: every operand (descriptors, TMEM
+    // address, barrier address) is then provably warp-uniform and lives in uniform registers.  Issuing from inside
+    // `if (lane == 0)` made ptxas wrap each tcgen05.mma / commit in an ELECT + R2UR + BRA.U.ANY loop (~35 extra SASS
+    // instructions): the issue thread needed 125-215 cycles per MMA, more than the 64-128 cycles the MMA itself takes -
+    // the kernel was ISSUE-bound (ncu r02: tensor pipe 49-52 % with the MMA warp never waiting for operands).
+    constexpr uint32_t idesc = ptx::umma_idesc(0 /*f16*/, 128, BN);
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t smem0 = __shfl_sync(0xffffffffu, ptx::smem_addr(smem), 0);
+    const uint32_t fb0 = smem0 + (uint32_t)(reinterpret_cast<uint8_t*>(full_bar) - smem);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int pair = cluster_id; pair < n_pairs; pair += n_clusters) {
+      ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tb + acc * Cfg::kAccStride;
+      int cb = 0;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
-        int cb = 0;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase);
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_addr(smem + stage * Cfg::kStage);
-          const uint64_t bdesc = ptx::umma_desc_sw128(sa + Cfg::kStageA);
-          // channel tail (e.g. 200 = 3 x 64 + 8): the zero-filled part of the last k-block is not multiplied
-          const int nk = (cb == p.kbc - 1) ? p.last_k : 4;
-          if (++cb == p.kbc) cb = 0;
+        const uint32_t sa = smem0 + stage * Cfg::kStage;
+        // channel tail (e.g. 200 = 3 x 64 + 8): the zero-filled part of the last k-block is not multiplied
+        const bool last = cb == p.kbc - 1;
+        const int nk = last ? p.last_k : 4;
+        if (++cb == p.kbc) cb = 0;
+        const uint32_t b_lo = ptx::umma_desc_lo(sa + Cfg::kStageA);
+        if (last && p.tail) {                            // one K = 16 step from the 32-byte-wide boxes
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            const uint64_t adesc_mt = ptx::umma_desc_sw128(sa + mt * 16384);
+          for (int mt = 0; mt < MT; ++mt)
+            if (ptx::elect_one())
+              ptx::umma_lo<1>(d_tmem + mt * 128, ptx::umma_desc_lo(sa + mt * 4096), b_lo, ptx::kDescHiSw32, idesc, kb ? 1u : 0u);
+        } else if (nk == 4) {                            // hot path: no per-MMA predicate, everything uniform
+          const uint32_t a_lo0 = ptx::umma_desc_lo(sa);
+          if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (k < nk) ptx::umma<1>(d_tmem + mt * 128, adesc_mt + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                ptx::umma_lo<1>(d_tmem + mt * 128, a_lo0 + mt * 1024 + 2 * k, b_lo + 2 * k, ptx::kDescHiSw128, idesc, (kb | k) ? 1u : 0u);
           }
-          ptx::umma_commit(&empty_bar[stage]);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        } else {                                         // channel tail of 32 or 48 channels (not in this network)
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint32_t a_lo = ptx::umma_desc_lo(sa + mt * 16384);
+            for (int k = 0; k < nk; ++k)
+              if (ptx::elect_one())
+                ptx::umma_lo<1>(d_tmem + mt * 128, a_lo + 2 * k, b_lo + 2 * k, ptx::kDescHiSw128, idesc, (kb | k) ? 1u : 0u);
+          }
         }
-        ptx::umma_commit(&tmem_full[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (ptx::elect_one()) ptx::umma_commit_mcast_addr(fb0 + (Cfg::kStages + stage) * 8, (uint16_t)0x3);   // empty_bar[stage] in both CTAs
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
+      if (ptx::elect_one()) ptx::umma_commit_addr(fb0 + (2 * Cfg::kStages + acc) * 8);                        // tmem_full[acc]
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
+    // 8 epilogue warps, two per TMEM lane quadrant, each taking every other 64-channel chunk: with 4 warps the epilogue
+    // (~3.6 us per chunk: residual staging, tcgen05.ld, bias / act / pack, TMA store) took longer than the MMAs of every
+    // layer with K < 256 (r02: N = 208 layers ran at 72 % of the sustained tensor peak, N = 128 at 74 %)
     const int quad = warp & 3;
-    uint8_t* wstage = staging + (warp - 2) * 8192;
+    const int ehalf = (warp - 2) >> 2;
+    uint8_t* box = staging + (warp - 2) * 4096;
     int acc = 0; uint32_t acc_phase = 0;
-    uint32_t box_ctr = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int pair = cluster_id; pair < n_pairs; pair += n_clusters) {
+      bool ghost;
+      const int t = tile_of(pair, ghost);
       const int b = t / tiles_per_img, r = t - b * tiles_per_img;
       const int ty0 = (r / p.tiles_x) * (8 * MT), x0 = (r % p.tiles_x) * 16;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
@@ -164,13 +229,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
       const int y0 = ty0 + 8 * mt;
-      if (y0 >= p.h) break;
+      if (y0 >= p.h || ghost) break;
       const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * Cfg::kAccStride + mt * 128;
-      for (int c0 = 0; c0 < BN; c0 += 64) {
+      for (int c0 = ehalf * 64; c0 < BN; c0 += 128) {
         if (c0 >= p.cout_p) break;
-        uint8_t* box = wstage + (box_ctr & 1) * 4096;
-        ++box_ctr;
-        if (lane == 0) ptx::bulk_wait_read<1>();
+        if (lane == 0) ptx::bulk_wait_read<0>();          // the previous store of this warp has read the box
         __syncwarp();
         if (p.residual) {
           // coalesced: 4 pixels x 128 B per instruction (pixel = it*4 + lane/8, 16-byte chunk = lane%8)
@@ -243,6 +306,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
   ptx::tc_fence_before();
   __syncthreads();
+  ptx::cluster_sync();                     // no CTA leaves while its peer may still multicast into it or signal its barriers
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -365,29 +429,53 @@ EncodeTiledFn encode_fn();
 // NHWC fp16 map: dims {C, W, H, B}; box {64, box_w, box_h, 1}; 128B swizzle; OOB -> 0 on load, clipped on store
 // `stride` > 1: W and H are traversed with that element stride; the box then spans box_w*stride x box_h*stride source
 // elements and delivers box_w x box_h of them (cuTensorMapEncodeTiled: ceil(boxDim / elementStride) per dimension).
-static int make_nhwc_tmap(CUtensorMap* m, const void* base, int c, int w, int h, int b, int box_w, int box_h, int stride = 1) {
+// box_c = 64 (128-byte rows, 128B swizzle) or 16 (32-byte rows, 32B swizzle: the channel-tail boxes)
+static int make_nhwc_tmap(CUtensorMap* m, const void* base, int c, int w, int h, int b, int box_w, int box_h, int stride = 1,
+                          int box_c = 64) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return gf_set_error(GF_ERR_DRIVER, "gf_init() was not called");
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)b};
   cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)c * 2 * w, (cuuint64_t)c * 2 * w * h};
-  cuuint32_t box[4] = {64, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return gf_set_error(GF_ERR_DRIVER, "cuTensorMapEncodeTiled(nhwc) failed");
   return GF_OK;
 }
 
+// weight map for the channel-tail boxes: dims {K, rows}; box {16 elements = 32 B, box_rows}; 32B swizzle
+static int make_wtail_tmap(CUtensorMap* m, const void* base, int64_t k, int64_t rows, int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return gf_set_error(GF_ERR_DRIVER, "gf_init() was not called");
+  cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, 1};
+  cuuint64_t strides[2] = {(cuuint64_t)k * 2, (cuuint64_t)k * 2 * (cuuint64_t)rows};
+  cuuint32_t box[3] = {16, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return gf_set_error(GF_ERR_DRIVER, "cuTensorMapEncodeTiled(weight tail) failed");
+  return GF_OK;
+}
+
 template <int BN, int MT = 1>
-static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const ConvParams& p,
-                       cudaStream_t stream) {
+static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const CUtensorMap& txt,
+                       const CUtensorMap& twt, const ConvParams& p, cudaStream_t stream) {
   using Cfg = ConvCfg<BN, MT>;
   auto kern = conv3x3_tc_kernel<BN, MT>;
   GF_SMEM_OPTIN(kern, Cfg::kSmem);
   const int tiles = p.batch * p.tiles_x * p.tiles_y;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 192, Cfg::kSmem, stream>>>(tx, tw, ty, p);
+  const int pairs = (tiles + 1) / 2, max_clusters = num_sms() / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * (pairs < max_clusters ? pairs : max_clusters));
+  cfg.blockDim = dim3(320); cfg.dynamicSmemBytes = Cfg::kSmem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, kern, tx, tw, ty, txt, twt, p) != cudaSuccess) return gf_set_error(GF_ERR_LAUNCH, cudaGetErrorString(cudaGetLastError()));
   g_launches++;
   GF_CHECK_LAUNCH();
   return GF_OK;
@@ -413,20 +501,26 @@ extern "C" int gf_conv_f16(const void* x, const void* wt, const float* bias, con
   int rc;
   if ((rc = make_nhwc_tmap(&tx, x, cin_p, w, h, batch, 16, 8, stride))) return rc;
   if ((rc = make_nhwc_tmap(&ty, y, cout_p, wo, ho, batch, 16, 2))) return rc;
-  if ((rc = make_tmap(&tw, wt, 2, taps * (int64_t)cin_k, cout_p, 1, taps * (int64_t)cin_k, 0, BN))) return rc;
+  if ((rc = make_tmap(&tw, wt, 2, taps * (int64_t)cin_k, cout_p, 1, taps * (int64_t)cin_k, 0, BN / 2))) return rc;   // half a weight box per CTA of the cluster
   ConvParams p{};
   p.bias = bias; p.residual = (const __half*)residual; p.batch = batch; p.h = ho; p.w = wo; p.cout_p = cout_p;
   p.kbc = cin_k / 64; p.taps = taps; p.stride = stride; p.pad = ksize / 2;
   p.last_k = (cin_p - (p.kbc - 1) * 64 + 15) / 16;
   if (p.last_k < 1 || p.last_k > 4) return gf_set_error(GF_ERR_ARG, "gf_conv_f16: cin_k must be cin_p rounded up to 64");
+  p.tail = (p.last_k == 1 && getenv("GF_CONV_NOTAIL") == nullptr) ? 1 : 0;
+  CUtensorMap txt = tx, twt = tw;           // only dereferenced when p.tail
+  if (p.tail) {
+    if ((rc = make_nhwc_tmap(&txt, x, cin_p, w, h, batch, 16, 8, stride, 16))) return rc;
+    if ((rc = make_wtail_tmap(&twt, wt, taps * (int64_t)cin_k, cout_p, BN / 2))) return rc;
+  }
   p.tiles_x = gf_cdiv(wo, 16); p.tiles_y = gf_cdiv(ho, 8); p.act = act;
   if (BN == 128 && ho >= 32 && getenv("GF_CONV_MT1") == nullptr) {     // two stacked pixel tiles per weight box
     p.tiles_y = gf_cdiv(ho, 16);
-    return launch_conv<128, 2>(tx, tw, ty, p, (cudaStream_t)stream);
+    return launch_conv<128, 2>(tx, tw, ty, txt, twt, p, (cudaStream_t)stream);
   }
-  if (BN == 128) return launch_conv<128>(tx, tw, ty, p, (cudaStream_t)stream);
-  if (BN == 208) return launch_conv<208>(tx, tw, ty, p, (cudaStream_t)stream);
-  return launch_conv<256>(tx, tw, ty, p, (cudaStream_t)stream);
+  if (BN == 128) return launch_conv<128>(tx, tw, ty, txt, twt, p, (cudaStream_t)stream);
+  if (BN == 208) return launch_conv<208>(tx, tw, ty, txt, twt, p, (cudaStream_t)stream);
+  return launch_conv<256>(tx, tw, ty, txt, twt, p, (cudaStream_t)stream);
 }
 
 extern "C" int gf_conv3x3_f16(const void* x, const void* wt, const float* bias, const void* residual, void* y,

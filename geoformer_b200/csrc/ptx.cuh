@@ -128,6 +128,40 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
   }
 }
+// Lean issue path: shared-memory descriptors as (low word, shared high word).  Only the low word (start address >> 4)
+// changes between the MMAs of a tile, so the per-MMA arithmetic is one 32-bit add that stays in a uniform register.
+// Call from a CONVERGED warp under `if (elect_one())` (see conv_tc.cu for why).
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);     // SBO 1024 B, version 1, SWIZZLE_128B
+constexpr uint32_t kDescHiSw32 = (256u >> 4) | (1u << 14) | (6u << 29);       // SBO 256 B, version 1, SWIZZLE_32B
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_byte_addr) {
+  return ((smem_byte_addr >> 4) & 0x3FFFu) | (1u << 16);
+}
+template <int KIND>
+__device__ __forceinline__ void umma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if constexpr (KIND == 0) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %4};\n\tmov.b64 db, {%2, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(desc_hi), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %4};\n\tmov.b64 db, {%2, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(desc_hi), "r"(accumulate) : "memory");
+  }
+}
+// A operand in tensor memory, B descriptor as (low word, high word)
+__device__ __forceinline__ void umma_ts_f16_lo(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 db, {%2, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(desc_hi), "r"(accumulate) : "memory");
+}
+
 // same with the A operand in tensor memory (".ts" form, kind::f16): A = this CTA's 128 lanes x (K / 2) 32-bit columns at
 // `tmem_a` holding two consecutive K elements per column (low half first); B from shared memory
 __device__ __forceinline__ void umma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -141,10 +175,68 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
 
+// variants taking the barrier's shared-memory address (lets the caller keep it in a uniform register)
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar_smem_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_smem_addr) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast_addr(uint32_t bar_smem_addr, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar_smem_addr), "h"(cta_mask) : "memory");
+}
+
 // same, arriving on the barrier at this offset in every CTA of `cta_mask` (slot release for multicast operands)
 __device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_addr(bar)), "h"(cta_mask) : "memory");
+}
+
+// ---------------- CTA pairs (cta_group::2): one MMA spans two SMs ----------------
+// D rows 0..127 live in CTA 0's tensor memory, rows 128..255 in CTA 1's; each CTA supplies its own 128 rows of A and HALF
+// of the N rows of B from its own shared memory (same offsets in both CTAs), so every weight byte is written to and read
+// from shared memory once per 256 output rows instead of once per 128.  Only the leader CTA (rank 0) issues.
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_slot, uint32_t ncols) {   // one whole warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(smem_slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address of the same offset in the pair's leader CTA
+// TMA loads of a CTA pair: the box lands in the ISSUING CTA's shared memory, the bytes are counted on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_addr(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_addr(bar) & kPeerBitMask),
+        "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_addr(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_addr(bar) & kPeerBitMask),
+        "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// kind::f16 MMA over the CTA pair (M = 256); descriptors as (low word, shared high word) like umma_lo
+__device__ __forceinline__ void umma2_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %4};\n\tmov.b64 db, {%2, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(desc_hi), "r"(accumulate) : "memory");
+}
+// arrive (once all earlier MMAs of this thread retired) on the barrier at this offset in the CTAs of `cta_mask`
+__device__ __forceinline__ void umma2_commit_mcast_addr(uint32_t bar_smem_addr, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar_smem_addr), "h"(cta_mask) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_addr(bar)), "r"(rank) : "memory");
 }
 
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive 32-bit columns (thread t <- lane t)
@@ -205,6 +297,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_byte_addr) {
   d |= static_cast<uint64_t>(1024 >> 4) << 32;                  // SBO = 1024 B, bits [32,46)
   d |= static_cast<uint64_t>(1) << 46;                          // descriptor version (Blackwell)
   d |= static_cast<uint64_t>(2) << 61;                          // layout: SWIZZLE_128B
+  return d;
+}
+
+// Same for a K-major tile that is only 32 bytes wide (one K = 16 step of 16-bit elements): rows of 32 bytes with the
+// 32-byte swizzle (TMA box {32 B, rows} with CU_TENSOR_MAP_SWIZZLE_32B); 8-row atoms every 256 bytes.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_byte_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_byte_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1) << 16;                          // LBO (ignored)
+  d |= static_cast<uint64_t>(256 >> 4) << 32;                   // SBO = 256 B
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;                          // layout: SWIZZLE_32B
   return d;
 }
 
