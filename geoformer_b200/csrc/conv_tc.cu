@@ -10,12 +10,17 @@
 // The im2col never exists: for tap (dy,dx) and 64-channel block cb the A tile is ONE 4-D TMA box
 // {64 ch, 16 px, 8 rows, 1} at (cb*64, x0+dx-1, y0+dy-1, b); TMA zero-fills the padding halo and the channel tail,
 // and lands the box as 128 rows x 128 B with the 128B swizzle == a K-major UMMA operand.
-// The kernel runs as 2-CTA thread-block clusters (r02): the two CTAs of a cluster work on neighbouring pixel tiles with the
-// SAME weights in lockstep; each loads half of every weight box and multicasts it into both CTAs' shared memory
-// (cp.async.bulk.tensor ... .multicast::cluster), which cuts the L2 -> SM operand traffic per CTA from A + B to A + B/2.
-// r01 measured the N >= 200 layers AT the L2 feed limit (102 B/clk/SM demanded, e.g. 29.4 GB per launch of the
-// 200 -> 200 @ 240x320 layer = 1.88 ms at ~16 TB/s while its MMA floor is 1.26 ms).  A stage is recycled when the MMAs of
-// BOTH CTAs have consumed it (tcgen05.commit ... .multicast::cluster on the empty barrier, count 2).
+// CTA pairs (r02).  ncu on the single-CTA kernel (profiles/r02_conv_ncu_before_pair.txt): tensor pipe 49-52 % (74 % for the
+// K = N = 256 layer) while the MMA warp never waited for operands and the epilogue warps waited for the MMAs - neither the
+// L2 feed (2-CTA weight multicast: no change), nor the epilogue (8 instead of 4 warps: no change), nor the issue rate (lean
+// uniform-register issue loop: no change) was the limit.  What fits all layers is the shared-memory port: with M = 128
+// per MMA every weight byte is written once (TMA) and read once per 128 output pixels, e.g. N = 256: 48 KB written + 48 KB
+// read per 64-channel k-block = 768 cycles at 128 B/clk for 512 cycles of MMA.  Hence tcgen05.mma.cta_group::2: the two
+// CTAs of a cluster take neighbouring pixel tiles (M = 256 across the pair); each holds its own 128 pixels of A and only
+// HALF of the weight rows, so weight traffic through each SM's shared memory is halved (N = 256: 64 KB per k-block =
+// 512 cycles).  The leader CTA (rank 0) issues every MMA; both CTAs' TMA loads count on the leader's full barrier; MMA
+// completion is multicast to both CTAs' empty / tmem_full barriers; the peer's epilogue releases its accumulator with a
+// remote arrive on the leader's tmem_empty barrier.
 // Same warp-specialised persistent structure as gemm_tc.cu (TMA producer / single-thread MMA issuer / 8 epilogue
 // warps, double-buffered TMEM accumulator); epilogue fuses bias, residual add, ReLU / LeakyReLU, fp16 pack and
 // writes 4-D TMA boxes {64 ch, 16 px, 2 rows}.
@@ -46,9 +51,9 @@ struct ConvParams {
 // i.e. 48 KB instead of 64 KB of operands per 2 x 128 pixels (the N = 128 layers are bound by the L2 -> smem feed).
 template <int BN, int MT = 1> struct ConvCfg {
   static constexpr int kStageA = MT * 128 * 128;
-  static constexpr int kStageB = BN * 128;
+  static constexpr int kStageB = (BN / 2) * 128;                  // this CTA's half of the weight rows
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (BN <= 128) ? (MT == 2 ? 4 : 5) : 3;
+  static constexpr int kStages = (BN <= 128) ? (MT == 2 ? 4 : 6) : 5;
   static constexpr int kAccStride = (BN <= 128) ? MT * 128 : 256;      // TMEM column offset of accumulator buffer 1
   static constexpr int kTmemCols = (BN <= 128 && MT == 1) ? 256 : 512;
   static constexpr int kStaging = 8 * 4096;                       // per epilogue warp: one box of 32 px x 128 B
@@ -97,12 +102,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < Cfg::kStages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 2); }   // 2: both CTAs' MMAs
-      for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], 8); }
+      for (int i = 0; i < Cfg::kStages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+      // tmem_empty is only used in the leader CTA: 8 epilogue warps of each CTA of the pair arrive there
+      for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], 16); }
       ptx::fence_barrier_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_alloc2(tmem_slot, Cfg::kTmemCols);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -120,7 +126,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer: whole warp converged, one elected lane issues (uniform-register operands)
+    {
       int stage = 0; uint32_t phase = 0;
       for (int pair = cluster_id; pair < n_pairs; pair += n_clusters) {
         bool ghost;
@@ -130,86 +137,85 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int kb = 0; kb < kblocks; ++kb) {
           const int tap = kb / p.kbc, cb = kb - tap * p.kbc;
           const int dy = tap / 3, dx = tap - dy * 3;       // single-tap (1x1) convolutions: tap == 0, pad == 0
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);    // both CTAs have consumed this stage
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);    // the pair's MMAs have consumed this stage (commit is multicast)
           uint8_t* sa = smem + stage * Cfg::kStage;
-          if (p.tail && cb == p.kbc - 1) {
+          const bool tail_blk = p.tail && cb == p.kbc - 1;
+          if (ptx::elect_one()) {
+          // the LEADER's full barrier counts the bytes of both CTAs (each: own A box(es) + own half of the weight box)
+          if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * (tail_blk ? MT * 4096 + (BN / 2) * 32 : Cfg::kStage));
+          if (tail_blk) {
             // channel tail (e.g. channels 192..199 of 200): 32-byte-wide boxes, a quarter of the bytes of a full k-block
-            ptx::mbar_expect_tx(&full_bar[stage], MT * 4096 + BN * 32);
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
-              ptx::tma_load_4d(sa + mt * 4096, &tmXt, &full_bar[stage], cb * 64, x0 * p.stride + dx - p.pad,
-                               (y0 + 8 * mt) * p.stride + dy - p.pad, b);
-            ptx::tma_load_3d_mcast(sa + Cfg::kStageA + rank * (BN / 2 * 32), &tmWt, &full_bar[stage], kb * 64,
-                                   (int)rank * (BN / 2), 0, (uint16_t)0x3);
-            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
-            continue;
-          }
-          ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStage);     // own A box(es) + BOTH halves of the weight box
-          // the input map traverses W and H with element stride == conv stride: the box is 16 x 8 OUTPUT pixels
+              ptx::tma_load_4d_2sm(sa + mt * 4096, &tmXt, &full_bar[stage], cb * 64, x0 * p.stride + dx - p.pad,
+                                   (y0 + 8 * mt) * p.stride + dy - p.pad, b);
+            ptx::tma_load_3d_2sm(sa + Cfg::kStageA, &tmWt, &full_bar[stage], kb * 64, (int)rank * (BN / 2), 0);
+          } else {
+            // the input map traverses W and H with element stride == conv stride: the box is 16 x 8 OUTPUT pixels
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt)
-            ptx::tma_load_4d(sa + mt * 16384, &tmX, &full_bar[stage], cb * 64, x0 * p.stride + dx - p.pad,
-                             (y0 + 8 * mt) * p.stride + dy - p.pad, b);
-          // this CTA's half of the weight box (rows [rank * BN/2, +BN/2)) lands in both CTAs of the cluster
-          ptx::tma_load_3d_mcast(sa + Cfg::kStageA + rank * (Cfg::kStageB / 2), &tmW, &full_bar[stage], kb * 64,
-                                 (int)rank * (BN / 2), 0, (uint16_t)0x3);
+            for (int mt = 0; mt < MT; ++mt)
+              ptx::tma_load_4d_2sm(sa + mt * 16384, &tmX, &full_bar[stage], cb * 64, x0 * p.stride + dx - p.pad,
+                                   (y0 + 8 * mt) * p.stride + dy - p.pad, b);
+            ptx::tma_load_3d_2sm(sa + Cfg::kStageA, &tmW, &full_bar[stage], kb * 64, (int)rank * (BN / 2), 0);
+          }
+          }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // MMA issuer.  The WHOLE warp runs this loop converged and one elected lane issues: every operand (descriptors, TMEM
-    // address, barrier address) is then provably warp-uniform and lives in uniform registers.  Issuing from inside
-    // `if (lane == 0)` made ptxas wrap each tcgen05.mma / commit in an ELECT + R2UR + BRA.U.ANY loop (~35 extra SASS
-    // instructions): the issue thread needed 125-215 cycles per MMA, more than the 64-128 cycles the MMA itself takes -
-    // the kernel was ISSUE-bound (ncu r02: tensor pipe 49-52 % with the MMA warp never waiting for operands).
-    constexpr uint32_t idesc = ptx::umma_idesc(0 /*f16*/, 128, BN);
-    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const uint32_t smem0 = __shfl_sync(0xffffffffu, ptx::smem_addr(smem), 0);
-    const uint32_t fb0 = smem0 + (uint32_t)(reinterpret_cast<uint8_t*>(full_bar) - smem);
-    int stage = 0; uint32_t phase = 0;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int pair = cluster_id; pair < n_pairs; pair += n_clusters) {
-      ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-      ptx::tc_fence_after();
-      const uint32_t d_tmem = tb + acc * Cfg::kAccStride;
-      int cb = 0;
-      for (int kb = 0; kb < kblocks; ++kb) {
-        ptx::mbar_wait(&full_bar[stage], phase);
+    // MMA issuer: only in the leader CTA of the pair.  The WHOLE warp runs this loop converged and one elected lane
+    // issues: every operand (descriptors, TMEM address, barrier address) is then provably warp-uniform and lives in
+    // uniform registers (issuing from inside `if (lane == 0)` made ptxas wrap each tcgen05.mma / commit in an
+    // ELECT + R2UR + BRA.U.ANY loop of ~35 SASS instructions).
+    if (rank == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc(0 /*f16*/, 256, BN);      // M = 256 over the CTA pair
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t smem0 = __shfl_sync(0xffffffffu, ptx::smem_addr(smem), 0);
+      const uint32_t fb0 = smem0 + (uint32_t)(reinterpret_cast<uint8_t*>(full_bar) - smem);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int pair = cluster_id; pair < n_pairs; pair += n_clusters) {
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // both CTAs' epilogues have drained this accumulator
         ptx::tc_fence_after();
-        const uint32_t sa = smem0 + stage * Cfg::kStage;
-        // channel tail (e.g. 200 = 3 x 64 + 8): the zero-filled part of the last k-block is not multiplied
-        const bool last = cb == p.kbc - 1;
-        const int nk = last ? p.last_k : 4;
-        if (++cb == p.kbc) cb = 0;
-        const uint32_t b_lo = ptx::umma_desc_lo(sa + Cfg::kStageA);
-        if (last && p.tail) {                            // one K = 16 step from the 32-byte-wide boxes
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt)
-            if (ptx::elect_one())
-              ptx::umma_lo<1>(d_tmem + mt * 128, ptx::umma_desc_lo(sa + mt * 4096), b_lo, ptx::kDescHiSw32, idesc, kb ? 1u : 0u);
-        } else if (nk == 4) {                            // hot path: no per-MMA predicate, everything uniform
+        const uint32_t d_tmem = tb + acc * Cfg::kAccStride;
+        int cb = 0;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);              // both CTAs' boxes of this stage have landed
+          ptx::tc_fence_after();
+          const uint32_t sa = smem0 + stage * Cfg::kStage;
+          // channel tail (e.g. 200 = 3 x 64 + 8): the zero-filled part of the last k-block is not multiplied
+          const bool last = cb == p.kbc - 1;
+          const int nk = last ? p.last_k : 4;
+          if (++cb == p.kbc) cb = 0;
+          const uint32_t b_lo = ptx::umma_desc_lo(sa + Cfg::kStageA);
           const uint32_t a_lo0 = ptx::umma_desc_lo(sa);
-          if (ptx::elect_one()) {
+          if (last && p.tail) {                            // one K = 16 step from the 32-byte-wide boxes
+            if (ptx::elect_one()) {
 #pragma unroll
+              for (int mt = 0; mt < MT; ++mt)
+                ptx::umma2_f16_lo(d_tmem + mt * 128, a_lo0 + mt * 256, b_lo, ptx::kDescHiSw32, idesc, kb ? 1u : 0u);
+            }
+          } else if (nk == 4) {                            // hot path: no per-MMA predicate, everything uniform
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  ptx::umma2_f16_lo(d_tmem + mt * 128, a_lo0 + mt * 1024 + 2 * k, b_lo + 2 * k, ptx::kDescHiSw128, idesc, (kb | k) ? 1u : 0u);
+            }
+          } else {                                         // channel tail of 32 or 48 channels (not in this network)
             for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                ptx::umma_lo<1>(d_tmem + mt * 128, a_lo0 + mt * 1024 + 2 * k, b_lo + 2 * k, ptx::kDescHiSw128, idesc, (kb | k) ? 1u : 0u);
+              for (int k = 0; k < nk; ++k)
+                if (ptx::elect_one())
+                  ptx::umma2_f16_lo(d_tmem + mt * 128, a_lo0 + mt * 1024 + 2 * k, b_lo + 2 * k, ptx::kDescHiSw128, idesc, (kb | k) ? 1u : 0u);
           }
-        } else {                                         // channel tail of 32 or 48 channels (not in this network)
-          for (int mt = 0; mt < MT; ++mt) {
-            const uint32_t a_lo = ptx::umma_desc_lo(sa + mt * 16384);
-            for (int k = 0; k < nk; ++k)
-              if (ptx::elect_one())
-                ptx::umma_lo<1>(d_tmem + mt * 128, a_lo + 2 * k, b_lo + 2 * k, ptx::kDescHiSw128, idesc, (kb | k) ? 1u : 0u);
-          }
+          if (ptx::elect_one()) ptx::umma2_commit_mcast_addr(fb0 + (Cfg::kStages + stage) * 8, (uint16_t)0x3);   // empty_bar[stage], both CTAs
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        if (ptx::elect_one()) ptx::umma_commit_mcast_addr(fb0 + (Cfg::kStages + stage) * 8, (uint16_t)0x3);   // empty_bar[stage] in both CTAs
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        if (ptx::elect_one()) ptx::umma2_commit_mcast_addr(fb0 + (2 * Cfg::kStages + acc) * 8, (uint16_t)0x3);    // tmem_full[acc], both CTAs
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (ptx::elect_one()) ptx::umma_commit_addr(fb0 + (2 * Cfg::kStages + acc) * 8);                        // tmem_full[acc]
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // 8 epilogue warps, two per TMEM lane quadrant, each taking every other 64-channel chunk: with 4 warps the epilogue
@@ -299,17 +305,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) ptx::mbar_arrive_cluster(&tmem_empty[acc], 0);     // the pair's MMA issuer lives in the leader CTA
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) ptx::bulk_wait<0>();
   }
   ptx::tc_fence_before();
   __syncthreads();
-  ptx::cluster_sync();                     // no CTA leaves while its peer may still multicast into it or signal its barriers
+  ptx::cluster_sync();                     // no CTA leaves (or frees tensor memory) while its peer may still use it
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    ptx::tmem_dealloc2(tmem_base, Cfg::kTmemCols);
   }
 }
 

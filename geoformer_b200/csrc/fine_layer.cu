@@ -198,26 +198,36 @@ fine_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
+    // The whole warp runs this loop converged and one elected lane issues (operands stay in uniform registers; from
+    // inside `if (lane == 0)` ptxas wraps every tcgen05.mma in an ELECT / R2UR / BRA.U.ANY loop of ~35 instructions,
+    // which put ~100 cycles of issue latency per MMA on this kernel's serial GEMM chain).
+    {
       constexpr uint32_t id_tf32 = ptx::umma_idesc(2, 128, 128);
       constexpr uint32_t id_f16 = ptx::umma_idesc(0, 128, 128);
-      const uint32_t s_r1 = ptx::smem_addr(smem + R1), s_r2 = ptx::smem_addr(smem + R2), s_r3 = ptx::smem_addr(smem + R3);
-      const uint32_t s_ring = ptx::smem_addr(smem + RING);
+      const uint32_t smem0 = __shfl_sync(0xffffffffu, ptx::smem_addr(smem), 0);
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t s_r1 = smem0 + R1, s_r2 = smem0 + R2, s_r3 = smem0 + R3, s_ring = smem0 + RING;
+      const uint32_t bar0 = smem0 + BARS;                // full_bar[0]; the other barriers follow in declaration order
+      auto bar_addr = [&](const uint64_t* b) -> uint32_t { return bar0 + (uint32_t)((const uint8_t*)b - (const uint8_t*)full_bar); };
       int stage = 0; uint32_t phase = 0;
       // one weight block against one resident A block: 4 MMAs (32 bytes of K each)
       auto step = [&](int kind, uint32_t a_addr, uint32_t d_col, bool first) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        const uint64_t adesc = ptx::umma_desc_sw128(a_addr);
-        const uint64_t bdesc = ptx::umma_desc_sw128(s_ring + stage * BLK);
+        const uint32_t a_lo = ptx::umma_desc_lo(a_addr), b_lo = ptx::umma_desc_lo(s_ring + stage * BLK);
+        if (ptx::elect_one()) {
+          if (kind == 0) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (kind == 0) ptx::umma<0>(tmem_base + d_col, adesc + 2 * k, bdesc + 2 * k, id_tf32, (first && k == 0) ? 0u : 1u);
-          else           ptx::umma<1>(tmem_base + d_col, adesc + 2 * k, bdesc + 2 * k, id_f16, (first && k == 0) ? 0u : 1u);
+            for (int k = 0; k < 4; ++k) ptx::umma_lo<0>(tb + d_col, a_lo + 2 * k, b_lo + 2 * k, ptx::kDescHiSw128, id_tf32, (first && k == 0) ? 0u : 1u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ptx::umma_lo<1>(tb + d_col, a_lo + 2 * k, b_lo + 2 * k, ptx::kDescHiSw128, id_f16, (first && k == 0) ? 0u : 1u);
+          }
+          ptx::umma_commit_addr(bar_addr(&empty_bar[stage]));
         }
-        ptx::umma_commit(&empty_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       };
+      auto commit = [&](const uint64_t* b) { if (ptx::elect_one()) ptx::umma_commit_addr(bar_addr(b)); };
       // GEMM0 of iteration `i`: q from x, k|v from src (== x for a self layer)
       auto gemm0 = [&](int i) {
         ptx::mbar_wait(x_full, i & 1);
@@ -227,7 +237,7 @@ fine_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const uint32_t a0 = p.cross ? s_r2 : s_r1;
         for (int nc = 1; nc < 3; ++nc)
           for (int kb = 0; kb < 4; ++kb) step(0, a0 + kb * BLK, D0 + nc * 128, kb == 0);
-        ptx::umma_commit(&d_full[0]);
+        commit(&d_full[0]);
       };
       gemm0(0);
       int it = 0;
@@ -238,24 +248,24 @@ fine_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         ptx::tc_fence_after();
         for (int nc = 0; nc < 2; ++nc)
           for (int kb = 0; kb < 4; ++kb) step(0, s_r1 + kb * BLK, D2 + nc * 128, kb == 0);
-        ptx::umma_commit(r1_free);                       // last read of the x tile: R1 may take the next one
+        commit(r1_free);                                 // last read of the x tile: R1 may take the next one
         // GEMM1: merge(message)
         ptx::mbar_wait(&a_full[0], par);
         ptx::tc_fence_after();
         for (int kb = 0; kb < 2; ++kb) step(1, s_r3 + kb * BLK, D1, kb == 0);
-        ptx::umma_commit(&d_full[1]);
+        commit(&d_full[1]);
         // GEMM2, m1 half (f16) into the same accumulator
         ptx::mbar_wait(&a_full[1], par);
         ptx::tc_fence_after();
         for (int nc = 0; nc < 2; ++nc)
           for (int kb = 0; kb < 2; ++kb) step(1, s_r2 + 2 * BLK + kb * BLK, D2 + nc * 128, false);
-        ptx::umma_commit(&d_full[2]);
+        commit(&d_full[2]);
         // GEMM3: MLP down, into the columns of the (consumed) merge accumulator
         ptx::mbar_wait(&a_full[2], par);
         ptx::tc_fence_after();
         for (int kb = 0; kb < 4; ++kb) step(1, s_r2 + kb * BLK, D3, kb == 0);
-        ptx::umma_commit(&d_full[3]);
-        ptx::umma_commit(r2_free);                       // last read of R2 (hidden): it may take the next src tile
+        commit(&d_full[3]);
+        commit(r2_free);                                 // last read of R2 (hidden): it may take the next src tile
         // GEMM0 of the next tile: D2 [0,256) was drained before a_full[2], [256,384) before d0_free -> runs under E3
         if (t + (int)gridDim.x < p.tiles) gemm0(it + 1);
       }

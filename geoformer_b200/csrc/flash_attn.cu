@@ -138,23 +138,31 @@ geo_flash_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
     // ------------------------------------ MMA issuer ------------------------------------
     // issue order S0, S1, P V0, S2, P V1, ...: S(t) lands in the buffer whose first 32 columns held P(t-2); the tensor
     // core executes in issue order, so it is written only after P V(t-2) has read them
-    if (lane == 0) {
+    // (whole warp converged, one elected lane issues: operands stay in uniform registers - see conv_tc.cu)
+    {
       constexpr uint32_t idesc = ptx::umma_idesc(0 /*f16*/, kBQ, 64);
       constexpr uint32_t idesc_l = ptx::umma_idesc(0 /*f16*/, kBQ, 16);
       ptx::mbar_wait(q_ready, 0);
       ptx::tc_fence_after();
-      const uint64_t dOnes = ptx::umma_desc_sw128(ptx::smem_addr(sOnes));
+      const uint32_t smem0 = __shfl_sync(0xffffffffu, ptx::smem_addr(smem), 0);
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t bar0 = smem0 + (uint32_t)((uint8_t*)bars - smem);
+      auto bar_addr = [&](const uint64_t* b) -> uint32_t { return bar0 + (uint32_t)((const uint8_t*)b - (const uint8_t*)bars); };
+      const uint32_t ones_lo = ptx::umma_desc_lo(smem0 + (uint32_t)(sOnes - smem));
+      const uint32_t sK0 = smem0, sV0 = smem0 + kRing * kKBytes;
       for (int t = 0; t <= T; ++t) {
         if (t < T) {
           const int ks = t % kRing; const uint32_t kph = (t / kRing) & 1;
           const int sb = t & 1;
           ptx::mbar_wait(&k_full[ks], kph);
           ptx::tc_fence_after();
-          const uint64_t bd = ptx::umma_desc_sw128(ptx::smem_addr(sK + ks * kKBytes));
+          const uint32_t b_lo = ptx::umma_desc_lo(sK0 + ks * kKBytes);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) ptx::umma_ts_f16(tmem_base + sb * 64, tmem_base + kColQ + 8 * k, bd + 2 * k, idesc, k ? 1u : 0u);
-          ptx::umma_commit(&k_empty[ks]);
-          ptx::umma_commit(&s_full[sb]);
+            for (int k = 0; k < 4; ++k) ptx::umma_ts_f16_lo(tb + sb * 64, tb + kColQ + 8 * k, b_lo + 2 * k, ptx::kDescHiSw128, idesc, k ? 1u : 0u);
+            ptx::umma_commit_addr(bar_addr(&k_empty[ks]));
+            ptx::umma_commit_addr(bar_addr(&s_full[sb]));
+          }
         }
         if (t > 0) {
           const int u = t - 1;
@@ -163,16 +171,19 @@ geo_flash_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
           ptx::mbar_wait(&p_full[pb], pph);
           ptx::mbar_wait(&v_full[vs], vph);
           ptx::tc_fence_after();
-          const uint64_t bd = ptx::umma_desc_sw128(ptx::smem_addr(sV + vs * kVBytes));
+          const uint32_t b_lo = ptx::umma_desc_lo(sV0 + vs * kVBytes);
+          const uint32_t acc0 = u > 0 ? 1u : 0u;
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) ptx::umma_ts_f16(tmem_base + kColO, tmem_base + pb * 64 + 8 * k, bd + 2 * k, idesc, (u > 0 || k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) ptx::umma_ts_f16_lo(tb + kColO, tb + pb * 64 + 8 * k, b_lo + 2 * k, ptx::kDescHiSw128, idesc, k ? 1u : acc0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) ptx::umma_ts_f16(tmem_base + kColL, tmem_base + pb * 64 + 8 * k, dOnes + 2 * k, idesc_l, (u > 0 || k) ? 1u : 0u);
-          ptx::umma_commit(&v_empty[vs]);
-          ptx::umma_commit(&pv_done[pb]);
+            for (int k = 0; k < 4; ++k) ptx::umma_ts_f16_lo(tb + kColL, tb + pb * 64 + 8 * k, ones_lo + 2 * k, ptx::kDescHiSw128, idesc_l, k ? 1u : acc0);
+            ptx::umma_commit_addr(bar_addr(&v_empty[vs]));
+            ptx::umma_commit_addr(bar_addr(&pv_done[pb]));
+          }
         }
       }
-      ptx::umma_commit(o_full);
+      if (ptx::elect_one()) ptx::umma_commit_addr(bar_addr(o_full));
     }
   } else {
     // ------------------------------------ softmax / epilogue (warps 2..5) ------------------------------------

@@ -128,7 +128,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
+    // whole warp converged, one elected lane issues (uniform-register operands, see conv_tc.cu)
+    {
       int stage = 0; uint32_t phase = 0;
       for (int t = t_first; t < total_tiles; t += t_step) {
         const int n_blk = t % p.tiles_n;
@@ -139,14 +140,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + kStageABytes;
-          ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          if (kb < p.kblocks1) ptx::tma_load_3d(sa, &tmA, &full_bar[stage], kb * BKE, m_blk * kBM, batch);
-          else                 ptx::tma_load_3d(sa, &tmA2, &full_bar[stage], (kb - p.kblocks1) * BKE, m_blk * kBM, batch);
-          if constexpr (CL == 2) {
-            ptx::tma_load_3d_mcast(sb + cta_rank * (BN / 2) * 128, &tmB, &full_bar[stage], kb * BKE,
-                                   n_blk * BN + cta_rank * (BN / 2), batch, (uint16_t)0x3);
-          } else {
-            ptx::tma_load_3d(sb, &tmB, &full_bar[stage], kb * BKE, n_blk * BN, batch);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            if (kb < p.kblocks1) ptx::tma_load_3d(sa, &tmA, &full_bar[stage], kb * BKE, m_blk * kBM, batch);
+            else                 ptx::tma_load_3d(sa, &tmA2, &full_bar[stage], (kb - p.kblocks1) * BKE, m_blk * kBM, batch);
+            if constexpr (CL == 2) {
+              ptx::tma_load_3d_mcast(sb + cta_rank * (BN / 2) * 128, &tmB, &full_bar[stage], kb * BKE,
+                                     n_blk * BN + cta_rank * (BN / 2), batch, (uint16_t)0x3);
+            } else {
+              ptx::tma_load_3d(sb, &tmB, &full_bar[stage], kb * BKE, n_blk * BN, batch);
+            }
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
@@ -154,31 +157,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
+    // whole warp converged, one elected lane issues: operands stay in uniform registers (see conv_tc.cu)
+    {
       constexpr uint32_t idesc = ptx::umma_idesc(KIND == 0 ? 2 : 0, kBM, BN);
+      const uint32_t smem0 = __shfl_sync(0xffffffffu, ptx::smem_addr(smem), 0);
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t fb0 = smem0 + (uint32_t)(reinterpret_cast<uint8_t*>(full_bar) - smem);
+      const uint32_t eb0 = smem0 + (uint32_t)(reinterpret_cast<uint8_t*>(empty_bar) - smem);
+      const uint32_t tf0 = smem0 + (uint32_t)(reinterpret_cast<uint8_t*>(tmem_full) - smem);
+      (void)fb0;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = t_first; t < total_tiles; t += t_step) {
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tb + acc * BN;
         for (int kb = 0; kb < kblocks; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_addr(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + kStageABytes;
-          const uint64_t adesc = ptx::umma_desc_sw128(sa);
-          const uint64_t bdesc = ptx::umma_desc_sw128(sb);
+          const uint32_t sa = smem0 + stage * Cfg::kStageBytes;
+          const uint32_t a_lo = ptx::umma_desc_lo(sa), b_lo = ptx::umma_desc_lo(sa + kStageABytes);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // advance 32 bytes of K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-            ptx::umma<KIND>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)      // advance 32 bytes of K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+              ptx::umma_lo<KIND>(d_tmem, a_lo + 2 * k, b_lo + 2 * k, ptx::kDescHiSw128, idesc, (kb | k) ? 1u : 0u);
+            if constexpr (CL == 2) ptx::umma_commit_mcast_addr(eb0 + stage * 8, (uint16_t)0x3);   // frees the slot in both CTAs
+            else ptx::umma_commit_addr(eb0 + stage * 8);      // frees the smem slot when these MMAs retire
           }
-          if constexpr (CL == 2) ptx::umma_commit_mcast(&empty_bar[stage], (uint16_t)0x3);   // frees the slot in both CTAs
-          else ptx::umma_commit(&empty_bar[stage]);     // frees the smem slot when these MMAs retire
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&tmem_full[acc]);              // accumulator complete -> epilogue
+        if (ptx::elect_one()) ptx::umma_commit_addr(tf0 + acc * 8);     // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

@@ -96,7 +96,8 @@ sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer: whole warp converged, one elected lane issues (uniform-register operands, see conv_tc.cu)
+    {
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         if (skip_tile(t)) continue;
@@ -105,34 +106,43 @@ sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < p.kblocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStage;
-          ptx::mbar_expect_tx(&full_bar[stage], kStage);
-          ptx::tma_load_3d(sa, &tmA, &full_bar[stage], kb * 64, m_blk * kBM, batch);
-          ptx::tma_load_3d(sa + kStageA, &tmB, &full_bar[stage], kb * 64, n_blk * kBN, batch);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(&full_bar[stage], kStage);
+            ptx::tma_load_3d(sa, &tmA, &full_bar[stage], kb * 64, m_blk * kBM, batch);
+            ptx::tma_load_3d(sa + kStageA, &tmB, &full_bar[stage], kb * 64, n_blk * kBN, batch);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issuer: whole warp converged, one elected lane issues
+    {
       constexpr uint32_t idesc = ptx::umma_idesc(0 /*f16*/, kBM, kBN);
+      const uint32_t smem0 = __shfl_sync(0xffffffffu, ptx::smem_addr(smem), 0);
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t eb0 = smem0 + (uint32_t)(reinterpret_cast<uint8_t*>(empty_bar) - smem);
+      const uint32_t tf0 = smem0 + (uint32_t)(reinterpret_cast<uint8_t*>(tmem_full) - smem);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         if (skip_tile(t)) continue;
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kBN;
+        const uint32_t d_tmem = tb + acc * kBN;
         for (int kb = 0; kb < p.kblocks; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_addr(smem + stage * kStage);
-          const uint64_t adesc = ptx::umma_desc_sw128(sa), bdesc = ptx::umma_desc_sw128(sa + kStageA);
+          const uint32_t sa = smem0 + stage * kStage;
+          const uint32_t a_lo = ptx::umma_desc_lo(sa), b_lo = ptx::umma_desc_lo(sa + kStageA);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) ptx::umma<1>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
-          ptx::umma_commit(&empty_bar[stage]);
+            for (int k = 0; k < 4; ++k) ptx::umma_lo<1>(d_tmem, a_lo + 2 * k, b_lo + 2 * k, ptx::kDescHiSw128, idesc, (kb | k) ? 1u : 0u);
+            ptx::umma_commit_addr(eb0 + stage * 8);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&tmem_full[acc]);
+        if (ptx::elect_one()) ptx::umma_commit_addr(tf0 + acc * 8);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
