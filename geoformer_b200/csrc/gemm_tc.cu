@@ -44,13 +44,14 @@ struct GemmParams {
 constexpr int kBM = 128;
 constexpr int kStageABytes = kBM * 128;
 
-template <int BN> struct GemmCfg {
+template <int BN, bool FULL = false> struct GemmCfg {
   static constexpr int kStageBBytes = BN * 128;
   static constexpr int kStageBytes = kStageABytes + kStageBBytes;
-  static constexpr int kStages = (BN == 256) ? 3 : 5;
+  static constexpr int kStages = (BN == 256) ? 3 : (FULL ? 4 : 5);     // the LayerNorm partials of the full epilogue need 4 KB
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
   static constexpr int kStagingBytes = 4 * 4 * 4096;   // per epilogue warp: ring of 4 x (32 rows x 128 B) output boxes
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kLnBytes = FULL ? 2 * 2 * 128 * 8 : 0;   // LayerNorm partials: 2 tile parities x 2 column halves x 128 rows x (sum, sum of squares)
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kLnBytes;
 };
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -81,10 +82,10 @@ __device__ __forceinline__ float fast_tanh(float x) {
 // intermediates whose only consumers round to a 10-bit mantissa anyway (tf32 / fp16 MMA operands) or are the linear
 // attention kernels: halves the HBM stream these short-K GEMMs are bound by.
 template <int KIND, int BN, bool FULL, int CL, bool OUT16>
-__global__ void __launch_bounds__(FULL ? 192 : 320, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, FULL>;
   constexpr int BKE = (KIND == 0) ? 32 : 64;   // elements per 128-byte K block
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -115,7 +116,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < Cfg::kStages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], CL); }
-      for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], FULL ? 4 : 8); }
+      for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], 8); }
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -191,12 +192,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ------------------------------ epilogue (warps 2..5) ------------------------------
-    // lean epilogue: 8 warps, two per TMEM lane quadrant, each owning half of the tile's columns (with one epilogue
-    // warp per scheduler every dependency stall was exposed); full epilogue (LayerNorm needs whole rows): 4 warps
-    constexpr int EW = FULL ? 4 : 8;
+    // ------------------------------ epilogue (warps 2..9) ------------------------------
+    // 8 warps, two per TMEM lane quadrant, each owning half of the tile's columns (with one epilogue warp per scheduler
+    // every dependency stall was exposed).  r02: also for the LayerNorm epilogue - with 4 warps and three sweeps over the
+    // accumulator it took 17.6 us per 128 x 256 tile (ncu: tensor pipe 14.6 %, DRAM 37 %: bound by neither) where the HBM
+    // streams of the tile need 8 us; now each warp makes ONE statistics sweep over its 128 columns (sum and sum of
+    // squares), the two warps of a quadrant exchange partials through shared memory, then one emit sweep.
+    constexpr int EW = 8;
     constexpr int WCOLS = BN / (EW / 4);                 // columns per epilogue warp
-    constexpr int G = FULL ? 2 : 1;                      // boxes per TMA-store group (ring of 2 groups per warp)
+    constexpr int G = 1;                                 // boxes per TMA-store group (ring of 2 groups per warp)
+    float2* lnx = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(tmem_slot) + 64);      // [2 parities][2 halves][128 rows]
     const int quad = warp & 3;                           // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;
     int acc = 0; uint32_t acc_phase = 0;
@@ -236,25 +241,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       float mean = 0.f, rstd = 1.f;
       if constexpr (FULL) {
         if (p.epi & GF_EPI_LN) {
-          // LayerNorm over the full row (BN == N): two extra sweeps over TMEM (mean, then centred variance)
-          float s = 0.f;
-          for (int c = 0; c < BN; c += 32) {
+          // LayerNorm over the full row (BN == N): one sweep over this warp's half of the columns for (sum, sum of
+          // squares), partials of the two halves combined through shared memory (double-buffered by tile parity)
+          float s1 = 0.f, s2 = 0.f;
+          {
             float v[32];
-            ptx::tmem_ld_32x32(t_row + c, v);
-            ptx::tmem_ld_wait();
+            ptx::tmem_ld_32x32(t_row, v);
+#pragma unroll 1
+            for (int c = 0; c < WCOLS; c += 32) {
+              ptx::tmem_ld_wait();
+              float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) s += v[j] * p.out_scale;
+              for (int j = 0; j < 32; j += 2) {
+                const float x0 = v[j] * p.out_scale, x1 = v[j + 1] * p.out_scale;
+                a0 += x0; a1 += x1; q0 = fmaf(x0, x0, q0); q1 = fmaf(x1, x1, q1);
+              }
+              if (c + 32 < WCOLS) ptx::tmem_ld_32x32(t_row + c + 32, v);
+              s1 += a0 + a1; s2 += q0 + q1;
+            }
           }
-          mean = s * (1.f / BN);
-          float q = 0.f;
-          for (int c = 0; c < BN; c += 32) {
-            float v[32];
-            ptx::tmem_ld_32x32(t_row + c, v);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { const float d = v[j] * p.out_scale - mean; q += d * d; }
-          }
-          rstd = rsqrtf(q * (1.f / BN) + 1e-5f);
+          float2* mine = lnx + (acc * 2 + half) * 128 + quad * 32 + lane;
+          float2* other = lnx + (acc * 2 + (half ^ 1)) * 128 + quad * 32 + lane;
+          *mine = make_float2(s1, s2);
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");     // the two warps of this lane quadrant
+          const float2 o = *other;
+          mean = (s1 + o.x) * (1.f / BN);
+          rstd = rsqrtf(fmaxf((s2 + o.y) * (1.f / BN) - mean * mean, 0.f) + 1e-5f);
         }
       }
       // one 32-column chunk: math on v[] (thread == row), swizzled smem box, grouped TMA store
@@ -498,7 +510,7 @@ int make_out_tmap16(CUtensorMap* m, void* base, int64_t n, int64_t rows, int64_t
 template <int KIND, int BN, bool FULL, int CL, bool OUT16 = false>
 static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& ty,
                          const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, FULL>;
   auto kern = gemm_tc_kernel<KIND, BN, FULL, CL, OUT16>;
   GF_SMEM_OPTIN(kern, Cfg::kSmemBytes);
   const int64_t groups = (int64_t)p.batches * gf_cdiv(gf_cdiv(p.M, kBM), CL) * p.tiles_n;
@@ -506,7 +518,7 @@ static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& ta2, const CU
   const int64_t max_groups = g_num_sms / CL;
   const int grid = (int)(groups < max_groups ? groups : max_groups) * CL;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(FULL ? 192 : 320); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = stream;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(320); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;

@@ -8,6 +8,10 @@
 //                   element) -> per-row best (conf, first j) merged with a 64-bit atomicMax, per-column best conf with
 //                   a 32-bit atomicMax.
 //   then mnn_from_best_kernel applies threshold / border / mutual check on vectors.
+// CTA pairs (r02): the two CTAs of a cluster take neighbouring 128-row blocks of f0 against the same 256 columns of f1 and
+// run ONE tcgen05.mma.cta_group::2 (M = 256) per K step; each CTA stages only half of the f1 tile, so per 64-wide k-block a
+// CTA's shared memory sees 32 KB written + 32 KB read (512 cycles at 128 B/clk) for 512 cycles of MMA, instead of
+// 48 + 48 KB (768 cycles): the single-CTA kernel sat at 67-68 % tensor pipe for exactly this reason.
 // Nothing of size L x S touches HBM: per call the kernels read the packed operands (2 x n*L*3C fp16) and write
 // O(n*(L+S)*tiles) partials, so the similarity contraction is tensor-bound instead of bound by a 1.5 GB fp32 store.
 //
@@ -28,8 +32,8 @@ namespace gf {
 extern std::atomic<int64_t> g_launches;
 
 namespace sf {
-constexpr int kBM = 128, kBN = 256, kStages = 4;
-constexpr int kStageA = kBM * 128, kStageB = kBN * 128, kStage = kStageA + kStageB;
+constexpr int kBM = 128, kBN = 256, kStages = 5;
+constexpr int kStageA = kBM * 128, kStageB = (kBN / 2) * 128, kStage = kStageA + kStageB;     // B: this CTA's half of the f1 rows
 constexpr int kEpiWarps = 8;            // two epilogue warps per TMEM lane quadrant (each takes 128 of the 256 columns):
                                         // with one warp per scheduler every dependency stall of the softmax math was exposed
 constexpr int kThreads = 64 + 32 * kEpiWarps;
@@ -70,64 +74,81 @@ sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.n * p.tiles_m * p.tiles_n;
+  const int tiles_mp = (p.tiles_m + 1) >> 1;                 // pairs of 128-row blocks
+  const int total_tiles = p.n * tiles_mp * p.tiles_n;        // work items of a CTA pair
   if constexpr (MODE == 2) {
-    if (p.rescan_cnt[p.n * p.tiles_m] == 0) return;        // nothing to re-scan (uniform over the grid)
+    if (p.rescan_cnt[p.n * p.tiles_m] == 0) return;        // nothing to re-scan (uniform over the grid, before any cluster barrier)
   }
-  // MODE 2 visits only the 128-row blocks that hold a row to re-scan (all three roles skip the same tiles)
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int t0 = blockIdx.x >> 1, tstep = gridDim.x >> 1;
+  // work item t -> (batch, row-block pair, column block); this CTA's row block is 2 * pair + rank (may lie beyond L:
+  // TMA zero-fills it and every row fails row_ok)
+  auto decode = [&](int t, int& batch, int& m_blk, int& n_blk) {
+    n_blk = t % p.tiles_n;
+    const int rest = t / p.tiles_n;
+    m_blk = (rest % tiles_mp) * 2 + (int)rank;
+    batch = rest / tiles_mp;
+  };
+  // MODE 2 visits only the pairs of 128-row blocks that hold a row to re-scan (all roles of both CTAs skip the same items)
   auto skip_tile = [&](int t) -> bool {
-    if constexpr (MODE == 2) return p.rescan_cnt[t / p.tiles_n] == 0;
-    else return false;
+    if constexpr (MODE == 2) {
+      const int rest = t / p.tiles_n, mp = rest % tiles_mp, batch = rest / tiles_mp;
+      const int* c = p.rescan_cnt + batch * p.tiles_m + 2 * mp;
+      return c[0] == 0 && (2 * mp + 1 >= p.tiles_m || c[1] == 0);
+    } else return false;
   };
 
   if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmB); }
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < kStages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
-      for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], kEpiWarps); }
+      // tmem_empty is used in the leader CTA only: the epilogue warps of both CTAs arrive there
+      for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], 2 * kEpiWarps); }
       ptx::fence_barrier_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_alloc2(tmem_slot, kTmemCols);
   }
   ptx::tc_fence_before();
   __syncthreads();
+  ptx::cluster_sync();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // TMA producer: whole warp converged, one elected lane issues (uniform-register operands, see conv_tc.cu)
+    // TMA producer: whole warp converged, one elected lane issues (uniform-register operands, see conv_tc.cu).  Both CTAs'
+    // boxes (own 128 rows of f0, own half of the 256 rows of f1) count on the LEADER's full barrier.
     {
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = t0; t < total_tiles; t += tstep) {
         if (skip_tile(t)) continue;
-        const int n_blk = t % p.tiles_n, rest = t / p.tiles_n;
-        const int m_blk = rest % p.tiles_m, batch = rest / p.tiles_m;
+        int batch, m_blk, n_blk;
+        decode(t, batch, m_blk, n_blk);
         for (int kb = 0; kb < p.kblocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStage;
           if (ptx::elect_one()) {
-            ptx::mbar_expect_tx(&full_bar[stage], kStage);
-            ptx::tma_load_3d(sa, &tmA, &full_bar[stage], kb * 64, m_blk * kBM, batch);
-            ptx::tma_load_3d(sa + kStageA, &tmB, &full_bar[stage], kb * 64, n_blk * kBN, batch);
+            if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * kStage);
+            ptx::tma_load_3d_2sm(sa, &tmA, &full_bar[stage], kb * 64, m_blk * kBM, batch);
+            ptx::tma_load_3d_2sm(sa + kStageA, &tmB, &full_bar[stage], kb * 64, n_blk * kBN + (int)rank * (kBN / 2), batch);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // MMA issuer: whole warp converged, one elected lane issues
-    {
-      constexpr uint32_t idesc = ptx::umma_idesc(0 /*f16*/, kBM, kBN);
+    // MMA issuer (leader CTA only): whole warp converged, one elected lane issues; M = 256 over the CTA pair
+    if (rank == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc(0 /*f16*/, 2 * kBM, kBN);
       const uint32_t smem0 = __shfl_sync(0xffffffffu, ptx::smem_addr(smem), 0);
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t eb0 = smem0 + (uint32_t)(reinterpret_cast<uint8_t*>(empty_bar) - smem);
       const uint32_t tf0 = smem0 + (uint32_t)(reinterpret_cast<uint8_t*>(tmem_full) - smem);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = t0; t < total_tiles; t += tstep) {
         if (skip_tile(t)) continue;
-        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // both CTAs' epilogue warps have drained this accumulator
         ptx::tc_fence_after();
         const uint32_t d_tmem = tb + acc * kBN;
         for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -137,12 +158,12 @@ sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t a_lo = ptx::umma_desc_lo(sa), b_lo = ptx::umma_desc_lo(sa + kStageA);
           if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) ptx::umma_lo<1>(d_tmem, a_lo + 2 * k, b_lo + 2 * k, ptx::kDescHiSw128, idesc, (kb | k) ? 1u : 0u);
-            ptx::umma_commit_addr(eb0 + stage * 8);
+            for (int k = 0; k < 4; ++k) ptx::umma2_f16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, ptx::kDescHiSw128, idesc, (kb | k) ? 1u : 0u);
+            ptx::umma2_commit_mcast_addr(eb0 + stage * 8, (uint16_t)0x3);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        if (ptx::elect_one()) ptx::umma_commit_addr(tf0 + acc * 8);
+        if (ptx::elect_one()) ptx::umma2_commit_mcast_addr(tf0 + acc * 8, (uint16_t)0x3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -151,17 +172,18 @@ sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int half = (warp - 2) >> 2;                    // which 128-column half of the tile this warp handles
     uint8_t* box = staging + (warp - 2) * 4096;          // this warp's 32 x 32 fp32 transpose box (128B-swizzled rows)
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = t0; t < total_tiles; t += tstep) {
       if (skip_tile(t)) continue;
-      const int n_blk = t % p.tiles_n, rest = t / p.tiles_n;
-      const int m_blk = rest % p.tiles_m, batch = rest / p.tiles_m;
+      int batch, m_blk, n_blk;
+      decode(t, batch, m_blk, n_blk);
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const int row = m_blk * kBM + quad * 32 + lane;
       const bool row_ok = row < p.l;
       const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * kBN + half * (kBN / 2);
       const int col0 = n_blk * kBN + half * (kBN / 2);
-      const int nch = max(0, min(kBN / 64, (p.s - col0 + 31) / 32));
+      // (a row block beyond L - the odd block's partner in the last pair - does no epilogue work and writes nothing)
+      const int nch = m_blk >= p.tiles_m ? 0 : max(0, min(kBN / 64, (p.s - col0 + 31) / 32));
       float rm = -INFINITY, rsum = 0.f;                  // MODE 0: running row (max, sum)
       float r_m2 = 0.f, r_inv = 0.f;                     // MODE 1: final row stats
       float best = 0.f; int best_j = 0;
@@ -289,15 +311,16 @@ sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) ptx::mbar_arrive_cluster(&tmem_empty[acc], 0);     // the MMA issuer lives in the leader CTA
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  ptx::cluster_sync();                 // no CTA leaves (or frees tensor memory) while its peer may still use it
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, sf::kTmemCols);
+    ptx::tmem_dealloc2(tmem_base, sf::kTmemCols);
   }
 }
 
@@ -418,7 +441,7 @@ static int coarse_match_fused_impl(const void* a3, const void* b3, int n, int l,
   CUtensorMap ta, tb;
   int rc;
   if ((rc = make_tmap(&ta, a3, 2, c3, l, n, c3, (int64_t)l * c3, sf::kBM))) return rc;
-  if ((rc = make_tmap(&tb, b3, 2, c3, s, n, c3, (int64_t)s * c3, sf::kBN))) return rc;
+  if ((rc = make_tmap(&tb, b3, 2, c3, s, n, c3, (int64_t)s * c3, sf::kBN / 2))) return rc;     // half a column block per CTA of the pair
   GF_SMEM_OPTIN(sim_fused_kernel<0>, sf::kSmem);
   GF_SMEM_OPTIN(sim_fused_kernel<1>, sf::kSmem);
   GF_SMEM_OPTIN(sim_fused_kernel<2>, sf::kSmem);
@@ -428,21 +451,31 @@ static int coarse_match_fused_impl(const void* a3, const void* b3, int n, int l,
   p.rowp = rowp; p.colp = colp; p.row_m2 = row_m2; p.row_inv = row_inv; p.col_m2 = col_m2; p.col_inv = col_inv;
   p.row_best = row_best; p.col_best = col_best; p.row_tie = row_tie; p.rescan_cnt = rescan_cnt; p.rescan_j = rescan_j;
   p.border = border; p.h0c = h0c; p.w0c = w0c; p.h1c = h1c; p.w1c = w1c;
-  const int64_t tiles = (int64_t)n * tiles_m * tiles_n;
-  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  if (only_pass == 0) { sim_fused_kernel<0><<<grid, sf::kThreads, sf::kSmem, st>>>(ta, tb, p); g_launches++; GF_CHECK_LAUNCH(); return GF_OK; }
-  if (only_pass == 1) { sim_fused_kernel<1><<<grid, sf::kThreads, sf::kSmem, st>>>(ta, tb, p); g_launches++; GF_CHECK_LAUNCH(); return GF_OK; }
-  sim_fused_kernel<0><<<grid, sf::kThreads, sf::kSmem, st>>>(ta, tb, p);
+  const int64_t items = (int64_t)n * ((tiles_m + 1) / 2) * tiles_n;           // work items of a CTA pair
+  const int grid = 2 * (int)(items < num_sms() / 2 ? items : num_sms() / 2);
+  auto launch = [&](auto kern) -> int {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(sf::kThreads); cfg.dynamicSmemBytes = sf::kSmem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, ta, tb, p) != cudaSuccess) return gf_set_error(GF_ERR_LAUNCH, cudaGetErrorString(cudaGetLastError()));
+    return GF_OK;
+  };
+  if (only_pass == 0) { if ((rc = launch(sim_fused_kernel<0>))) return rc; g_launches++; GF_CHECK_LAUNCH(); return GF_OK; }
+  if (only_pass == 1) { if ((rc = launch(sim_fused_kernel<1>))) return rc; g_launches++; GF_CHECK_LAUNCH(); return GF_OK; }
+  if ((rc = launch(sim_fused_kernel<0>))) return rc;
   merge_stats2_kernel<<<gf_cdiv((int64_t)n * l, 256), 256, 0, st>>>(rowp, (int64_t)n * l, tiles_n * 2, tiles_n * 2, 1, (int64_t)n * l, 0,
                                                                    row_m2, row_inv);
   merge_stats2_kernel<<<gf_cdiv((int64_t)n * s, 256), 256, 0, st>>>(colp, (int64_t)n * s, tiles_m * 4, 1, s, s,
                                                                    (int64_t)tiles_m * 4 * s, col_m2, col_inv);
   cudaMemsetAsync(zero0, 0, zero_bytes, st);
-  sim_fused_kernel<1><<<grid, sf::kThreads, sf::kSmem, st>>>(ta, tb, p);
+  if ((rc = launch(sim_fused_kernel<1>))) return rc;
   mnn_from_best_kernel<<<gf_cdiv((int64_t)n * l, 256), 256, 0, st>>>(row_best, col_best, row_tie, n, l, s, thr, border, h0c, w0c,
                                                                     h1c, w1c, tiles_m, match_j, match_conf, rescan_j, rescan_cnt);
   // exact tie handling: both kernels return at once unless a tied row maximum was rejected (see the header comment)
-  sim_fused_kernel<2><<<grid, sf::kThreads, sf::kSmem, st>>>(ta, tb, p);
+  if ((rc = launch(sim_fused_kernel<2>))) return rc;
   mnn_apply_rescan_kernel<<<gf_cdiv((int64_t)n * l, 256), 256, 0, st>>>(row_best, rescan_j, rescan_cnt, (int64_t)n * l, n * tiles_m,
                                                                        match_j, match_conf);
   g_launches += 7;
