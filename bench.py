@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--backbone", default=os.environ.get("GF_BACKBONE", "f16"))
     ap.add_argument("--ransac", default=os.environ.get("GF_RANSAC", "cv2"), choices=["cv2", "gpu"],
                     help="cv2 = host cv2.findHomography as the reference (default); gpu = csrc/ransac.cu (not bit-identical)")
-    ap.add_argument("--depth", type=int, default=2, help="batches in flight (MatchPipeline); 1 = plain serial forward")
+    ap.add_argument("--depth", type=int, default=3, help="batches in flight (MatchPipeline); 1 = plain serial forward")
     ap.add_argument("--hw", default=None, help="HxW override for informational runs of the other BASELINE configs (e.g. 768x768)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stage-times", action="store_true", help="print a per-stage CUDA-event breakdown to stderr")
@@ -51,7 +51,7 @@ def workload_config(args, extra=None):
     cfg = {"workload": f"HPatches-shaped synthetic 640x480 pairs, batch {args.batch}, regime '{args.regime}' "
                        f"(image1 == image0: heaviest match count), random-init weights, coarse_thr 0.0",
            "image_hw": [H, W], "pairs_per_step": args.batch, "coarse_tokens": (H // 8) * (W // 8),
-           "cache": "working set per step (sim matrix 1.5 GB, activations > 3 GB) >> 126 MB L2; no explicit flush"}
+           "cache": "working set per step (activations > 3 GB per batch, several batches in flight) >> 126 MB L2; no explicit flush"}
     if extra:
         cfg.update(extra)
     return cfg
@@ -139,7 +139,11 @@ def run_reference(args):
     v, cores, spp, mf = cpu_forward_pairs_per_sec(steps, warmup, args.regime)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": 1e3 * spp, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args, {"pairs_per_step": 1}),
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, {"pairs_per_step": 1,
+                                             "steps_note": f"CPU arm: each step is ONE pair (~2-5 s of all-core CPU work); requested "
+                                                           f"--steps {args.steps} / --warmup {args.warmup} clamped to {steps} / {warmup} "
+                                                           f"so that the run ends within a few minutes"}),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{steps} single-pair 640x480 forwards of the CPU oracle port after {warmup} warm-up "
                                        f"(the reference is pure PyTorch; /root/reference is absent on the GPU box)"},
@@ -184,21 +188,48 @@ def run_ours(args):
     from geoformer_b200.pipeline import MatchPipeline
     pipe = MatchPipeline(model, depth=args.depth, device=device, freeze_gc=True)
 
+    from geoformer_b200.dist import all_gather_match_block, pack_match_list, reduce_sums, unpack_match_lists
     done_t = []                    # host completion time of every batch (GF_BENCH_TRACE=1 prints the gaps to stderr)
+    cap = args.batch * (H // 8) * (W // 8)          # matches per batch <= pairs * L (at most one per coarse row)
+    xstream = torch.cuda.Stream(device=device)      # the path's only collective runs here, beside the next batches' compute
+    xev = []                                        # CUDA events around every exchange (reported, not part of the timing)
+    last_gather = {}
+
+    def block_of(d):               # packed match list of the batch (device, fixed capacity, no host sync); pair id = global
+        return pack_match_list(d["mkpts0_f"], d["mkpts1_f"], d["mconf"], d["m_bids"] * world + rank, cap)
 
     def counts_only(d):            # keep only what the report needs (frees the big per-batch tensors early)
         done_t.append(time.perf_counter())
-        return {"b_ids": d["b_ids"].shape[0], "mkpts0_f": d["mkpts0_f"].shape[0]}
+        return {"b_ids": d["b_ids"].shape[0], "mkpts0_f": d["mkpts0_f"].shape[0], "block": block_of(d)}
 
     def to_host(d):                # what match_pairs() reads back (geoformer.py:53-54,73)
         k0, k1, cf = d["mkpts0_f"].cpu(), d["mkpts1_f"].cpu(), d["mconf"].cpu()
         return counts_only(d), k0.numel() * 4 + k1.numel() * 4 + cf.numel() * 4
 
+    def exchange(block):
+        """Gather this batch's match list over all ranks: ONE all_gather_into_tensor of the packed int32 block, issued
+        from the main thread in batch order (same order on every rank) on a side stream."""
+        with torch.cuda.stream(xstream):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out, _ = all_gather_match_block(block)
+            e1.record()
+        xev.append((e0, e1))
+        last_gather["blocks"] = out
+
+    def drive(batches, post):
+        outs = []
+        for res in pipe.run_iter(batches, post):
+            blk = (res[0] if isinstance(res, tuple) else res).pop("block")
+            exchange(blk)
+            outs.append(res)
+        return outs
+
     def run_resident(steps):
-        return pipe.run(({"image0": dev[i % pool][0], "image1": dev[i % pool][1]} for i in range(steps)), counts_only)
+        return drive(({"image0": dev[i % pool][0], "image1": dev[i % pool][1]} for i in range(steps)), counts_only)
 
     def run_e2e(steps):
-        return pipe.run(({"image0": host[i % pool][0], "image1": host[i % pool][1]} for i in range(steps)), to_host)
+        return drive(({"image0": host[i % pool][0], "image1": host[i % pool][1]} for i in range(steps)), to_host)
 
     def barrier():
         if world > 1:
@@ -211,6 +242,7 @@ def run_ours(args):
         l0 = _lib.launch_count()
         e0.record()
         outs = fn(steps)
+        torch.cuda.current_stream().wait_stream(xstream)      # the exchanges belong to the timed region
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -290,23 +322,46 @@ def run_ours(args):
             del xf, yf
     except Exception:
         fl_ms = []
+    # projection GEMMs of one coarse-transformer layer in their shipped variants, timed live (rows = both images of the batch)
+    gemm_ms = []
+    try:
+        from geoformer_b200.ops import EPI_ELU1, EPI_LN, EPI_RELU
+        lw = model._weights(device).coarse[0]
+        m_rows = 2 * args.batch * L_
+        gx = torch.randn(m_rows, 256, device=device)
+        q_ = ops.linear(gx, lw["wqkv"], epi=EPI_ELU1, act_cols=512, out_f16=True)
+        msg_ = q_[:, :256].contiguous()
+        n1_ = ops.linear(msg_, lw["wm16"], epi=EPI_LN, gamma=lw["n1w"], beta=lw["n1b"])
+        h_ = ops.linear(gx, lw["w1"], a2=n1_, epi=EPI_RELU, out_f16=True)
+        calls = [lambda: ops.linear(gx, lw["wqkv"], epi=EPI_ELU1, act_cols=512, out_f16=True),
+                 lambda: ops.linear(msg_, lw["wm16"], epi=EPI_LN, gamma=lw["n1w"], beta=lw["n1b"]),
+                 lambda: ops.linear(gx, lw["w1"], a2=n1_, epi=EPI_RELU, out_f16=True),
+                 lambda: ops.linear(h_, lw["w2_16"], epi=EPI_LN, gamma=lw["n2w"], beta=lw["n2b"], residual=gx)]
+        for fn in calls:
+            evs = []
+            for it in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record()
+                if it >= 2:
+                    evs.append((e0, e1))
+            torch.cuda.synchronize()
+            gemm_ms.append(float(np.mean([a.elapsed_time(b) for a, b in evs])))
+        del gx, q_, msg_, n1_, h_
+    except Exception as e:      # diagnostic block only
+        print("gemm timing skipped:", e, file=sys.stderr)
+        gemm_ms = []
     clocks = sampler.stop() if rank == 0 else None
 
     mc = float(np.mean([o["b_ids"] for o in outs])) / args.batch
     mf = float(np.mean([o["mkpts0_f"] for o in outs])) / args.batch
     d2h = int(np.mean([o[1] for o in outs_e2e]))
-    # the path's only exchange step (outside the per-step loop): gather one batch's match lists + metric sums
-    from geoformer_b200.dist import gather_match_lists, reduce_sums
-    d = model({"image0": dev[0][0], "image1": dev[0][1]})
-    lists = torch.cat([d["mkpts0_f"], d["mkpts1_f"], d["mconf"][:, None]], 1)
-    pair_ids = d["m_bids"] * world + rank
+    # the path's only exchange step ran inside the timed loops (one all_gather_into_tensor per batch); its device time:
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    allm, allid = gather_match_lists(lists, pair_ids)
-    mc, mf = [v / world for v in reduce_sums([mc, mf], device)]
-    torch.cuda.synchronize()
-    exchange_ms = 1e3 * (time.perf_counter() - t0)
+    xms = [a.elapsed_time(b) for a, b in xev[-2 * args.steps:]]
+    exchange_ms = float(np.mean(xms)) if xms else 0.0
+    allm, allid = unpack_match_lists(last_gather["blocks"])
     gathered = int(allm.shape[0])
+    mc, mf = [v / world for v in reduce_sums([mc, mf], device)]
     if args.stage_times and rank == 0:
         stage_breakdown(model, dev[0])
     if rank != 0:
@@ -323,48 +378,83 @@ def run_ours(args):
     except Exception:
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"
+    # ncu evidence committed under profiles/ (tools/ncu_summary.py of `ncu --set full` on tools/prof_r02_ncu.py, same shapes)
+    ncu = {}
+    try:
+        for k in json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_main_kernels.json")))["kernels"]:
+            ncu.setdefault(k["kernel"], []).append(k)
+    except Exception:
+        pass
+
+    def ncu_of(name, idx=0):
+        v = ncu.get(name)
+        return v[min(idx, len(v) - 1)] if v else None
+
     L = (H // 8) * (W // 8)
     flops = 2.0 * L * L * 256 * args.batch                                   # algorithmic: 2*L*S*C per pair per launch
     sim_avg_ms = float(np.mean(sim_ms)) if len(sim_ms) else float("nan")
     achieved = flops / (sim_avg_ms * 1e-3) / 1e12
-    roof = {"kernel": "sim_fused_kernel<pass 0|1> (coarse similarity contraction, split-fp16 K=768, dual-softmax fused "
-                      "into the epilogue; average over the two passes)",
+    n0, n1 = ncu_of("sim_fused_kernel<0>"), ncu_of("sim_fused_kernel<1>")
+    roof = {"kernel": "sim_fused_kernel<pass 0|1> (coarse similarity contraction on CTA pairs, split-fp16 K=768, dual-softmax "
+                      "fused into the epilogue; average over the two passes)",
             "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
+            "peak_source": peak_src,
             "algorithmic_flops_per_launch": flops, "issued_flops_per_launch": 3 * flops,
             "issued_frac": 3 * achieved / peak_tf,      # tensor-pipe view: the split-fp16 product issues 3 MMAs per algorithmic one
             "avg_launch_ms": sim_avg_ms, "launches_timed": len(sim_ms),
-            # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full of the same kernels at this size
-            # (profiles/r01_ncu_final_raw.txt): pass 0 = 236.1 + 97.1 MB, pass 1 = 238.1 + 4.2 MB; algorithmic bytes per
-            # launch = packed operands 235.9 MB (+ 105 MB statistics partials in pass 0) -> no re-reads
-            "traffic": 287.7e6 * args.batch / 16, "tensor_pipe_active_pct_ncu": {"pass0": 68.5, "pass1": 66.5}}
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (16 pairs), scaled to this
+            # batch; algorithmic bytes per launch = packed operands 235.9 MB (+ 105 MB statistics partials in pass 0)
+            "traffic": (0.5 * (n0["dram_bytes"] + n1["dram_bytes"]) * args.batch / 16) if n0 and n1 else None,
+            "traffic_source": "profiles/r02_ncu_main_kernels.json" if n0 else None,
+            "tensor_pipe_active_pct_ncu": {"pass0": n0["tensor_pipe_pct"], "pass1": n1["tensor_pipe_pct"],
+                                           "sm_clock_ghz_under_ncu": [n0["sm_clock_ghz"], n1["sm_clock_ghz"]]} if n0 and n1 else None}
     roof2 = None
     if fl_ms:
-        hbm = float(peaks.get("hbm_gbs", 6500.0))
         fl_avg = float(np.mean(fl_ms))
-        fl_bytes = fl_windows * 25 * 128 * 4 * 2.0                            # algorithmic: x read once + y written once
+        # algorithmic FLOPs of one fine-level layer application: per 25-token window q/k/v/merge 4 x 2*25*128*128, MLP
+        # 2*25*256*256 + 2*25*256*128, linear attention ~0.2 M  =  8.4 MFLOP (33.6 MFLOP per match / 4 applications)
+        fl_flops = fl_windows * 8.4e6
+        nf = ncu_of("fl::fine_layer_kernel")
         roof2 = {"kernel": "fine_layer_kernel (one whole fine-level LoFTR layer per launch, self layer over both images' "
                            "windows; qkv / attention / merge / LN / MLP / LN / residual never leave the SM)",
-                 "bound": "hbm", "achieved": fl_bytes / (fl_avg * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                 "frac": fl_bytes / (fl_avg * 1e-3) / 1e9 / hbm,
-                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.5 TB/s",
-                 "algorithmic_bytes_per_launch": fl_bytes, "windows": fl_windows, "avg_launch_ms": fl_avg,
-                 # ncu --set full, profiles/r01_fine_layer_ncu_details.txt (112000 windows): dram read 1.434 GB + write
-                 # 1.392 GB == algorithmic 2.867 GB; tensor pipe 28.8 %: the kernel is bound by its serial per-tile chain
-                 # (MMA -> epilogue -> MMA ...), not by HBM; the unfused kernels it replaces moved ~6.9 KB per token-layer
-                 "traffic": fl_bytes * (2.826 / 2.867), "tensor_pipe_active_pct_ncu": 28.8}
+                 "bound": "tensor", "achieved": fl_flops / (fl_avg * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                 "frac": fl_flops / (fl_avg * 1e-3) / 1e12 / peak_tf, "peak_source": peak_src,
+                 "algorithmic_flops_per_launch": fl_flops, "windows": fl_windows, "avg_launch_ms": fl_avg,
+                 "algorithmic_bytes_per_launch": fl_windows * 25 * 128 * 4 * 2.0,      # x read once + y written once (HBM view)
+                 "traffic": (nf["dram_bytes"] * fl_windows / 130898.0) if nf else None,
+                 "traffic_source": "profiles/r02_ncu_main_kernels.json (130898 windows), scaled" if nf else None,
+                 "tensor_pipe_active_pct_ncu": nf["tensor_pipe_pct"] if nf else None}
+    line_gemms = None
+    if gemm_ms:
+        m_rows = 2 * args.batch * L
+        spec = {"qkv 768x256 (tf32 in, fp16 out, elu+1)": (2.0 * m_rows * 768 * 256, m_rows * (256 * 4 + 768 * 2), "gemm_tc_kernel<0, 256, 0, 1, 1>"),
+                "merge 256x256 (fp16 in, LayerNorm)": (2.0 * m_rows * 256 * 256, m_rows * (256 * 2 + 256 * 4), "gemm_tc_kernel<1, 256, 1, 1, 0>"),
+                "mlp.0 512x512 (tf32 in, fp16 out, ReLU)": (2.0 * m_rows * 512 * 512, m_rows * (512 * 4 + 512 * 2), "gemm_tc_kernel<0, 256, 0, 1, 1>"),
+                "mlp.2 256x512 (fp16 in, LayerNorm + residual)": (2.0 * m_rows * 512 * 256, m_rows * (512 * 2 + 256 * 4 + 256 * 4), "gemm_tc_kernel<1, 256, 1, 1, 0>")}
+        hbm = float(peaks.get("hbm_gbs", 6500.0))
+        line_gemms = {}
+        for (name, (fl_, by_, kn)), t_ms in zip(spec.items(), gemm_ms):
+            nk = ncu_of(kn, 1 if name.startswith("mlp.2") else 0)
+            line_gemms[name] = {"avg_launch_ms": t_ms, "tflops": fl_ / (t_ms * 1e-3) / 1e12, "frac_of_tensor_peak": fl_ / (t_ms * 1e-3) / 1e12 / peak_tf,
+                                "hbm_gbs_algorithmic": by_ / (t_ms * 1e-3) / 1e9, "frac_of_hbm_peak": by_ / (t_ms * 1e-3) / 1e9 / hbm,
+                                "bound": "hbm" if by_ / hbm / 1e9 > fl_ / peak_tf / 1e12 else "tensor",
+                                "tensor_pipe_active_pct_ncu": nk["tensor_pipe_pct"] if nk else None,
+                                "dram_pct_ncu": nk["dram_pct"] if nk else None}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": ("tf32 / fp16 tensor-core operands with fp32 accumulation (fp32 residual stream, fp16 intermediates), "
-                      f"split-fp16 similarity, {args.backbone} backbone"),
+                      f"split-fp16 similarity, {args.backbone} backbone activations"),
             "data": "synthetic",
             "config": workload_config(args, {"matches_coarse_per_pair": mc, "matches_fine_per_pair": mf,
                                              "batches_in_flight": args.depth, "ransac": args.ransac,
-                                             "untimed_steps_before_timing": f"{args.warmup} warm-up (resident) + {args.warmup} warm-up (host inputs) + {settle} power-cap settle", "exchange_ms_per_batch_gather": exchange_ms,
-                                             "gathered_matches": gathered,
+                                             "untimed_steps_before_timing": f"{args.warmup} warm-up (resident) + {args.warmup} warm-up (host inputs) + {settle} power-cap settle", "exchange": "inside the timed region: one all_gather_into_tensor per batch (int16 coordinates + fp32 confidence + pair id, 16 B per match, fixed capacity, no host sync) on a side stream",
+                                             "exchange_ms_per_batch": exchange_ms, "exchange_bytes_per_rank_per_batch": (cap + 1) * 16,
+                                             "gathered_matches_last_batch_all_ranks": gathered,
                                              "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective"}),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * args.batch * H * W * 4, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_top_kernel_by_time": roof2}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_top_kernel_by_time": roof2,
+            "roofline_projection_gemms": line_gemms}
     if not args.no_cpu_baseline and world == 1:
         v, cores, spp, _ = cpu_forward_pairs_per_sec(2, 1, args.regime)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

@@ -40,6 +40,54 @@ def gather_match_lists(matches: torch.Tensor, pair_ids: torch.Tensor, group=None
     return allm[order, :5].to(torch.float32), ids[order]
 
 
+# --------------------------------------------------------------------------------------------
+# fixed-capacity exchange of one batch's match list (the path's only collective; bench.py runs it inside the timed region)
+# --------------------------------------------------------------------------------------------
+def pack_match_list(mkpts0: torch.Tensor, mkpts1: torch.Tensor, mconf: torch.Tensor, pair_ids: torch.Tensor,
+                    capacity: int) -> torch.Tensor:
+    """One batch's matches as an int32 block [capacity + 1, 4], no host synchronisation: row 0 = (count, 0, 0, 0); row
+    1 + k = (x0 | y0 << 16, x1 | y1 << 16, float bits of conf, global pair id).  GeoFormer's fine coordinates are even
+    integer pixels (fine_matching2.py:103-115), so int16 is exact up to 32767 px; 16 bytes per match instead of the
+    48 bytes of the fp64 x 6 layout gather_match_lists uses.  capacity must be >= the number of matches (<= pairs * L)."""
+    m = mkpts0.shape[0]
+    assert m <= capacity, (m, capacity)
+    buf = torch.zeros((capacity + 1, 4), device=mkpts0.device, dtype=torch.int32)
+    k0, k1 = mkpts0.to(torch.int32), mkpts1.to(torch.int32)
+    buf[0, 0] = m
+    buf[1:m + 1, 0] = (k0[:, 0] & 0xFFFF) | (k0[:, 1] << 16)
+    buf[1:m + 1, 1] = (k1[:, 0] & 0xFFFF) | (k1[:, 1] << 16)
+    buf[1:m + 1, 2] = mconf.to(torch.float32).view(torch.int32)
+    buf[1:m + 1, 3] = pair_ids.to(torch.int32)
+    return buf
+
+
+def unpack_match_lists(blocks: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[world, capacity + 1, 4] gathered blocks -> (matches [M, 5] fp32 (x0, y0, x1, y1, conf), pair_ids [M] int64),
+    concatenated in rank order and stably sorted by pair id."""
+    out, ids = [], []
+    for blk in blocks:
+        m = int(blk[0, 0])
+        r = blk[1:m + 1]
+        xy = torch.stack([(r[:, 0] << 16) >> 16, r[:, 0] >> 16, (r[:, 1] << 16) >> 16, r[:, 1] >> 16], 1).to(torch.float32)
+        out.append(torch.cat([xy, r[:, 2].contiguous().view(torch.float32)[:, None]], 1))
+        ids.append(r[:, 3].to(torch.int64))
+    allm, allid = torch.cat(out, 0), torch.cat(ids, 0)
+    order = torch.argsort(allid, stable=True)
+    return allm[order], allid[order]
+
+
+def all_gather_match_block(block: torch.Tensor, group=None, async_op: bool = False):
+    """ONE collective for a batch's packed match list: all_gather_into_tensor of the fixed-capacity int32 block (NCCL
+    over NVLink on GPUs, gloo on CPU).  Returns (gathered [world, capacity + 1, 4], work handle or None)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    out = torch.empty((world,) + tuple(block.shape), device=block.device, dtype=block.dtype)
+    if world == 1:
+        out[0].copy_(block)
+        return out, None
+    work = dist.all_gather_into_tensor(out.view(-1), block.contiguous().view(-1), group=group, async_op=async_op)
+    return out, work
+
+
 def reduce_sums(values: Sequence[float], device, group=None) -> List[float]:
     """Sum scalars (pair counts, match counts, error sums) over ranks."""
     t = torch.tensor(list(values), device=device, dtype=torch.float64)

@@ -41,6 +41,13 @@ class MatchPipeline:
         inside the pipeline).  ``post(data)`` runs on the batch's stream (e.g. device->host of the results).
         ``depth`` worker threads, each owning one stream, pull batches from the shared iterator, so ``depth``
         batches stay in flight until the input is exhausted; results keep the input order."""
+        return list(self.run_iter(batches, post))
+
+    def run_iter(self, batches: Iterable[Dict[str, torch.Tensor]], post: Optional[Callable] = None):
+        """Generator form of ``run``: yields each batch's result IN INPUT ORDER as soon as it (and all earlier ones) is
+        done, while the workers keep going.  The consumer runs on the calling thread - that is where per-batch
+        collectives belong (every rank then issues them in the same, deterministic order; bench.py gathers the match
+        lists there)."""
         main = torch.cuda.current_stream(self.device)
         for s in self.streams:
             s.wait_stream(main)
@@ -55,33 +62,62 @@ class MatchPipeline:
             self._frozen = True
         it = enumerate(batches)
         lock = threading.Lock()
+        done = threading.Condition()
         results: Dict[int, object] = {}
         errors: List[BaseException] = []
+        state = {"issued": 0, "exhausted": False}
 
         def worker(slot: int):
             torch.cuda.set_device(self.device)
             while not errors:
                 with lock:
                     nxt = next(it, None)
+                    if nxt is None:
+                        state["exhausted"] = True
+                    else:
+                        state["issued"] += 1
                 if nxt is None:
-                    return
+                    break
                 idx, batch = nxt
                 try:
-                    results[idx] = self._job(slot, batch, post)
+                    res = self._job(slot, batch, post)
                 except BaseException as e:      # surfaced to the caller below (the helpers count match failures)
                     errors.append(e)
-                    return
+                    break
+                with done:
+                    results[idx] = res
+                    done.notify_all()
+            with done:
+                done.notify_all()
 
         threads = [threading.Thread(target=worker, args=(i,), daemon=True) for i in range(self.depth)]
         for t in threads:
             t.start()
-        for t in threads:
-            t.join()
-        for s in self.streams:
-            main.wait_stream(s)
+        nxt_idx = 0
+        try:
+            while True:
+                with done:
+                    while nxt_idx not in results and not errors and \
+                            not (state["exhausted"] and nxt_idx >= state["issued"] and not any(t.is_alive() for t in threads)):
+                        done.wait(timeout=0.05)
+                    if errors:
+                        break
+                    if nxt_idx in results:
+                        res = results.pop(nxt_idx)
+                    else:
+                        break
+                yield res
+                nxt_idx += 1
+        finally:
+            for t in threads:
+                t.join()
+            for s in self.streams:
+                main.wait_stream(s)
         if errors:
             raise errors[0]
-        return [results[i] for i in range(len(results))]
+        while nxt_idx in results:               # results that completed while the last wait timed out
+            yield results.pop(nxt_idx)
+            nxt_idx += 1
 
     def close(self):
         pass

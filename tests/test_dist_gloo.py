@@ -7,7 +7,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from geoformer_b200.dist import gather_match_lists, reduce_sums, shard_pairs
+from geoformer_b200.dist import (all_gather_match_block, gather_match_lists, pack_match_list, reduce_sums, shard_pairs,
+                                 unpack_match_lists)
 
 
 def _fake_matches(pair: int):
@@ -25,7 +26,12 @@ def _worker(rank, world, port, q):
     ids = torch.cat([torch.full((len(l),), p, dtype=torch.int64) for l, p in zip(lists, mine)]) if lists else torch.zeros(0, dtype=torch.int64)
     allm, allid = gather_match_lists(matches, ids)
     sums = reduce_sums([len(mine), matches.shape[0]], torch.device("cpu"))
-    q.put((rank, allm, allid, sums))
+    # the packed fixed-capacity exchange (one all_gather_into_tensor, no size negotiation): coordinates are even integers
+    coords = (matches[:, :4] * 400).round() * 2
+    blk = pack_match_list(coords[:, :2], coords[:, 2:], matches[:, 4], ids, capacity=9 * 40)
+    gathered, _ = all_gather_match_block(blk)
+    pm, pid = unpack_match_lists(gathered)
+    q.put((rank, allm, allid, sums, pm, pid))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -49,7 +55,23 @@ def test_gather_match_lists_world2():
         assert p.exitcode == 0
     want = torch.cat([_fake_matches(p) for p in range(9)], 0)
     want_ids = torch.cat([torch.full((len(_fake_matches(p)),), p, dtype=torch.int64) for p in range(9)])
-    for rank, allm, allid, sums in res:
+    want_packed = torch.cat([(want[:, :4] * 400).round() * 2, want[:, 4:]], 1)
+    for rank, allm, allid, sums, pm, pid in res:
         assert torch.equal(allid, want_ids)
         assert torch.equal(allm, want)
         assert sums == [9.0, float(want.shape[0])]
+        assert torch.equal(pid, want_ids) and torch.equal(pm, want_packed)      # bit-exact incl. the fp32 confidences
+
+
+def test_pack_unpack_roundtrip_single_process():
+    g = torch.Generator().manual_seed(3)
+    k0 = (torch.randint(0, 420, (57, 2), generator=g) * 2).float()
+    k1 = (torch.randint(0, 16383, (57, 2), generator=g) * 2).float()          # up to the int16 limit
+    conf = torch.rand(57, generator=g)
+    ids = torch.randint(0, 5, (57,), generator=g).sort()[0]
+    gathered, _ = all_gather_match_block(pack_match_list(k0, k1, conf, ids, capacity=64))
+    m, i = unpack_match_lists(gathered)
+    assert torch.equal(i, ids) and torch.equal(m, torch.cat([k0, k1, conf[:, None]], 1))
+    empty, _ = all_gather_match_block(pack_match_list(k0[:0], k1[:0], conf[:0], ids[:0], capacity=8))
+    m, i = unpack_match_lists(empty)
+    assert m.shape == (0, 5) and i.shape == (0,)
