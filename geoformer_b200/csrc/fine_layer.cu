@@ -355,9 +355,13 @@ fine_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           for (int ks = 0; ks < 2; ++ks) {
             const int tok0 = TOK * w + 16 * ks;
             uint32_t a[4], b[4];
-            const int arow = tok0 + lrow + ((lmat >> 1) << 3), achunk = 2 * h + (lmat & 1);
+            // rows 25.. of the 32-token span belong to the next window (or lie beyond the tile): their values are masked
+            // below, so the addresses are clamped to this window's last token - no warp ever reads rows that another warp
+            // owns (keeps compute-sanitizer racecheck clean)
+            const int wlast = TOK * w + TOK - 1;
+            const int arow = min(tok0 + lrow + ((lmat >> 1) << 3), wlast), achunk = 2 * h + (lmat & 1);
             ldsm_x4_trans(a, v16 + arow * 256 + ((achunk ^ (arow & 15)) << 4));
-            const int brow = tok0 + lrow + ((lmat & 1) << 3), bchunk = 2 * h + (lmat >> 1);
+            const int brow = min(tok0 + lrow + ((lmat & 1) << 3), wlast), bchunk = 2 * h + (lmat >> 1);
             ldsm_x4_trans(b, k16 + brow * 256 + ((bchunk ^ (brow & 15)) << 4));
             uint32_t o0 = (g == 0) ? 0x3C003C00u : 0u, o2 = o0;
             if (ks == 1) {                               // tokens 25.. of the 32-token span belong to the next window
@@ -375,7 +379,7 @@ fine_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           for (int mt = 0; mt < 2; ++mt) {
             const int tok0 = TOK * w + 16 * mt;
             uint32_t aq[4];
-            const int qrow = tok0 + lrow + ((lmat & 1) << 3), qchunk = (h & 3) * 2 + (lmat >> 1);
+            const int qrow = min(tok0 + lrow + ((lmat & 1) << 3), TOK * w + TOK - 1), qchunk = (h & 3) * 2 + (lmat >> 1);   // clamped: see above
             ldsm_x4(aq, q16 + (h >> 2) * BLK + qrow * 128 + ((qchunk ^ (qrow & 7)) << 4));
             float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f}, dn[4] = {0.f, 0.f, 0.f, 0.f};
             mma16816(o0, aq, bq[0][0], bq[0][1]);
@@ -384,6 +388,7 @@ fine_layer_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const float z_lo = 1.f / (__shfl_sync(0xffffffffu, dn[0], lane & ~3) + 1e-6f);
             const float z_hi = 1.f / (__shfl_sync(0xffffffffu, dn[2], lane & ~3) + 1e-6f);
             const int row_lo = tok0 + g, row_hi = row_lo + 8;
+            __syncwarp();                                // (the message overwrites the Q rows this warp's ldmatrix just read)
             uint8_t* blk = r3 + (h >> 2) * BLK;
             const int c0 = (h & 3) * 2;
             *reinterpret_cast<uint32_t*>(blk + row_lo * 128 + ((c0 ^ (row_lo & 7)) << 4) + 4 * tq) = pack2(o0[0] * z_lo, o0[1] * z_lo);
