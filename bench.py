@@ -48,7 +48,9 @@ def parse():
 
 
 def workload_config(args, extra=None):
-    cfg = {"workload": f"HPatches-shaped synthetic 640x480 pairs, batch {args.batch}, regime '{args.regime}' "
+    shape = {(480, 640): "HPatches-shaped synthetic 640x480", (768, 768): "FIRE-shaped synthetic 768x768 (9216 coarse tokens)",
+             (840, 840): "MegaDepth-shaped synthetic 840x840 (11025 coarse tokens, high match count)"}.get((H, W), f"synthetic {W}x{H}")
+    cfg = {"workload": f"{shape} pairs, batch {args.batch}, regime '{args.regime}' "
                        f"(image1 == image0: heaviest match count), random-init weights, coarse_thr 0.0",
            "image_hw": [H, W], "pairs_per_step": args.batch, "coarse_tokens": (H // 8) * (W // 8),
            "cache": "working set per step (activations > 3 GB per batch, several batches in flight) >> 126 MB L2; no explicit flush"}
@@ -176,7 +178,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        import datetime
+        # a collective mismatch between ranks must fail within minutes, not after NCCL's default 10-minute watchdog
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
     model = build_model(device, args.backbone, args.ransac)
 
     # a small pool of distinct batches, resident in HBM (value) and in pinned host memory (e2e)
@@ -217,16 +221,20 @@ def run_ours(args):
         xev.append((e0, e1))
         last_gather["blocks"] = out
 
-    def drive(batches, post):
+    def drive(batches, post, collective=True):
+        """collective=False: a pass that only SOME ranks run (rank 0's densely clock-sampled repeat) must not issue the
+        all-gather - every rank has to execute the same sequence of collectives (an r02 8-GPU attempt hung on exactly
+        this: rank 0 issued extra all-gathers while the others waited in the final all-reduce)."""
         outs = []
         for res in pipe.run_iter(batches, post):
             blk = (res[0] if isinstance(res, tuple) else res).pop("block")
-            exchange(blk)
+            if collective:
+                exchange(blk)
             outs.append(res)
         return outs
 
-    def run_resident(steps):
-        return drive(({"image0": dev[i % pool][0], "image1": dev[i % pool][1]} for i in range(steps)), counts_only)
+    def run_resident(steps, collective=True):
+        return drive(({"image0": dev[i % pool][0], "image1": dev[i % pool][1]} for i in range(steps)), counts_only, collective)
 
     def run_e2e(steps):
         return drive(({"image0": host[i % pool][0], "image1": host[i % pool][1]} for i in range(steps)), to_host)
@@ -272,7 +280,7 @@ def run_ours(args):
     if rank == 0 and sampler.h is not None:      # same load once more, untimed, densely sampled (see ClockSampler)
         sampler.timed_samples = len(sampler.samples) - sampler.first
         sampler.interval = 0.04
-        run_resident(max(4, args.steps // 2))
+        run_resident(max(4, args.steps // 2), collective=False)      # rank 0 only: no collective in here
         sampler.interval = 0.3
     # dominant-kernel timing, live in this run: the two tcgen05 passes of the conf-matrix kernel (statistics pass and
     # confidence pass; each launch contracts the full n x L x S x C problem), CUDA events on the launching stream
