@@ -213,6 +213,7 @@ def run_ours(args):
     def exchange(block):
         """Gather this batch's match list over all ranks: ONE all_gather_into_tensor of the packed int32 block, issued
         from the main thread in batch order (same order on every rank) on a side stream."""
+        block.record_stream(xstream)       # allocated on a worker's stream, consumed here
         with torch.cuda.stream(xstream):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()

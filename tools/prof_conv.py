@@ -1,4 +1,5 @@
-"""Time the tcgen05 conv against cuDNN at backbone sizes (32 images)."""
+"""Time the tcgen05 conv at backbone sizes (32 images); the torch/cuDNN column is a tool-side yardstick only (the package
+itself calls no vendor library)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.nn.functional as F
