@@ -147,7 +147,7 @@ def run_reference(args):
                                                            f"--steps {args.steps} / --warmup {args.warmup} clamped to {steps} / {warmup} "
                                                            f"so that the run ends within a few minutes"}),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{steps} single-pair 640x480 forwards of the CPU oracle port after {warmup} warm-up "
+                             "sample": f"{steps} single-pair {W}x{H} forwards of the CPU oracle port after {warmup} warm-up "
                                        f"(the reference is pure PyTorch; /root/reference is absent on the GPU box)"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(line)
@@ -467,7 +467,7 @@ def run_ours(args):
     if not args.no_cpu_baseline and world == 1:
         v, cores, spp, _ = cpu_forward_pairs_per_sec(2, 1, args.regime)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "2 single-pair 640x480 forwards of the CPU oracle port after 1 warm-up "
+                                "sample": f"2 single-pair {W}x{H} forwards of the CPU oracle port after 1 warm-up "
                                           f"({spp:.2f} s/pair)"}
     else:
         line["cpu_baseline"] = None

@@ -1,0 +1,91 @@
+"""Host-side logic that needs no GPU: the ordered-iterator pipeline (results in input order, error propagation) and the
+reference arm of bench.py (contract keys of its JSON line)."""
+import json
+import os
+import random
+import subprocess
+import sys
+import time
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class _StubPipeline:
+    """MatchPipeline with the CUDA plumbing stubbed out: exercises the worker / ordering / error logic of run_iter."""
+
+    def __new__(cls, depth, fail_at=None, monkeypatch=None):
+        from geoformer_b200.pipeline import MatchPipeline
+
+        class Stream:
+            def wait_stream(self, s):
+                pass
+
+        class Dev:
+            def __init__(self, *a):
+                pass
+
+            def __enter__(self):
+                return self
+
+            def __exit__(self, *a):
+                return False
+
+        monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: Stream())
+        monkeypatch.setattr(torch.cuda, "device", Dev)
+        monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+
+        class P(MatchPipeline):
+            def __init__(self):
+                self.depth, self.streams, self.freeze_gc, self._frozen, self.device = depth, [], False, False, None
+                self.model = type("M", (), {"_weights": lambda self, d: None})()
+
+            def _job(self, slot, data, post):
+                time.sleep(random.random() * 0.005)
+                if fail_at is not None and data["i"] == fail_at:
+                    raise RuntimeError("boom")
+                return data["i"] if post is None else post(data)
+
+        return P()
+
+
+@pytest.mark.parametrize("depth", [1, 2, 4])
+def test_run_iter_yields_in_input_order(depth, monkeypatch):
+    p = _StubPipeline(depth, monkeypatch=monkeypatch)
+    seen = []
+    for r in p.run_iter(({"i": i} for i in range(41))):
+        seen.append(r)                       # the consumer runs on the calling thread, in batch order
+    assert seen == list(range(41))
+    assert p.run([]) == []
+    assert p.run(({"i": i} for i in range(5)), post=lambda d: d["i"] * 2) == [0, 2, 4, 6, 8]
+
+
+def test_run_iter_propagates_worker_errors(monkeypatch):
+    p = _StubPipeline(3, fail_at=7, monkeypatch=monkeypatch)
+    got = []
+    with pytest.raises(RuntimeError, match="boom"):
+        for r in p.run_iter(({"i": i} for i in range(30))):
+            got.append(r)
+    assert got == list(range(len(got))) and len(got) <= 7       # everything before the failing batch, in order
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the oracle port timed on the host cores): one JSON line on stdout with the contract's
+    keys; under torchrun only rank 0 prints."""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--hw", "96x128"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "steps_note" in d["config"] and d["steps"] == 1 and d["warmup"] == 0
+    # a non-zero rank prints nothing and exits 0
+    r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                        capture_output=True, text=True, timeout=120, env=dict(os.environ, RANK="1", WORLD_SIZE="2"), cwd=ROOT)
+    assert r2.returncode == 0 and r2.stdout.strip() == ""
