@@ -164,8 +164,10 @@ int gf_mnn_select(const float* conf, int n, int l, int s, float thr, int border,
                   gf_stream_t stream);
 /* Fused inference path of the whole coarse-matching stage: two tcgen05 passes over the packed operands (statistics,
  * then confidences + per-row / per-column bests), never materialising the L x S matrix; then the mutual / threshold /
- * border test on vectors.  Fills match_j / match_conf [n*l] exactly like gf_mnn_select (feed gf_compact_coarse).
- * Exact ties between row maxima resolve to the smallest j before the column test (see sim_fused.cu). */
+ * border test on vectors.  Fills match_j / match_conf [n*l] exactly like gf_mnn_select (feed gf_compact_coarse),
+ * including the reference's tie order (first j that is row maximum AND column maximum AND inside the border,
+ * coarse_matching.py:176-188): rows whose maximum is attained more than once and whose smallest-j candidate is rejected
+ * are re-scanned exactly by a third, normally empty, tensor pass (see sim_fused.cu).  The kernels run as 2-CTA clusters. */
 int64_t gf_coarse_match_fused_workspace_bytes(int n, int l, int s);
 int gf_coarse_match_fused(const void* a3, const void* b3, int n, int l, int s, int c3, float out_scale, float thr,
                           int border, int h0c, int w0c, int h1c, int w1c, void* workspace, int* match_j,
