@@ -1,6 +1,6 @@
 // fp32 FFMA reference of the backbone (resnet_fpn.py:15-40, 58-118) for the accurate mode of this library: the
-// golden-match parity tests need a backbone whose features agree with the fp32 reference to ~1e-5, which the bf16
-// tcgen05 path (conv_tc.cu) cannot give.  Same contract as gf_conv_bf16 / gf_upsample_add_bf16, NHWC fp32 throughout,
+// golden-match parity tests need a backbone whose features agree with the fp32 reference to ~1e-5, which the fp16
+// tcgen05 path (conv_tc.cu) cannot give.  Same contract as gf_conv_f16 / gf_upsample_add_f16, NHWC fp32 throughout,
 // any ksize in {1, 3, 7} (pad = ksize / 2), stride 1 or 2, any channel counts (the 1-channel stem included).
 // Not a product kernel: a plain smem-tiled SGEMM-style implicit GEMM (64 pixels x 64 channels per CTA, 4 x 4 per thread).
 #include "common.cuh"

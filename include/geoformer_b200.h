@@ -208,7 +208,8 @@ int gf_gather_anchor_kv(const float* k, int ldk, const float* v, int ldv, int n,
                         gf_stream_t stream);
 int gf_masked_softmax_rows(float* x, int heads, int n, int l, int s_pad, const int* cnt_per_sample, gf_stream_t stream);
 /* Fused version of the three steps above: one tcgen05 kernel per call, 128 queries of one (sample, head) per CTA,
- * two passes over 64-key tiles (row maxima, then exp / P V), scores stay in TMEM / shared memory.  Operands are
+ * ONE pass over 64-key tiles (running reference maximum raised lazily, accumulator rescaled only then; Q and P are
+ * tensor-memory operands, the row sums accumulate on the tensor core), scores never leave the SM.  Operands are
  * fp16 (kind::f16, fp32 accumulate) prepared by gf_gather_anchor_kv_f16: q16 [n*l, heads*dim] (converted query rows),
  * kg [heads][n][s_pad][dim], vt [heads][n][dim][s_pad] (zero beyond anchor_cnt[n]); s_pad % 64 == 0. */
 int gf_gather_anchor_kv_f16(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int n, int l,
