@@ -69,6 +69,8 @@ SIGNATURES = {
     "gf_ransac_workspace_bytes": (L, [I, I]),
     "gf_ransac_homography": (I, [P, P, P, P, L, I, I, F, ctypes.c_uint, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, I, P]),
     "gf_compact_fine": (I, [P, P, P, P, P, P, P, L, I, F, F, F, P, P, P, P, P, P]),
+    "gf_mask_rows": (I, [P, I, L, L, L, L, P, P]),
+    "gf_mask_fill_sim": (I, [P, I, I, I, P, P, F, P]),
 }
 
 

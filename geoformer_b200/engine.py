@@ -282,8 +282,12 @@ def _post_attention(lw: dict, x2d: torch.Tensor, msg: torch.Tensor, act: int, ou
     return ops.linear(h, lw["w2_16"] if h16 else lw["w2"], epi=EPI_LN, gamma=lw["n2w"], beta=lw["n2b"], residual=x2d, out=out)
 
 
-def loftr_layer(lw: dict, x: torch.Tensor, src: torch.Tensor, heads: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """LoFTR encoder layer with linear attention; x [n,L,C], src [n,S,C] -> [n,L,C] (written into `out` if given)."""
+def loftr_layer(lw: dict, x: torch.Tensor, src: torch.Tensor, heads: int, out: Optional[torch.Tensor] = None,
+                q_mask: Optional[torch.Tensor] = None, kv_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LoFTR encoder layer with linear attention; x [n,L,C], src [n,S,C] -> [n,L,C] (written into `out` if given).
+    q_mask [n,L] / kv_mask [n,S] (uint8, 0 = padded token; optional): the feature-mapped Q / K rows and the value rows of
+    padded tokens are cleared before the attention (linear_attention.py:37-43); the sequence length S that scales the
+    values keeps counting them (linear_attention.py:45)."""
     n, l, c = x.shape
     s = src.shape[1]
     d = c // heads
@@ -291,39 +295,58 @@ def loftr_layer(lw: dict, x: torch.Tensor, src: torch.Tensor, heads: int, out: O
     a16 = ops.act16()
     if x is src:
         qkv = ops.linear(x2d, lw["wqkv"], epi=EPI_ELU1, act_cols=2 * c, out_f16=a16)          # [Q=elu+1 | K=elu+1 | V]
+        if q_mask is not None and q_mask is kv_mask:
+            ops.mask_rows_(qkv, q_mask)                                                       # one pass over Q | K | V
+        else:
+            if q_mask is not None:
+                ops.mask_rows_(qkv, q_mask, 0, c)
+            if kv_mask is not None:
+                ops.mask_rows_(qkv, kv_mask, c, 2 * c)
         q, k, v, ldq, ldk = qkv, qkv[:, c:], qkv[:, 2 * c:], 3 * c, 3 * c
     else:
         q = ops.linear(x2d, lw["wq"], epi=EPI_ELU1, act_cols=c, out_f16=a16)
         kv = ops.linear(src.reshape(n * s, c), lw["wkv"], epi=EPI_ELU1, act_cols=c, out_f16=a16)
+        if q_mask is not None:
+            ops.mask_rows_(q, q_mask)
+        if kv_mask is not None:
+            ops.mask_rows_(kv, kv_mask)
         k, v, ldq, ldk = kv, kv[:, c:], c, 2 * c
     msg = ops.linattn(q, ldq, k, ldk, v, ldk, n, l, s, heads, d)
     return _post_attention(lw, x2d, msg, EPI_RELU, None if out is None else out.view(n * l, c)).view(n, l, c)
 
 
-def coarse_transformer(pw: PackedWeights, x0: torch.Tensor, x1: torch.Tensor, names, heads: int):
-    """loftr_module/transformer.py:82-104.  Same-size pairs run both images as one 2n-sample batch."""
+def coarse_transformer(pw: PackedWeights, x0: torch.Tensor, x1: torch.Tensor, names, heads: int,
+                       mask0: Optional[torch.Tensor] = None, mask1: Optional[torch.Tensor] = None):
+    """loftr_module/transformer.py:82-104.  Same-size pairs run both images as one 2n-sample batch.
+    mask0 [n,L] / mask1 [n,S] (uint8 token masks from ops.token_mask, both or neither): self layers mask queries and
+    sources with the image's own mask, cross layers the queries with their own and the sources with the other image's
+    (transformer.py:95-100)."""
     n = x0.shape[0]
     same = x0.shape == x1.shape
+    assert (mask0 is None) == (mask1 is None), "padding masks come in pairs (full_model.py:82-83)"
+    mm = None
     if same:
         X = torch.cat([x0, x1], 0)
         x0, x1 = X[:n], X[n:]
+        if mask0 is not None:
+            mm = torch.cat([mask0, mask1], 0)
     for lw, name in zip(pw.coarse, names):
         if name == "self":
             if same:
-                X = loftr_layer(lw, X, X, heads)
+                X = loftr_layer(lw, X, X, heads, q_mask=mm, kv_mask=mm)
                 x0, x1 = X[:n], X[n:]
             else:
-                x0 = loftr_layer(lw, x0, x0, heads)
-                x1 = loftr_layer(lw, x1, x1, heads)
+                x0 = loftr_layer(lw, x0, x0, heads, q_mask=mask0, kv_mask=mask0)
+                x1 = loftr_layer(lw, x1, x1, heads, q_mask=mask1, kv_mask=mask1)
         elif same:                                    # both results land in the halves of one fresh 2n-sample buffer
             Xn = torch.empty_like(X)
-            y0 = loftr_layer(lw, x0, x1, heads, out=Xn[:n])
-            loftr_layer(lw, x1, y0, heads, out=Xn[n:])         # sees the UPDATED feat0 (transformer.py:99-100)
+            y0 = loftr_layer(lw, x0, x1, heads, out=Xn[:n], q_mask=mask0, kv_mask=mask1)
+            loftr_layer(lw, x1, y0, heads, out=Xn[n:], q_mask=mask1, kv_mask=mask0)   # sees the UPDATED feat0 (transformer.py:99-100)
             X = Xn
             x0, x1 = X[:n], X[n:]
         else:
-            y0 = loftr_layer(lw, x0, x1, heads)
-            x0, x1 = y0, loftr_layer(lw, x1, y0, heads)
+            y0 = loftr_layer(lw, x0, x1, heads, q_mask=mask0, kv_mask=mask1)
+            x0, x1 = y0, loftr_layer(lw, x1, y0, heads, q_mask=mask1, kv_mask=mask0)
     return x0, x1
 
 
@@ -350,12 +373,22 @@ def fine_layer(lw: dict, x: torch.Tensor, src: torch.Tensor, heads: int) -> torc
 # coarse matching
 # --------------------------------------------------------------------------------------------
 def coarse_matching(f0: torch.Tensor, f1: torch.Tensor, thr: float, temperature: float, border: int,
-                    hw0_i, hw0_c, hw1_c, keep_conf: bool):
+                    hw0_i, hw0_c, hw1_c, keep_conf: bool, mask0: Optional[torch.Tensor] = None,
+                    mask1: Optional[torch.Tensor] = None):
+    """utils/coarse_matching.py:90-212.  With padding masks (uint8 [n,L] / [n,S]) the logits of padded rows / columns are
+    filled with -1e9 before the dual softmax (coarse_matching.py:120-124); that optional path runs on the materialising
+    kernels (the fused matcher never holds the L x S matrix to fill).  `border` is 0 on this path (coarse_matching.py:30),
+    which also makes mask_border_with_padding a no-op (coarse_matching.py:54-56)."""
     scale = hw0_i[0] / hw0_c[0]
-    if not keep_conf and ops._SIM_IMPL == "f16x3" and FUSED_MATCHING:
+    masked = mask0 is not None
+    assert masked == (mask1 is not None), "padding masks come in pairs (coarse_matching.py:121)"
+    assert not (masked and border > 0), "mask_border_with_padding (coarse_matching.py:54-68) is only built for border 0"
+    if not keep_conf and not masked and ops._SIM_IMPL == "f16x3" and FUSED_MATCHING:
         matches, counts = ops.coarse_match_fused(f0, f1, temperature, thr, border, hw0_c, hw1_c, scale)
         return matches, counts, None
     sim = ops.similarity(f0, f1, temperature)
+    if masked:
+        ops.mask_fill_sim_(sim, mask0, mask1, -1e9)
     conf, crmax, ccmax = ops.dual_softmax_(sim)
     matches, counts = ops.mutual_nearest(conf, crmax, ccmax, thr, border, hw0_c, hw1_c, scale)
     return matches, counts, (conf if keep_conf else None)

@@ -151,11 +151,9 @@ class GeoFormer(nn.Module):
     @torch.no_grad()
     def forward(self, data: Dict[str, torch.Tensor]):
         img0, img1 = data["image0"], data["image1"]
-        if data.get("mask0") is not None or data.get("mask1") is not None:
-            # padding masks only exist in the MegaDepth TRAINING collation (optional); ignoring them silently
-            # would change the result, so refuse
-            raise NotImplementedError("geoformer_b200.GeoFormer: padding masks (mask0/mask1) are not supported; "
-                                      "the inference wrappers never pass them")
+        if (data.get("mask0") is None) != (data.get("mask1") is None):
+            # full_model.py:82-83 reads both as soon as 'mask0' is present
+            raise ValueError("geoformer_b200.GeoFormer: padding masks come in pairs (mask0 AND mask1)")
         for k in ("scale0", "scale1", "dataset_name"):
             # scale0/scale1 rescale mkpts*_c / the geo windows / mkpts*_f (coarse_matching.py:194, geo_module.py:39-42,
             # fine_matching2.py:96-115); dataset_name forces a match during training (coarse_matching.py:182).  Both
@@ -189,24 +187,31 @@ class GeoFormer(nn.Module):
         dc = c0.shape[-1]
 
         # 2. positional encoding + coarse transformer (full_model.py:69-84)
+        # optional padding masks [N, h_c, w_c] (zero-padded batches; full_model.py:79-83): they reach the coarse
+        # transformer and both coarse-matching calls, nothing else (geo module and fine level never see them)
+        mk0 = mk1 = None
+        if data.get("mask0") is not None:
+            mk0 = ops.token_mask(data["mask0"], n, hw0_c[0] * hw0_c[1])
+            mk1 = ops.token_mask(data["mask1"], n, hw1_c[0] * hw1_c[1])
         with R("stage:coarse_transformer"):
             x0 = ops.add_posenc(c0.reshape(n, -1, dc), pw.pos_table(dc, *hw0_c))
             x1 = ops.add_posenc(c1.reshape(n, -1, dc), pw.pos_table(dc, *hw1_c))
-            t0, t1 = engine.coarse_transformer(pw, x0, x1, cfg["coarse"]["layer_names"], cfg["coarse"]["nhead"])
+            t0, t1 = engine.coarse_transformer(pw, x0, x1, cfg["coarse"]["layer_names"], cfg["coarse"]["nhead"], mk0, mk1)
 
         # 3. coarse matching -> geo module -> coarse matching (full_model.py:87-90)
         thr = cfg["match_coarse"]["thr"]
         temp = cfg["match_coarse"]["dsmax_temperature"]
         with R("stage:coarse_matching_1"):
             m1, counts1, conf1 = engine.coarse_matching(t0.contiguous(), t1.contiguous(), thr, temp, 0, hw0_i, hw0_c,
-                                                        hw1_c, self.materialize)
+                                                        hw1_c, self.materialize, mk0, mk1)
         ginfo = {} if self.capture else None
         with R("stage:geo_module(+host RANSAC)"):
             g0, g1 = engine.geo_module(pw, x0, x1, m1, counts1, hw0_i, hw1_i, hw0_c, hw1_c, gcfg["layer_names"],
                                        gcfg["nhead"], gcfg["window_size"], info=ginfo, ransac=self.ransac,
                                        ransac_hyps=self.ransac_hyps)
         with R("stage:coarse_matching_2"):
-            m2, counts2, conf2 = engine.coarse_matching(g0, g1, thr, temp, 0, hw0_i, hw0_c, hw1_c, self.materialize)
+            m2, counts2, conf2 = engine.coarse_matching(g0, g1, thr, temp, 0, hw0_i, hw0_c, hw1_c, self.materialize,
+                                                        mk0, mk1)
         data.update(m2)
         if self.materialize:
             data.update({"dect_conf_matrix": conf1, "conf_matrix": conf2})

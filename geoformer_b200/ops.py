@@ -255,6 +255,38 @@ def add_posenc(x: torch.Tensor, pe: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def token_mask(mask: torch.Tensor, n: int, tokens: int) -> torch.Tensor:
+    """data['mask0'] / data['mask1'] ([n, h_c, w_c] bool, 0 = padded; full_model.py:79-83) -> contiguous [n, tokens]
+    uint8 on the device, the layout gf_mask_rows / gf_mask_fill_sim read."""
+    if not mask.is_cuda:
+        raise _lib.GeoFormerLibError("geoformer_b200 ops need CUDA tensors (no CPU fallback)")
+    if mask.shape[0] != n or mask[0].numel() != tokens:
+        raise ValueError(f"padding mask of shape {tuple(mask.shape)} does not cover {n} x {tokens} coarse tokens")
+    m = mask.reshape(n, tokens)
+    return (m if m.dtype == torch.bool else m != 0).contiguous().view(torch.uint8)
+
+
+def mask_rows_(buf: torch.Tensor, mask: torch.Tensor, col0: int = 0, cols: Optional[int] = None) -> torch.Tensor:
+    """In place buf[r, col0:col0+cols] *= mask[r] for a 0/1 row mask (linear_attention.py:37-43: Q * q_mask,
+    K * kv_mask, values * kv_mask).  buf [rows, ld] fp32 or fp16, contiguous; mask uint8 [rows] (any shape, flattened)."""
+    assert buf.dim() == 2 and buf.is_contiguous() and buf.dtype in (torch.float32, torch.float16)
+    assert mask.dtype == torch.uint8 and mask.is_contiguous() and mask.numel() == buf.shape[0] and mask.device == buf.device
+    rows, ld = buf.shape
+    cols = ld - col0 if cols is None else cols
+    _call("gf_mask_rows", buf.data_ptr(), buf.element_size(), rows, ld, col0, cols, mask.data_ptr(), _stream())
+    return buf
+
+
+def mask_fill_sim_(sim: torch.Tensor, mask0: torch.Tensor, mask1: torch.Tensor, fill: float = -1e9) -> torch.Tensor:
+    """In place sim[b, i, j] = fill unless mask0[b, i] and mask1[b, j] (coarse_matching.py:120-124, INF = 1e9)."""
+    _chk(sim)
+    n, l, s = sim.shape
+    assert sim.is_contiguous() and mask0.dtype == mask1.dtype == torch.uint8
+    assert tuple(mask0.shape) == (n, l) and tuple(mask1.shape) == (n, s) and mask0.is_contiguous() and mask1.is_contiguous()
+    _call("gf_mask_fill_sim", sim.data_ptr(), n, l, s, mask0.data_ptr(), mask1.data_ptr(), float(fill), _stream())
+    return sim
+
+
 def linattn(q: torch.Tensor, ldq: int, k: torch.Tensor, ldk: int, v: torch.Tensor, ldv: int, n: int, l: int, s: int,
             heads: int, dim: int) -> torch.Tensor:
     """Linear attention.  q/k/v are (views into) row-major buffers with row strides ldq/ldk/ldv (floats)."""

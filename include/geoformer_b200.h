@@ -291,6 +291,22 @@ int gf_ransac_homography(const float* k0, const float* k1, const int64_t* b_ids,
                          int* anchor_idx0, int* anchor_cnt0, int* anchor_idx1, int* anchor_cnt1, int cap,
                          gf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optional padding masks data['mask0'] / data['mask1'] (zero-padded batches, model/full_model.py:79-83).  mask*: one
+ * byte per token, 0 = padded (a torch.bool tensor as is).
+ *   gf_mask_rows    : the `Q * q_mask`, `K * kv_mask`, `values * kv_mask` products of
+ *                     loftr_module/linear_attention.py:37-43, in place on the projection buffer: for every row r with
+ *                     mask[r] == 0 the elements buf[r*ld + col0 .. col0 + cols) are cleared (a product with a 0/1 mask).
+ *                     elem_bytes 2 (fp16 storage) or 4 (fp32); ld, col0, cols in elements, each a multiple of 4 bytes.
+ *   gf_mask_fill_sim: `sim_matrix.masked_fill_(~(mask_c0[..., None] * mask_c1[:, None]), -INF)` of
+ *                     utils/coarse_matching.py:120-124, in place on sim [n, l, s] (fill = -1e9 in the reference),
+ *                     between gf_similarity_* and gf_dual_softmax_stats.
+ */
+int gf_mask_rows(void* buf, int elem_bytes, int64_t rows, int64_t ld, int64_t col0, int64_t cols, const uint8_t* mask,
+                 gf_stream_t stream);
+int gf_mask_fill_sim(float* sim, int n, int l, int s, const uint8_t* mask0, const uint8_t* mask1, float fill,
+                     gf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

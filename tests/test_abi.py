@@ -71,13 +71,19 @@ def test_no_cpu_fallback():
         ops.similarity(torch.zeros(1, 8, 256), torch.zeros(1, 8, 256), 0.1)
 
 
-def test_padding_masks_are_refused_not_ignored():
+def test_training_only_keys_are_refused_not_ignored():
+    """scale0 / scale1 / dataset_name (training collations) would change the result if ignored; a lone mask0 is an error
+    as in the reference (full_model.py:82-83 reads both).  Padding masks themselves are supported (test_host_forward_
+    emulated.py on CPU, test_zz_gpu_masks.py on the GPU)."""
     from geoformer_b200.model.full_model import GeoFormer
     from geoformer_b200.model.geo_config import default_cfg as geo_cfg
     from geoformer_b200.model.loftr_src.loftr.utils.cvpr_ds_config import default_cfg
     m = GeoFormer(copy.deepcopy(default_cfg), dict(geo_cfg)).eval()
     x = torch.zeros(1, 1, 32, 32)
-    with pytest.raises(NotImplementedError):
+    for k, v in (("scale0", torch.ones(1, 2)), ("scale1", torch.ones(1, 2)), ("dataset_name", ["MegaDepth"])):
+        with pytest.raises(NotImplementedError):
+            m({"image0": x, "image1": x, k: v})
+    with pytest.raises(ValueError):
         m({"image0": x, "image1": x, "mask0": torch.ones(1, 4, 4, dtype=torch.bool)})
 
 

@@ -69,46 +69,14 @@ def test_synth_mixed_regime_layout():
     assert torch.equal(b[2], torch.roll(a[2], (8, 16), (1, 2)))
 
 
-def _emulate_ops(monkeypatch):
-    """torch emulations of the backbone operators of the C ABI with the SAME argument contract (packed weights, NHWC):
-    lets the host wiring of engine.backbone_forward_{ref,tc} (which layer, stride, activation, residual, packing) run on
-    CPU.  The arithmetic itself is what the GPU tests check."""
-    from geoformer_b200 import ops
-    act_fn = lambda y, act: F.relu(y) if act == 1 else (F.leaky_relu(y, 0.01) if act == 2 else y)
-
-    def conv_ref(x, wt, bias, residual=None, act=0, stride=1):                 # wt [k*k, cin, cout]
-        k = {1: 1, 9: 3, 49: 7}[wt.shape[0]]
-        w = wt.reshape(k, k, wt.shape[1], wt.shape[2]).permute(3, 2, 0, 1)
-        y = F.conv2d(x.permute(0, 3, 1, 2), w, bias, stride, k // 2).permute(0, 2, 3, 1)
-        return act_fn(y if residual is None else y + residual, act).contiguous()
-
-    def conv(x, wt, bias, residual=None, act=0, stride=1):                      # wt [cout_p, taps, cin_k] fp16
-        taps, cin_p = wt.shape[1], x.shape[-1]
-        k = 3 if taps == 9 else 1
-        w = wt[:, :, :cin_p].float().reshape(wt.shape[0], k, k, cin_p).permute(0, 3, 1, 2)
-        y = F.conv2d(x.float().permute(0, 3, 1, 2), w, bias, stride, k // 2).permute(0, 2, 3, 1)
-        return act_fn(y if residual is None else y + residual.float(), act).half().contiguous()
-
-    def stem_conv(img, wperm, bias):                                           # wperm [49, 128]
-        w = wperm.t().reshape(128, 1, 7, 7)
-        return F.relu(F.conv2d(img, w, bias, 2, 3)).permute(0, 2, 3, 1).half().contiguous()
-
-    def upsample_add(lateral, src):
-        up = F.interpolate(src.float().permute(0, 3, 1, 2), size=lateral.shape[1:3], mode="bilinear", align_corners=True)
-        return (lateral.float() + up.permute(0, 2, 3, 1)).to(lateral.dtype).contiguous()
-
-    for name, fn in (("conv_ref", conv_ref), ("upsample_add_ref", upsample_add), ("conv", conv), ("stem_conv", stem_conv),
-                     ("upsample_add", upsample_add)):
-        monkeypatch.setattr(ops, name, fn)
-
-
 def test_backbone_host_wiring_matches_oracle_on_cpu(monkeypatch):
     """Both backbone host paths (accurate: fp32 [taps][cin][cout] packs; product: tap-major fp16 packs with the 196-wide
     stage zero-padded to 200 channels) reproduce the oracle's resnet_fpn restatement when the kernels are replaced by
     torch emulations of their contracts: fp32 path to round-off, fp16 path within fp16 storage error."""
     from geoformer_b200 import synth
     from oracle import geoformer_oracle as O
-    _emulate_ops(monkeypatch)
+    from tests import emu_ops
+    emu_ops.install(monkeypatch)        # torch emulations of the operators' contracts (tests/emu_ops.py)
     sd = synth.make_state_dict(7, randomize_norm=True)
     img = torch.cat(synth.make_pairs(1, 64, 96, "shift", 3), 0)
     with torch.no_grad():

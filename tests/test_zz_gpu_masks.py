@@ -1,0 +1,204 @@
+"""GPU parity of the optional padding-mask path (data['mask0'] / data['mask1']; full_model.py:79-83,
+linear_attention.py:37-43, coarse_matching.py:120-124) through the C ABI: the two mask kernels against torch, a masked
+LoFTR layer against the oracle, and the full forward against the golden the unmodified reference produced
+(tests/golden/small_masked.npz).  The same host wiring runs on CPU in tests/test_host_forward_emulated.py.
+(This file sorts after the established suite on purpose: it was written in a session without GPU access.)"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from geoformer_b200 import synth
+from oracle import geoformer_oracle as O
+from tests.util import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from geoformer_b200 import ops as _ops
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    _ops.ensure_init(torch.device("cuda:0"))
+    return _ops
+
+
+def rnd(*shape, seed=0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_mask_rows_kernel_exact(ops, dtype):
+    """rows with mask 0 are cleared on the requested column range only; everything else is untouched (bit-exact)."""
+    rows, ld = 1003, 768
+    x = rnd(rows, ld, seed=1).to(dtype)
+    mask = (torch.rand(rows, generator=torch.Generator().manual_seed(2)) > 0.3)
+    for col0, cols in ((0, ld), (0, 256), (256, 512), (258, 6)):
+        want = x.clone()
+        want[~mask, col0:col0 + cols] = 0
+        got = ops.mask_rows_(x.cuda().contiguous(), mask.cuda().view(torch.uint8), col0, cols).cpu()
+        assert torch.equal(got, want), (dtype, col0, cols)
+    # all rows kept / all rows cleared / no rows at all
+    ones, zeros = torch.ones(rows, dtype=torch.uint8).cuda(), torch.zeros(rows, dtype=torch.uint8).cuda()
+    assert torch.equal(ops.mask_rows_(x.cuda().contiguous(), ones).cpu(), x)
+    assert ops.mask_rows_(x.cuda().contiguous(), zeros).abs().max().item() == 0
+    ops.mask_rows_(torch.empty((0, 8), device="cuda", dtype=dtype), torch.empty(0, device="cuda", dtype=torch.uint8))
+    from geoformer_b200._lib import GeoFormerLibError
+    if dtype == torch.float16:
+        with pytest.raises(GeoFormerLibError):          # 2-byte offset: not a whole 32-bit word
+            ops.mask_rows_(x.cuda().contiguous(), ones, 1, 4)
+
+
+def test_mask_fill_sim_kernel_exact(ops):
+    n, l, s = 2, 301, 517
+    sim = rnd(n, l, s, seed=3)
+    g = torch.Generator().manual_seed(4)
+    m0, m1 = torch.rand(n, l, generator=g) > 0.2, torch.rand(n, s, generator=g) > 0.2
+    m0[1, :] = False                                    # a fully padded sample side
+    want = sim.masked_fill(~(m0[..., None] * m1[:, None]).bool(), -1e9)          # coarse_matching.py:120-124
+    got = ops.mask_fill_sim_(sim.cuda().contiguous(), m0.cuda().view(torch.uint8), m1.cuda().view(torch.uint8)).cpu()
+    assert torch.equal(got, want)
+
+
+def test_masked_dual_softmax_and_matches_vs_oracle(ops):
+    """-1e9 logits through the statistics / confidence / mutual-nearest kernels: padded rows x padded columns tie at
+    1 / (L S) exactly as in the reference, the first padded column wins; (b, i, j) lists identical to the oracle."""
+    n, hc, wc, c = 2, 9, 12, 256
+    l = hc * wc
+    f0, f1 = rnd(n, l, c, seed=5), rnd(n, l, c, seed=6)
+    f1[:, :60] = f0[:, :60] + 0.05 * rnd(n, 60, c, seed=7)       # some genuine mutual matches
+    m0 = torch.ones(n, hc, wc, dtype=torch.bool); m1 = torch.ones(n, hc, wc, dtype=torch.bool)
+    m0[:, 7:] = False; m1[0, :, 10:] = False; m1[1, 8:] = False
+    mc0, mc1 = m0.flatten(-2), m1.flatten(-2)
+    conf = O.dual_softmax_conf(f0, f1, 0.1, mc0, mc1)
+    want = O.coarse_match(conf, 0.0, (hc * 8, wc * 8), (hc, wc), (hc, wc))
+    sim = ops.similarity(f0.cuda(), f1.cuda(), 0.1, impl="ref")
+    ops.mask_fill_sim_(sim, mc0.cuda().view(torch.uint8).contiguous(), mc1.cuda().view(torch.uint8).contiguous())
+    cg, crmax, ccmax = ops.dual_softmax_(sim)
+    assert (cg.cpu() - conf).abs().max().item() <= 1e-6 + 1e-5 * conf.max().item()
+    got, counts = ops.mutual_nearest(cg, crmax, ccmax, 0.0, 0, (hc, wc), (hc, wc), 8.0)
+    for k in ("b_ids", "i_ids", "j_ids"):
+        assert torch.equal(got[k].cpu(), want[k]), k
+    assert torch.equal(got["mkpts1_c"].cpu(), want["mkpts1_c"])
+    assert int(counts.sum()) == want["b_ids"].numel() and (~mc0[want["b_ids"], want["i_ids"]]).any()   # padded rows do match at thr 0
+
+
+@pytest.mark.parametrize("mode", ["accurate", "shipped"])
+def test_masked_loftr_layer_vs_oracle(ops, mode):
+    """One coarse LoFTR layer (cross: query and source masks of two different sequences; self: one mask for both; no
+    mask) against O.encoder_layer(q_mask, kv_mask): 2e-5 on the fp32 FFMA kernels, the tf32 / fp16-storage bar (8e-3) on the shipped ones."""
+    from geoformer_b200 import engine
+    sd = synth.make_state_dict(7, True)
+    pre = "loftr_coarse.layers.0"
+    n, l, s, c = 2, 300, 200, 256
+    x0, x1 = rnd(n, l, c, seed=8), rnd(n, s, c, seed=9)
+    g = torch.Generator().manual_seed(10)
+    q_mask, kv_mask = torch.rand(n, l, generator=g) > 0.25, torch.rand(n, s, generator=g) > 0.25
+    if mode == "accurate":
+        ops.set_precision(linear="ref", similarity="ref", attention="ref", activations="f32")
+        tol = 2e-5
+    else:
+        tol = 8e-3
+    pw = engine.PackedWeights(sd, torch.device("cuda:0"), torch.float16)
+    lw = pw.coarse[0]
+    u8 = lambda m: m.cuda().view(torch.uint8).contiguous()
+    with torch.no_grad():
+        want_cross = O.encoder_layer(sd, pre, x0, x1, 8, q_mask=q_mask, kv_mask=kv_mask)
+        want_self = O.encoder_layer(sd, pre, x0, x0, 8, q_mask=q_mask, kv_mask=q_mask)
+        want_nomask = O.encoder_layer(sd, pre, x0, x1, 8)
+    got_cross = engine.loftr_layer(lw, x0.cuda(), x1.cuda(), 8, q_mask=u8(q_mask), kv_mask=u8(kv_mask)).cpu()
+    xs = x0.cuda()
+    qm = u8(q_mask)
+    got_self = engine.loftr_layer(lw, xs, xs, 8, q_mask=qm, kv_mask=qm).cpu()
+    got_nomask = engine.loftr_layer(lw, x0.cuda(), x1.cuda(), 8).cpu()
+    for got, want in ((got_cross, want_cross), (got_self, want_self), (got_nomask, want_nomask)):
+        assert (got - want).abs().max().item() <= tol * max(1.0, want.abs().max().item())
+    assert (want_cross - want_nomask).abs().max().item() > 1e-2          # the masks matter on these inputs
+    # padded QUERY rows receive a zero message: the layer output there is x + LN2(mlp(cat[x, LN1(0)])) - covered above;
+    # additionally the result must not depend on what the padded SOURCE rows contain
+    x1b = x1.clone(); x1b[~kv_mask] = 123.0
+    again = engine.loftr_layer(lw, x0.cuda(), x1b.cuda(), 8, q_mask=u8(q_mask), kv_mask=u8(kv_mask)).cpu()
+    assert (again - got_cross).abs().max().item() <= 1e-6
+
+
+def _build(sd, mode):
+    from geoformer_b200 import ops
+    from geoformer_b200.model.full_model import GeoFormer
+    from geoformer_b200.model.geo_config import default_cfg as geo_cfg
+    from geoformer_b200.model.loftr_src.loftr.utils.cvpr_ds_config import default_cfg
+    g = dict(geo_cfg)
+    g["coarse_thr"] = 0.0
+    m = GeoFormer(copy.deepcopy(default_cfg), g)
+    m.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=True)
+    m.backbone_precision = "fp32" if mode == "accurate" else "f16"
+    m = m.eval().to("cuda:0")
+    if mode == "accurate":
+        ops.set_precision(linear="ref", similarity="ref", attention="ref", activations="f32")
+    m.capture = True
+    return m
+
+
+def _padded_case(n, h, w, seed0):
+    """Inputs of tests/golden/make_golden.py::masked_case."""
+    im0, im1 = synth.make_pairs(n, h, w, "dense", seed0)
+    hc, wc = h // 8, w // 8
+    m0, m1 = torch.zeros(n, hc, wc, dtype=torch.bool), torch.zeros(n, hc, wc, dtype=torch.bool)
+    for b in range(n):
+        m0[b, :hc - 2 - b, :wc - 3] = True
+        m1[b, :hc - 1, :wc - 4 - b] = True
+    im0 = im0 * F.interpolate(m0[:, None].float(), scale_factor=8, mode="nearest")
+    im1 = im1 * F.interpolate(m1[:, None].float(), scale_factor=8, mode="nearest")
+    return im0, im1, m0, m1
+
+
+def _final_set(d):
+    k = torch.cat([torch.as_tensor(np.asarray(d["mkpts0_f"].cpu() if torch.is_tensor(d["mkpts0_f"]) else d["mkpts0_f"])).float(),
+                   torch.as_tensor(np.asarray(d["mkpts1_f"].cpu() if torch.is_tensor(d["mkpts1_f"]) else d["mkpts1_f"])).float()], 1)
+    b = d["m_bids"].cpu().tolist() if torch.is_tensor(d["m_bids"]) else np.asarray(d["m_bids"]).tolist()
+    return {(int(bb), *r) for bb, r in zip(b, k.long().tolist())}
+
+
+def test_masked_forward_accurate_mode_vs_reference_golden(golden_dir):
+    """fp32 kernels: coarse features within 5e-5 of the reference run with masks; the final match set agrees with the
+    reference's (bar >= 0.99 of the union; the unmasked goldens reproduce exactly in this mode, identity is expected and
+    the measured value is printed)."""
+    g = load_golden(golden_dir, "small_masked")
+    h, w, n, seed0, rnd_norm = [int(v) for v in g["meta"]]
+    model = _build(synth.make_state_dict(7, bool(rnd_norm)), "accurate")
+    im0, im1, m0, m1 = _padded_case(n, h, w, seed0)
+    d = model({"image0": im0.cuda(), "image1": im1.cuda(), "mask0": m0.cuda(), "mask1": m1.cuda()})
+    st = d["_stages"]
+    rel = lambda a, b: ((a.float().cpu() - torch.from_numpy(b)).abs().max() / np.abs(b).max()).item()
+    assert rel(st["coarse0"], g["coarse0"]) <= 5e-5 and rel(st["coarse1"], g["coarse1"]) <= 5e-5
+    got, want = _final_set(d), _final_set(g)
+    iou = len(got & want) / max(1, len(got | want))
+    coarse_same = (d["i_ids"].numel() == len(g["i_ids"]) and np.array_equal(d["i_ids"].cpu().numpy(), g["i_ids"])
+                   and np.array_equal(d["j_ids"].cpu().numpy(), g["j_ids"]))
+    print(f"masked forward, accurate mode: final-match IoU {iou:.4f} ({len(got)} vs {len(want)}), coarse list identical: {coarse_same}")
+    assert iou >= 0.99
+    assert abs(d["i_ids"].numel() - len(g["i_ids"])) <= 2
+
+
+def test_masked_forward_shipped_configuration(golden_dir):
+    """The shipped configuration (fp16 tcgen05 backbone, tf32 / fp16 projections) with masks: the fused matcher is
+    bypassed for the materialising kernels, results stay near the reference run (>= 0.7 of its final matches on these
+    12 x 16-token images; 0.87 with exact arithmetic behind the same fp16 storage, tests/test_host_forward_emulated.py),
+    and the unmasked call of the same model still takes the fused route."""
+    from geoformer_b200 import ops
+    g = load_golden(golden_dir, "small_masked")
+    h, w, n, seed0, rnd_norm = [int(v) for v in g["meta"]]
+    model = _build(synth.make_state_dict(7, bool(rnd_norm)), "shipped")
+    im0, im1, m0, m1 = _padded_case(n, h, w, seed0)
+    d = model({"image0": im0.cuda(), "image1": im1.cuda(), "mask0": m0.cuda(), "mask1": m1.cuda()})
+    got, want = _final_set(d), _final_set(g)
+    print(f"masked forward, shipped configuration: {len(got & want)} of {len(want)} reference matches ({len(got)} found)")
+    assert len(got & want) >= 0.7 * len(want)
+    with pytest.raises(ValueError):
+        model({"image0": im0.cuda(), "image1": im1.cuda(), "mask0": m0.cuda()})
+    with pytest.raises(ValueError):
+        model({"image0": im0.cuda(), "image1": im1.cuda(), "mask0": m0[:, :5].cuda(), "mask1": m1.cuda()})
+    n0 = ops._lib.launch_count()
+    plain = model({"image0": im0.cuda(), "image1": im1.cuda()})
+    assert plain["mkpts0_f"].shape[0] > 0 and ops._lib.launch_count() > n0
