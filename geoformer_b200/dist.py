@@ -88,6 +88,26 @@ def all_gather_match_block(block: torch.Tensor, group=None, async_op: bool = Fal
     return out, work
 
 
+def all_gather_rows(rows: torch.Tensor, group=None) -> torch.Tensor:
+    """Variable-length gather of per-item records: rows [m, k] (m differs per rank, k does not) -> the concatenation over
+    ranks in rank order, identical on every rank.  Two collectives: the counts, then one padded all_gather_into_tensor
+    (geoformer_b200.hpatches gathers its per-pair metric records with it)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return rows
+    assert rows.dim() == 2
+    cnt = torch.tensor([rows.shape[0]], device=rows.device, dtype=torch.int64)
+    cnts = torch.empty(world, device=rows.device, dtype=torch.int64)
+    dist.all_gather_into_tensor(cnts, cnt, group=group)
+    sizes = [int(c) for c in cnts.tolist()]
+    cap = max(1, max(sizes))
+    pad = torch.zeros((cap, rows.shape[1]), device=rows.device, dtype=rows.dtype)
+    pad[:rows.shape[0]] = rows
+    out = torch.empty((world, cap, rows.shape[1]), device=rows.device, dtype=rows.dtype)
+    dist.all_gather_into_tensor(out.view(-1), pad.view(-1), group=group)
+    return torch.cat([out[r, :s] for r, s in enumerate(sizes)], 0)
+
+
 def reduce_sums(values: Sequence[float], device, group=None) -> List[float]:
     """Sum scalars (pair counts, match counts, error sums) over ranks."""
     t = torch.tensor(list(values), device=device, dtype=torch.float64)

@@ -6,12 +6,12 @@ fp32 tensor) and resized + normalised on the GPU by a kernel that reproduces cv2
 bit-exactly, so the model sees the same tensor as with the reference loader."""
 from __future__ import annotations
 
-from typing import Callable, Tuple, Union
+from typing import Callable, Optional, Tuple, Union
 
 import numpy as np
 import torch
 
-from . import _lib
+from . import ops
 
 
 def resize_dims(wo: int, ho: int, imsize=None, dfactor: int = 1, value_to_scale: Callable = max,
@@ -27,17 +27,21 @@ def resize_dims(wo: int, ho: int, imsize=None, dfactor: int = 1, value_to_scale:
 
 
 def gray_to_tensor(im: np.ndarray, device: torch.device, imsize=None, dfactor: int = 8,
-                   value_to_scale: Callable = min, aspan: bool = False):
-    """uint8 [ho, wo] grayscale image -> (fp32 [1,1,ht,wt] CUDA tensor in [0,1], (sx, sy))."""
+                   value_to_scale: Callable = min, aspan: bool = False, out: Optional[torch.Tensor] = None):
+    """uint8 [ho, wo] grayscale image -> (fp32 [1,1,ht,wt] CUDA tensor in [0,1], (sx, sy)).
+    out: optional fp32 [ht, wt] destination on the device (e.g. one image of a batch tensor) - then `out` is returned."""
     assert im.dtype == np.uint8 and im.ndim == 2
     ho, wo = im.shape
     wt, ht, scale = resize_dims(wo, ho, imsize=imsize, dfactor=dfactor, value_to_scale=value_to_scale, aspan=aspan)
-    host = torch.from_numpy(np.ascontiguousarray(im)).pin_memory()
-    src = host.to(device, non_blocking=True)
-    dst = torch.empty((1, 1, ht, wt), device=device, dtype=torch.float32)
-    idx = device.index if device.index is not None else torch.cuda.current_device()
-    _lib.init(idx)
-    _lib.call("gf_resize_gray_u8", src.data_ptr(), ho, wo, dst.data_ptr(), ht, wt, torch.cuda.current_stream().cuda_stream)
+    host = torch.from_numpy(np.ascontiguousarray(im))
+    src = (host.pin_memory() if device.type == "cuda" else host).to(device, non_blocking=True)
+    if out is not None:
+        assert tuple(out.shape) == (ht, wt), (tuple(out.shape), (ht, wt))
+        dst = out
+    else:
+        dst = torch.empty((1, 1, ht, wt), device=device, dtype=torch.float32)
+    ops.ensure_init(device)
+    ops.resize_gray_u8(src, dst if out is not None else dst[0, 0])
     return dst, scale
 
 

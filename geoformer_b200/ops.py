@@ -46,11 +46,14 @@ def set_precision(linear: Optional[str] = None, similarity: Optional[str] = None
 
 
 class _Profile:
-    """Optional CUDA-event instrumentation (bench.py): regions are timed on the launching stream."""
+    """Optional instrumentation: CUDA-event timing of regions on the launching stream (bench.py --stage-times) and /
+    or NVTX ranges around every stage and C-ABI call (GF_NVTX=1, or PROFILE.nvtx = True) so that a timeline profiler
+    names them.  Both are off by default and cost one attribute test per call when off."""
 
     def __init__(self):
         self.pattern = None
         self.records = {}
+        self.nvtx = os.environ.get("GF_NVTX", "0") == "1"
 
     def enable(self, pattern: str) -> None:
         self.pattern, self.records = pattern, {}
@@ -66,6 +69,9 @@ class _Profile:
             self.prof, self.name = prof, name
 
         def __enter__(self):
+            self.pushed = self.prof.nvtx
+            if self.pushed:
+                torch.cuda.nvtx.range_push(self.name)
             if self.prof.on(self.name):
                 self.e0 = torch.cuda.Event(enable_timing=True)
                 self.e1 = torch.cuda.Event(enable_timing=True)
@@ -78,6 +84,8 @@ class _Profile:
             if self.e0 is not None:
                 self.e1.record()
                 self.prof.records.setdefault(self.name, []).append((self.e0, self.e1))
+            if self.pushed:
+                torch.cuda.nvtx.range_pop()
             return False
 
     def region(self, name: str):
@@ -97,7 +105,7 @@ PROFILE = _Profile()
 
 def _call(name: str, *args, tag: str = "") -> None:
     """Launch through the C ABI, optionally timed as region 'k:<name><tag>'."""
-    if PROFILE.pattern is None:
+    if PROFILE.pattern is None and not PROFILE.nvtx:
         _lib.call(name, *args)
     else:
         with PROFILE.region("k:" + name[3:] + tag):
@@ -565,3 +573,17 @@ def ransac_homography(k0: torch.Tensor, k1: torch.Tensor, b_ids: torch.Tensor, c
           hm[1].data_ptr(), has_h.data_ptr(), inlier.data_ptr(), map0.data_ptr(), map1.data_ptr(), aidx[0].data_ptr(),
           acnt[0].data_ptr(), aidx[1].data_ptr(), acnt[1].data_ptr(), cap, _stream(), tag="ransac")
     return hm, has_h, inlier[:m], aidx, acnt
+
+
+# --------------------------------------------------------------------------------------------
+# image ingest (csrc/ingest.cu) — the step before the path (eval_tool/immatch/utils/data_io.py:48-62)
+# --------------------------------------------------------------------------------------------
+def resize_gray_u8(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """cv2.resize(src, (wt, ht)) (INTER_LINEAR on uint8, bit-exact) followed by to_tensor's / 255:
+    src uint8 [ho, wo] (device) -> dst fp32 [ht, wt] (device, contiguous; may be a slice of a batch tensor)."""
+    if not src.is_cuda or not dst.is_cuda:
+        raise _lib.GeoFormerLibError("geoformer_b200 ops need CUDA tensors (no CPU fallback)")
+    assert src.dtype == torch.uint8 and src.dim() == 2 and src.is_contiguous()
+    assert dst.dtype == torch.float32 and dst.dim() == 2 and dst.is_contiguous()
+    _call("gf_resize_gray_u8", src.data_ptr(), src.shape[0], src.shape[1], dst.data_ptr(), dst.shape[0], dst.shape[1], _stream())
+    return dst

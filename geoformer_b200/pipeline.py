@@ -16,10 +16,14 @@ import torch
 
 
 class MatchPipeline:
-    def __init__(self, model, depth: int = 2, device: Optional[torch.device] = None, freeze_gc: bool = False):
+    def __init__(self, model, depth: int = 2, device: Optional[torch.device] = None, freeze_gc: bool = False,
+                 prepare: Optional[Callable] = None):
         """freeze_gc: move the objects alive at the first run() to the permanent GC generation (gc.freeze()) — a
-        process-wide side effect, hence opt-in; bench.py uses it (see run())."""
+        process-wide side effect, hence opt-in; bench.py uses it (see run()).
+        prepare(batch) -> data dict: optional hook run by the worker ON THE BATCH'S STREAM before the forward (e.g. the
+        GPU image ingest of geoformer_b200.hpatches: uint8 upload + resize land on the stream that consumes them)."""
         self.model = model
+        self.prepare = prepare
         self.freeze_gc = freeze_gc
         self.depth = max(1, int(depth))
         self.device = device or next(model.parameters()).device
@@ -29,6 +33,8 @@ class MatchPipeline:
     def _job(self, slot: int, data: Dict[str, torch.Tensor], post: Optional[Callable]):
         s = self.streams[slot]
         with torch.cuda.stream(s):
+            if self.prepare is not None:
+                data = self.prepare(data)
             data = {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) and not v.is_cuda else v)
                     for k, v in data.items()}
             out = self.model(data)

@@ -365,6 +365,14 @@ def fine_match(f0, f1, temperature, thr, mkpts0_c, mkpts1_c, b_ids, window, coar
     return out, (conf if want_matrix else None), (sel.to(torch.int32), fi.to(torch.int32), fj.to(torch.int32), fconf)
 
 
+def resize_gray_u8(src, dst):
+    """gf_resize_gray_u8: cv2.resize (INTER_LINEAR, uint8) + / 255 (the GPU kernel is bit-exact to cv2, test_next_rows)."""
+    import cv2
+    _count("resize_gray_u8")
+    dst.copy_(torch.from_numpy(cv2.resize(src.numpy(), (dst.shape[1], dst.shape[0]))).float().div(255))
+    return dst
+
+
 # ------------------------------------------------------------------------------------------------ plumbing
 class _NoStream:
     cuda_stream = 0
@@ -379,7 +387,7 @@ class _NoStream:
 OPS = ("linear", "conv", "conv_ref", "stem_conv", "upsample_add", "add_posenc", "token_mask", "mask_rows_",
        "mask_fill_sim_", "linattn", "linattn_window", "fine_layer_fused", "similarity", "dual_softmax_", "mutual_nearest",
        "coarse_match_fused", "geo_window_table", "geo_self_attention", "geo_cross_attention", "select_rows_", "fine_gather",
-       "gather_rows", "fine_match")
+       "gather_rows", "fine_match", "resize_gray_u8")
 
 
 def install(monkeypatch):

@@ -274,9 +274,54 @@ def eval_and_ingest_case():
     print("eval_ingest", auc, fire, t.shape)
 
 
+def hpatches_case():
+    """The reference's own benchmark loop (eval_tool/immatch/utils/hpatches_helper.py::eval_hpatches, unmodified) on a
+    synthetic HPatches-shaped tree with a deterministic stand-in matcher (tests/util.py): everything it logs, prints and
+    hands to its summary functions, for both wrapper conventions (no_match_upscale on / off), stored as JSON."""
+    import contextlib
+    import io
+    import json
+    import tempfile
+    import_reference()
+    import eval_tool.immatch.utils.hpatches_helper as helper
+    from tests.util import make_hpatches_tree, stub_matcher
+    out = {}
+    with tempfile.TemporaryDirectory() as root:
+        make_hpatches_tree(root)
+        for tag, scaled, task, rthr in (("scaled_both", True, "both", 3), ("plain_both", False, "both", 3),
+                                        ("scaled_homography", True, "homography", 2)):
+            logged, grabbed = [], {}
+            orig_m, orig_h = helper.eval_summary_matching, helper.eval_summary_homography
+
+            def spy_m(results, thres=[1, 3, 5, 10], save_npy=None):
+                i_err, v_err, (seq_type, n_feats, n_matches) = results
+                grabbed.update(i_err={int(k): float(v) for k, v in i_err.items()}, v_err={int(k): float(v) for k, v in v_err.items()},
+                               seq_type=[str(x) for x in seq_type], n_feats=[int(x) for x in n_feats], n_matches=[int(x) for x in n_matches])
+                return orig_m(results, thres, save_npy)
+
+            def spy_h(dists_sa, dists_si, dists_sv, thres):
+                grabbed.update(dists_sa=[float(x) for x in dists_sa], dists_si=[float(x) for x in dists_si], dists_sv=[float(x) for x in dists_sv])
+                r = orig_h(dists_sa, dists_si, dists_sv, thres)
+                grabbed["auc"] = float(r)
+                return r
+            helper.eval_summary_matching, helper.eval_summary_homography = spy_m, spy_h
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                helper.eval_hpatches(stub_matcher(scaled), root, "stub", task=task, scale_H=scaled, h_solver="cv",
+                                     ransac_thres=rthr, lprint_=logged.append, print_out=False)
+            helper.eval_summary_matching, helper.eval_summary_homography = orig_m, orig_h
+            out[tag] = dict(scaled=scaled, task=task, ransac_thres=rthr, logged=logged, stdout=buf.getvalue(), **grabbed)
+            print(tag, "logged", len(logged), "lines; auc", grabbed.get("auc"))
+    with open(os.path.join(HERE, "hpatches_eval.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if "--only-hpatches" in sys.argv:
+        hpatches_case()
+        sys.exit(0)
     if "--only-masked" in sys.argv:
         masked_case("small_masked", 96, 128, 2, 40)
         sys.exit(0)
