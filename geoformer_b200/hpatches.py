@@ -298,6 +298,45 @@ def summary_homography(recs: np.ndarray, thres: Sequence[float]) -> Tuple[str, f
 
 
 # ------------------------------------------------------------------------------------------------ the benchmark loop
+def run_pairs(matcher, paths: Sequence[Tuple[str, str]], score: Callable, rec_len: int, world: int = 1,
+              score_threads: int = 8) -> Tuple[np.ndarray, float, bool]:
+    """The part every benchmark loop shares: run `matcher` over this rank's pairs — ``match_many`` when it has one
+    (``BatchedMatcher``), else the reference's serial ``matcher(im1_path, im2_path)`` calls with their try / except
+    (hpatches_helper.py:173-196) — score every result with ``score(position, result | Exception, seconds)`` in a thread
+    pool (cv2.findHomography releases the GIL) and, with world > 1, all-gather the records of all ranks.
+    Returns (records [pairs, rec_len], wall seconds of this rank, whether per-pair times exist)."""
+    t_start = time.time()
+    if hasattr(matcher, "match_many"):
+        stream: Iterable = matcher.match_many(list(paths))
+        timed = False
+    else:
+        def serial():
+            for k, (p1, p2) in enumerate(paths):
+                t0 = time.time()
+                try:
+                    yield k, (matcher(p1, p2), time.time() - t0)
+                except Exception as e:      # noqa: BLE001
+                    print(str(e))
+                    yield k, (e, time.time() - t0)
+        stream, timed = serial(), True
+    futures = []
+    with ThreadPoolExecutor(max_workers=score_threads) as ex:
+        for k, res in stream:
+            secs = 0.0
+            if timed:
+                res, secs = res
+            if isinstance(res, Exception) and not timed:
+                print(str(res))
+            futures.append(ex.submit(score, k, res, secs))
+        recs = np.stack([f.result() for f in futures]) if futures else np.zeros((0, rec_len))
+    wall = time.time() - t_start
+    if world > 1:
+        from .dist import all_gather_rows
+        dev = getattr(matcher, "device", torch.device("cpu"))
+        recs = all_gather_rows(torch.from_numpy(recs).to(dev)).cpu().numpy()
+    return recs, wall, timed
+
+
 def eval_hpatches(matcher, data_root: str, method: str = "", task: str = "both", scale_H: bool = False,
                   ransac_thres: float = 2, thres: Sequence[float] = (1, 3, 5, 10), lprint_: Callable = print,
                   debug: bool = False, rank: int = 0, world: int = 1, score_threads: int = 8) -> dict:
@@ -314,35 +353,9 @@ def eval_hpatches(matcher, data_root: str, method: str = "", task: str = "both",
     pairs = list_pairs(data_root, debug)
     lprint_(f"\n>>>>Eval hpatches: task={task} method={method} scale_H={scale_H} rthres={ransac_thres} thres={thres} ")
     mine = [pairs[i] for i in range(rank, len(pairs), world)]
-    t_start = time.time()
-    if hasattr(matcher, "match_many"):
-        stream: Iterable = matcher.match_many([(p.im1, p.im2) for p in mine])
-        timed = False
-    else:
-        def serial():
-            for k, p in enumerate(mine):
-                t0 = time.time()
-                try:
-                    yield k, (matcher(p.im1, p.im2), time.time() - t0)
-                except Exception as e:      # noqa: BLE001 - hpatches_helper.py:193-196
-                    print(str(e))
-                    yield k, (e, time.time() - t0)
-        stream, timed = serial(), True
-    futures = []
-    with ThreadPoolExecutor(max_workers=score_threads) as ex:          # cv2.findHomography releases the GIL
-        for k, res in stream:
-            secs = 0.0
-            if timed:
-                res, secs = res
-            if isinstance(res, Exception) and not timed:
-                print(str(res))
-            futures.append(ex.submit(score_pair, mine[k], res, task, scale_H, ransac_thres, secs))
-        recs = np.stack([f.result() for f in futures]) if futures else np.zeros((0, REC))
-    wall = time.time() - t_start
-    if world > 1:
-        from .dist import all_gather_rows
-        dev = getattr(matcher, "device", torch.device("cpu"))
-        recs = all_gather_rows(torch.from_numpy(recs).to(dev)).cpu().numpy()
+    recs, wall, timed = run_pairs(matcher, [(p.im1, p.im2) for p in mine],
+                                  lambda k, res, secs: score_pair(mine[k], res, task, scale_H, ransac_thres, secs),
+                                  REC, world, score_threads)
     recs = recs[np.argsort(recs[:, 0], kind="stable")]
     assert len(recs) == len(pairs) and np.array_equal(recs[:, 0], np.arange(len(pairs))), "every pair exactly once"
     o = 5 + len(THRES_RANGE)

@@ -316,11 +316,61 @@ def hpatches_case():
         json.dump(out, fh, indent=1)
 
 
+def fire_isc_case():
+    """The reference's FIRE and ISC-HE benchmark loops (fire_helper.eval_fire, my_helper.eval_homography_my, unmodified)
+    on synthetic inputs with deterministic stand-in matchers (tests/util.py): logged lines, stdout, returned value and
+    the per-pair distances handed to the summaries."""
+    import contextlib
+    import io
+    import json
+    import tempfile
+    import_reference()
+    import eval_tool.immatch.utils.fire_helper as fire
+    import eval_tool.immatch.utils.my_helper as isc
+    from tests.util import make_fire_tree, make_isc_tree, stub_matcher_named
+    out = {}
+    with tempfile.TemporaryDirectory() as root:
+        files, im_dir, gt_dir = make_fire_tree(os.path.join(root, "fire"))
+        triples = make_isc_tree(os.path.join(root, "isc"))
+        for tag, scaled, rthr in (("fire_scaled", True, 15), ("fire_plain", False, 15), ("isc_scaled", True, 3), ("isc_plain", False, 3)):
+            logged, grabbed = [], {}
+            buf = io.StringIO()
+            if tag.startswith("fire"):
+                orig = fire.eval_summary_homography
+
+                def spy(ss, sp, sa):
+                    grabbed.update(dists_ss=[float(x) for x in ss], dists_sp=[float(x) for x in sp], dists_sa=[float(x) for x in sa])
+                    return orig(ss, sp, sa)
+                fire.eval_summary_homography = spy
+                with contextlib.redirect_stdout(buf):
+                    r = fire.eval_fire(stub_matcher_named("fire", scaled), files, im_dir, gt_dir, "stub", task="homography",
+                                       scale_H=scaled, h_solver="cv", ransac_thres=rthr, lprint_=logged.append)
+                fire.eval_summary_homography = orig
+            else:
+                orig = isc.eval_summary_homography
+
+                def spy(sa, thres):
+                    grabbed.update(dists_all=[float(x) for x in sa])
+                    return orig(sa, thres)
+                isc.eval_summary_homography = spy
+                with contextlib.redirect_stdout(buf):
+                    r = isc.eval_homography_my(stub_matcher_named("isc", scaled), triples, "stub", task="homography",
+                                               scale_H=scaled, h_solver="cv", ransac_thres=rthr, lprint_=logged.append)
+                isc.eval_summary_homography = orig
+            out[tag] = dict(scaled=scaled, ransac_thres=rthr, logged=logged, stdout=buf.getvalue(), value=float(r), **grabbed)
+            print(tag, "value", float(r))
+    with open(os.path.join(HERE, "fire_isc_eval.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
     if "--only-hpatches" in sys.argv:
         hpatches_case()
+        sys.exit(0)
+    if "--only-fire-isc" in sys.argv:
+        fire_isc_case()
         sys.exit(0)
     if "--only-masked" in sys.argv:
         masked_case("small_masked", 96, 128, 2, 40)
