@@ -196,3 +196,27 @@ def test_mask_argument_checks():
         m({"image0": x, "image1": x, "mask0": torch.ones(1, 4, 4, dtype=torch.bool)})
     with pytest.raises(ValueError):
         emu.token_mask(torch.ones(1, 3, 4, dtype=torch.bool), 1, 16)
+
+
+@pytest.mark.parametrize("hw0,hw1,n,regime,thr", [
+    ((64, 96), (64, 96), 3, "mixed", 0.02),          # a real threshold: some samples lose most of their matches
+    ((56, 120), (56, 120), 2, "shift", 0.0),         # 7 x 15 coarse cells (odd sizes)
+    ((64, 64), (96, 64), 2, "rect", 0.0),            # batch of rectangular pairs, L = 64 vs S = 96
+    ((64, 96), (64, 96), 2, "unrelated", 0.0),       # noise matches: RANSAC on garbage, windows mostly out of bounds
+])
+def test_shape_and_regime_sweep_vs_oracle(monkeypatch, hw0, hw1, n, regime, thr):
+    """Integer outputs of the host path (accurate configuration, operators emulated) equal the oracle's over image
+    shapes, batch sizes, thresholds and pair regimes beyond the golden fixtures."""
+    sd = synth.make_state_dict(7, True)
+    m = _model(monkeypatch, sd, thr, "accurate")
+    if regime in ("rect", "unrelated"):
+        a = torch.cat([synth.make_image(hw0[0], hw0[1], 10 + i) for i in range(n)], 0)
+        b = torch.cat([synth.make_image(hw1[0], hw1[1], 20 + i) for i in range(n)], 0)
+    else:
+        a, b = synth.make_pairs(n, hw0[0], hw0[1], regime, 5)
+    d = _forward(m, a, b)
+    with torch.no_grad():
+        want = O.forward(sd, a, b, dict(coarse_thr=thr))
+    assert want["b_ids"].numel() > 20
+    for k in ("b_ids", "i_ids", "j_ids", "mkpts0_c", "mkpts1_c", "mkpts0_f", "mkpts1_f", "m_bids"):
+        assert np.array_equal(d[k].numpy(), want[k].numpy()), k

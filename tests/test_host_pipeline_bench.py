@@ -89,3 +89,58 @@ def test_bench_reference_arm_contract():
     r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                         capture_output=True, text=True, timeout=120, env=dict(os.environ, RANK="1", WORLD_SIZE="2"), cwd=ROOT)
     assert r2.returncode == 0 and r2.stdout.strip() == ""
+
+
+def _dryrun(world, extra_env=None, timeout=420):
+    """bench.py's own arm on `world` simulated ranks (tests/bench_dryrun.py: operators emulated on CPU, gloo for NCCL)."""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), LOCAL_WORLD_SIZE=str(world),
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2", **(extra_env or {}))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "bench_dryrun.py"), "--gpus", str(world), "--steps", "3",
+                                       "--warmup", "1", "--batch", "2", "--hw", "64x96", "--no-cpu-baseline", "--depth", "2"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, cwd=ROOT))
+    outs = []
+    deadline = time.time() + timeout
+    for p in procs:
+        try:
+            o, e = p.communicate(timeout=max(1, deadline - time.time()))
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            return None
+        outs.append((p.returncode, o, e))
+    return outs
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_bench_own_arm_control_flow_dry_run(world):
+    """The whole of bench.py's own arm — warm-up, settle, both timed loops through MatchPipeline, the per-batch
+    match-list exchange, barriers, max-over-ranks, the rank-0-only densely sampled pass, the diagnostics blocks and the
+    JSON line — runs to completion on every simulated rank, rank 0 prints exactly one line with the contract's keys, the
+    other ranks print nothing.  (A collective issued by some ranks only would hang here as it would under NCCL.)"""
+    outs = _dryrun(world)
+    assert outs is not None, "bench.py dry run timed out: the ranks' collective sequences differ"
+    for rc, _, err in outs:
+        assert rc == 0, err[-3000:]
+    lines = [l for l in outs[0][1].splitlines() if l.strip()]
+    assert len(lines) == 1 and all(o.strip() == "" for _, o, _ in outs[1:])
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["n_gpus"] == world and d["steps"] == 3 and d["scaling"] == "weak" and d["unit"] == "pairs/s"
+    assert d["value"] == pytest.approx(2 * 3 * world / (d["ms_per_step"] * 3 / 1e3))              # whole-job pairs / max-over-ranks time
+    assert d["e2e"]["h2d_bytes_per_step"] == 2 * 2 * 64 * 96 * 4 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and d["roofline"]["bound"] == "tensor"
+    assert d["clocks"]["samples_inside_timed_loops"] >= 0 and d["clocks"]["sm_max_mhz"] == 1965.0   # rank 0 took the sampling branches
+    # the exchange gathered the last batch of EVERY rank
+    per_rank = d["config"]["matches_fine_per_pair"] * 2
+    assert d["config"]["gathered_matches_last_batch_all_ranks"] == pytest.approx(per_rank * world, rel=0.25)
+
+
+def test_bench_dry_run_detects_a_rank0_only_collective():
+    """Sensitivity check of the dry run: re-injecting the round-2 bug (rank 0's extra pass issuing all-gathers) hangs."""
+    assert _dryrun(2, {"GF_DRYRUN_INJECT_RANK0_COLLECTIVE": "1"}, timeout=45) is None
