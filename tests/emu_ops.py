@@ -203,6 +203,11 @@ def dual_softmax_(sim):
     return sim, sim.max(dim=2)[0], sim.max(dim=1)[0]
 
 
+def conf_row_col_max(conf):
+    _count("conf_row_col_max")
+    return conf.max(dim=2)[0], conf.max(dim=1)[0]
+
+
 def _compact(mj, mc, hw0c, hw1c, scale):
     """gf_compact_coarse: ordered (b, i) compaction of match_j >= 0; per-sample counts as an int32 host tensor."""
     n, l = mj.shape
@@ -387,7 +392,7 @@ class _NoStream:
 OPS = ("linear", "conv", "conv_ref", "stem_conv", "upsample_add", "add_posenc", "token_mask", "mask_rows_",
        "mask_fill_sim_", "linattn", "linattn_window", "fine_layer_fused", "similarity", "dual_softmax_", "mutual_nearest",
        "coarse_match_fused", "geo_window_table", "geo_self_attention", "geo_cross_attention", "select_rows_", "fine_gather",
-       "gather_rows", "fine_match", "resize_gray_u8")
+       "gather_rows", "fine_match", "resize_gray_u8", "conf_row_col_max")
 
 
 def install(monkeypatch):
