@@ -108,6 +108,7 @@ class GeoFormer(nn.Module):
         self.materialize = False       # also return conf_matrix / dect_conf_matrix / fine_matrix (training-side keys)
         self.capture = False           # keep per-stage tensors in data['_stages'] (tests)
         self._packed: Optional[engine.PackedWeights] = None
+        self._tracked: list = []       # tensors the pack was built from (see _param_version)
         self._pack_lock = threading.Lock()
         if loftr_config["coarse"].get("temp_bug_fix", False):
             # position_encoding.py:26-28: only the (default) bug-compatible table is implemented
@@ -125,20 +126,33 @@ class GeoFormer(nn.Module):
         self._packed = None
         return super()._apply(fn, *a, **kw)
 
+    def _param_version(self) -> int:
+        """Sum of the in-place version counters of the parameters / buffers the current pack was built from: an in-place
+        edit of any weight (optimizer step, `.copy_`, `.mul_` ...) changes it and the next forward repacks.  (Replacing a
+        Parameter OBJECT is not seen here; load_state_dict / .to() reset the pack explicitly.)"""
+        try:
+            return sum(t._version for t in self._tracked)
+        except RuntimeError:            # inference tensors do not track versions
+            return 0
+
     def _weights(self, device) -> engine.PackedWeights:
         """Kernel-ready weights, packed once per device.  Thread-safe: MatchPipeline's workers call forward concurrently
         on their own streams, so packing happens under a lock and the packing stream is drained before the result is
         published (the H2D copies and casts are ordered on the packing stream only)."""
         pw = self._packed
-        if pw is not None and pw.device == device:
+        if pw is not None and pw.device == device and pw.version == self._param_version():
             return pw
         with self._pack_lock:
-            if self._packed is None or self._packed.device != device:
+            ver = self._param_version()
+            if self._packed is None or self._packed.device != device or self._packed.version != ver:
                 if self.backbone_precision not in _BACKBONE_DTYPES:
                     raise ValueError(f"backbone_precision must be one of {sorted(_BACKBONE_DTYPES)}")
                 ops.ensure_init(device)
+                self._tracked = list(self.parameters()) + list(self.buffers())
+                ver = self._param_version()
                 pw = engine.PackedWeights({k: v for k, v in self.state_dict().items()}, device,
                                           _BACKBONE_DTYPES[self.backbone_precision])
+                pw.version = ver
                 cfg, gcfg = self.config, self.geo_cfg
                 for got, names, what in ((pw.coarse, cfg["coarse"]["layer_names"], "coarse"),
                                          (pw.fine, cfg["fine"]["layer_names"], "fine"), (pw.geo, gcfg["layer_names"], "geo")):

@@ -220,3 +220,29 @@ def test_shape_and_regime_sweep_vs_oracle(monkeypatch, hw0, hw1, n, regime, thr)
     assert want["b_ids"].numel() > 20
     for k in ("b_ids", "i_ids", "j_ids", "mkpts0_c", "mkpts1_c", "mkpts0_f", "mkpts1_f", "m_bids"):
         assert np.array_equal(d[k].numpy(), want[k].numpy()), k
+
+
+def test_in_place_weight_edits_invalidate_the_packed_weights(monkeypatch):
+    """The kernel-ready weight pack follows in-place parameter edits (version counters), load_state_dict and is built
+    once otherwise."""
+    sd = synth.make_state_dict(7, True)
+    m = _model(monkeypatch, sd, 0.0, "accurate")
+    a, b = synth.make_pairs(1, 64, 96, "shift", 3)
+    d0 = _forward(m, a, b)
+    pw0 = m._packed
+    d1 = _forward(m, a, b)
+    assert m._packed is pw0 and torch.equal(d0["mkpts0_f"], d1["mkpts0_f"])            # no repack between identical calls
+    with torch.no_grad():
+        m.loftr_coarse.layers[3].mlp[0].weight.mul_(-1.0)                                # in-place edit of one weight
+    d2 = _forward(m, a, b)
+    assert m._packed is not pw0
+    sd2 = {k: v.clone() for k, v in sd.items()}
+    sd2["loftr_coarse.layers.3.mlp.0.weight"] *= -1.0
+    with torch.no_grad():
+        want = O.forward(sd2, a, b, dict(coarse_thr=0.0))
+    assert np.array_equal(d2["mkpts0_f"].numpy(), want["mkpts0_f"].numpy()) and np.array_equal(d2["j_ids"].numpy(), want["j_ids"].numpy())
+    assert not torch.equal(d2["_stages"]["coarse0"], d0["_stages"]["coarse0"])
+    pw2 = m._packed
+    m.load_state_dict({k: v.clone() for k, v in sd.items()})                              # back to the original weights
+    d3 = _forward(m, a, b)
+    assert m._packed is not pw2 and torch.equal(d3["mkpts0_f"], d0["mkpts0_f"]) and torch.equal(d3["j_ids"], d0["j_ids"])
