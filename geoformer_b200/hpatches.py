@@ -79,6 +79,8 @@ class _Guarded:
         return self.model._weights(device)
 
     def __call__(self, data):
+        if "_error" in data:            # the ingest of this batch already failed
+            return data
         try:
             return self.model(data)
         except Exception as e:          # noqa: BLE001 - surfaced per pair by BatchedMatcher
@@ -143,13 +145,16 @@ class BatchedMatcher:
         from . import ops
         (hw0, hw1), items = desc["_shape"], desc["_items"]
         n = len(items)
-        im0 = torch.empty((n, 1) + tuple(hw0), device=self.device, dtype=torch.float32)
-        im1 = torch.empty((n, 1) + tuple(hw1), device=self.device, dtype=torch.float32)
-        for b, (_, ims) in enumerate(items):
-            for dst, (raw, _, _) in ((im0[b, 0], ims[0]), (im1[b, 0], ims[1])):
-                host = torch.from_numpy(np.ascontiguousarray(raw))
-                src = (host.pin_memory() if self.device.type == "cuda" else host).to(self.device, non_blocking=True)
-                ops.resize_gray_u8(src, dst)
+        try:
+            im0 = torch.empty((n, 1) + tuple(hw0), device=self.device, dtype=torch.float32)
+            im1 = torch.empty((n, 1) + tuple(hw1), device=self.device, dtype=torch.float32)
+            for b, (_, ims) in enumerate(items):
+                for dst, (raw, _, _) in ((im0[b, 0], ims[0]), (im1[b, 0], ims[1])):
+                    host = torch.from_numpy(np.ascontiguousarray(raw))
+                    src = (host.pin_memory() if self.device.type == "cuda" else host).to(self.device, non_blocking=True)
+                    ops.resize_gray_u8(src, dst)
+        except Exception as e:          # noqa: BLE001 - a failed batch is a per-pair failure, not the end of the run
+            return {"_items": items, "_error": e}
         return {"image0": im0, "image1": im1, "_items": items}
 
     def _post(self, data: dict) -> list:

@@ -181,3 +181,39 @@ def test_batched_matcher_groups_by_shape_and_matches_the_per_pair_wrapper(monkey
     m2, a2, b2, s2 = bm2(*pairs[0])
     m1 = got[0]
     assert np.allclose(m2, m1[0] * m1[4][None]) and np.allclose(a2, m1[1] * m1[4][:2]) and np.allclose(b2, m1[2] * m1[4][2:])
+
+
+def test_failed_batches_become_per_pair_failures(tmp_path):
+    """A batch whose ingest or forward raises is reported as one failure per pair (the helper's try / except counts
+    match_failed per pair, hpatches_helper.py:193-196); the other batches are unaffected."""
+    root = make_hpatches_tree(str(tmp_path), seqs=(("i_a", (96, 128)), ("v_b", (128, 96))), seed=2)
+
+    class Model:
+        def __call__(self, data):
+            if data["image0"].shape[-1] == 96:                       # the 128x96 bucket blows up in the forward
+                raise RuntimeError("forward failed")
+            n = data["image0"].shape[0]
+            data.update(mkpts0_f=torch.zeros(n, 2), mkpts1_f=torch.ones(n, 2), mconf=torch.full((n,), 0.5), m_bids=torch.arange(n))
+            return data
+
+    def runner(batches, prepare, post):
+        g = HP._Guarded(Model())
+        for k, desc in enumerate(batches):
+            yield post(g(prepare(desc) if k != 0 else {"_items": desc["_items"], "_error": MemoryError("ingest failed")}))
+
+    import cv2
+    monkey_resize = lambda src, dst: dst.copy_(torch.from_numpy(cv2.resize(src.numpy(), (dst.shape[1], dst.shape[0]))).float().div(255))
+    from geoformer_b200 import ops
+    orig = ops.resize_gray_u8
+    ops.resize_gray_u8 = monkey_resize
+    try:
+        bm = HP.BatchedMatcher(None, "cpu", imsize=96, batch=2, runner=runner)
+        got = dict(bm.match_many([(p.im1, p.im2) for p in HP.list_pairs(root)]))
+    finally:
+        ops.resize_gray_u8 = orig
+    kinds = [type(got[k]).__name__ if isinstance(got[k], Exception) else "ok" for k in range(10)]
+    # list order: 5 pairs of v_b (128 x 96) then 5 of i_a; batches of 2: the first v_b batch fails in the ingest, the other
+    # v_b batches (2 + the flushed 1) in the forward, every i_a batch succeeds
+    assert kinds[:5].count("MemoryError") == 2 and kinds[:5].count("RuntimeError") == 3 and kinds[5:] == ["ok"] * 5
+    ok = [got[k] for k in range(10) if not isinstance(got[k], Exception)]
+    assert all(m[0].shape == (1, 4) and m[4].shape == (4,) for m in ok)
