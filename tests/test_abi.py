@@ -115,3 +115,19 @@ def test_header_is_valid_c_and_links_from_a_c_host(tmp_path):
                     "-l:" + os.path.basename(lib), "-Wl,-rpath," + os.path.dirname(lib)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert out[0] == "1"
+
+
+def test_mask_entry_points_validate_arguments_without_a_gpu():
+    """gf_mask_rows / gf_mask_fill_sim reject bad shapes and misaligned ranges with GF_ERR_ARG before any launch, and an
+    empty row set is a no-op (ctypes marshalling of the two new signatures included)."""
+    from geoformer_b200 import _lib
+    lib = _lib.load()
+    x = torch.zeros(8, 16); h = x.half(); m = torch.ones(8, dtype=torch.uint8)
+    assert lib.gf_mask_rows(h.data_ptr(), 2, 8, 16, 1, 4, m.data_ptr(), None) == -1          # 2-byte offset
+    assert b"multiples of 4 bytes" in lib.gf_last_error()
+    assert lib.gf_mask_rows(x.data_ptr(), 4, 8, 16, 10, 8, m.data_ptr(), None) == -1         # column range beyond the row
+    assert lib.gf_mask_rows(x.data_ptr(), 8, 8, 16, 0, 8, m.data_ptr(), None) == -1          # element size
+    assert lib.gf_mask_rows(None, 4, 0, 8, 0, 8, None, None) == 0                            # no rows: nothing to launch
+    sim = torch.zeros(1, 4, 4)
+    assert lib.gf_mask_fill_sim(sim.data_ptr(), 1, 70000, 4, m.data_ptr(), m.data_ptr(), -1e9, None) == -1   # grid.y limit
+    assert lib.gf_mask_fill_sim(sim.data_ptr(), 0, 4, 4, m.data_ptr(), m.data_ptr(), -1e9, None) == -1
