@@ -96,6 +96,15 @@ def main():
         old = "run_resident(max(4, args.steps // 2), collective=False)"
         assert src.count(old) == 1
         src = src.replace(old, "run_resident(max(4, args.steps // 2), collective=True)")
+    if os.environ.get("GF_DRYRUN_FAIL_EXTRA_ON_RANK1"):          # rank 1's measurement of the informational configs raises
+        from geoformer_b200 import synth
+        orig = synth.make_pairs
+
+        def make_pairs(n, h, w, regime, seed):
+            if 8000 <= seed < 9000:                              # bench.other_configs seeds: 7000 + 1000 * rank + 100 * p
+                raise MemoryError("simulated failure on rank 1")
+            return orig(n, h, w, regime, seed)
+        synth.make_pairs = make_pairs
     g = {"__name__": "__main__", "__file__": os.path.join(ROOT, "bench.py")}
     exec(compile(src, os.path.join(ROOT, "bench.py"), "exec"), g)
 

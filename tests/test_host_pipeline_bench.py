@@ -98,7 +98,8 @@ def _dryrun(world, extra_env=None, timeout=420):
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), LOCAL_WORLD_SIZE=str(world),
-                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2", **(extra_env or {}))
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2", GF_BENCH_EXTRA_HW="64x64,72x88",
+                   **(extra_env or {}))
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "bench_dryrun.py"), "--gpus", str(world), "--steps", "3",
                                        "--warmup", "1", "--batch", "2", "--hw", "64x96", "--no-cpu-baseline", "--depth", "2"],
                                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, cwd=ROOT))
@@ -136,6 +137,10 @@ def test_bench_own_arm_control_flow_dry_run(world):
     assert d["e2e"]["h2d_bytes_per_step"] == 2 * 2 * 64 * 96 * 4 and d["e2e"]["d2h_bytes_per_step"] > 0
     assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and d["roofline"]["bound"] == "tensor"
     assert d["clocks"]["samples_inside_timed_loops"] >= 0 and d["clocks"]["sm_max_mhz"] == 1965.0   # rank 0 took the sampling branches
+    # informational block for BASELINE configs[3] / configs[4] (shapes shrunk for the dry run)
+    oc = d["config"]["other_baseline_configs"]
+    assert set(oc) == {"64x64", "72x88"} and all(v["pairs_per_sec"] > 0 and v["steps"] == 4 and v["pairs_per_step"] == 2 for v in oc.values())
+    assert oc["72x88"]["coarse_tokens"] == 99 and oc["72x88"]["matches_coarse_per_pair"] > 20
     # the exchange gathered the last batch of EVERY rank
     per_rank = d["config"]["matches_fine_per_pair"] * 2
     assert d["config"]["gathered_matches_last_batch_all_ranks"] == pytest.approx(per_rank * world, rel=0.25)
@@ -144,3 +149,15 @@ def test_bench_own_arm_control_flow_dry_run(world):
 def test_bench_dry_run_detects_a_rank0_only_collective():
     """Sensitivity check of the dry run: re-injecting the round-2 bug (rank 0's extra pass issuing all-gathers) hangs."""
     assert _dryrun(2, {"GF_DRYRUN_INJECT_RANK0_COLLECTIVE": "1"}, timeout=45) is None
+
+
+def test_bench_informational_configs_cannot_desynchronise_the_ranks():
+    """One rank failing inside the informational 768x768 / 840x840 block (here: rank 1, simulated) neither hangs the run nor
+    costs the headline line: every rank still issues the block's collectives, the block reports the failure."""
+    outs = _dryrun(2, {"GF_DRYRUN_FAIL_EXTRA_ON_RANK1": "1"})
+    assert outs is not None, "hung"
+    assert all(rc == 0 for rc, _, _ in outs), outs[1][2][-2000:]
+    d = json.loads([l for l in outs[0][1].splitlines() if l.strip()][0])
+    assert d["value"] > 0 and d["n_gpus"] == 2
+    assert all(v.get("failed") is True for v in d["config"]["other_baseline_configs"].values())
+    assert "simulated failure on rank 1" in outs[1][2]
