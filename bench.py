@@ -371,7 +371,10 @@ def run_ours(args):
     allm, allid = unpack_match_lists(last_gather["blocks"])
     gathered = int(allm.shape[0])
     mc, mf = [v / world for v in reduce_sums([mc, mf], device)]
-    other = other_configs(args, rank, world, device, drive)
+    try:
+        other = other_configs(args, rank, world, device, drive)
+    except Exception as e:          # noqa: BLE001 - informational block (even a failed collective in it must not cost the line)
+        other = {"failed": True, "error": f"{type(e).__name__}: {e}"[:200]}
     if args.stage_times and rank == 0:
         stage_breakdown(model, dev[0])
     if rank != 0:
