@@ -148,7 +148,7 @@ def test_bench_own_arm_control_flow_dry_run(world):
 
 def test_bench_dry_run_detects_a_rank0_only_collective():
     """Sensitivity check of the dry run: re-injecting the round-2 bug (rank 0's extra pass issuing all-gathers) hangs."""
-    assert _dryrun(2, {"GF_DRYRUN_INJECT_RANK0_COLLECTIVE": "1"}, timeout=45) is None
+    assert _dryrun(2, {"GF_DRYRUN_INJECT_RANK0_COLLECTIVE": "1"}, timeout=30) is None
 
 
 def test_bench_informational_configs_cannot_desynchronise_the_ranks():
