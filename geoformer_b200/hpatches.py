@@ -122,22 +122,44 @@ class BatchedMatcher:
             return k, None, e
 
     def _batches(self, pairs: Sequence[Tuple[str, str]], failed: list) -> Iterator[dict]:
-        """Batch descriptors of pairs with equal resized shapes, emitted as soon as `batch` of them are decoded."""
-        buckets: Dict[tuple, list] = {}
-        with ThreadPoolExecutor(max_workers=self.decode_threads) as ex:
-            window = 4 * self.batch                                    # bounded prefetch of decoded images
-            items = list(enumerate(pairs))
-            for lo in range(0, len(items), window):
-                for k, ims, err in ex.map(self._decode, items[lo:lo + window]):
-                    if err is not None:
-                        failed.append((k, err))
-                        continue
-                    key = (ims[0][1], ims[1][1])
-                    buckets.setdefault(key, []).append((k, ims))
-                    if len(buckets[key]) == self.batch:
-                        yield {"_shape": key, "_items": buckets.pop(key)}
-        for key in sorted(buckets):
-            yield {"_shape": key, "_items": buckets[key]}
+        """Batch descriptors of pairs with equal resized shapes, emitted as soon as `batch` of them are decoded.  Decoding
+        runs ahead of the consumer in a producer thread (bounded queue), so the GPU is not idle while images are read."""
+        import queue
+        import threading
+        q: "queue.Queue" = queue.Queue(maxsize=self.depth + 2)
+        END = object()
+
+        def produce():
+            buckets: Dict[tuple, list] = {}
+            try:
+                with ThreadPoolExecutor(max_workers=self.decode_threads) as ex:
+                    window = 2 * self.batch                                # decoded images in flight beyond the queue
+                    items = list(enumerate(pairs))
+                    for lo in range(0, len(items), window):
+                        for k, ims, err in ex.map(self._decode, items[lo:lo + window]):
+                            if err is not None:
+                                failed.append((k, err))
+                                continue
+                            key = (ims[0][1], ims[1][1])
+                            buckets.setdefault(key, []).append((k, ims))
+                            if len(buckets[key]) == self.batch:
+                                q.put({"_shape": key, "_items": buckets.pop(key)})
+                for key in sorted(buckets):
+                    q.put({"_shape": key, "_items": buckets[key]})
+                q.put(END)
+            except BaseException as e:      # noqa: BLE001 - re-raised in the consumer
+                q.put(e)
+
+        t = threading.Thread(target=produce, daemon=True)
+        t.start()
+        while True:
+            item = q.get()
+            if item is END:
+                break
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+        t.join()
 
     # -- device side (runs on the batch's stream inside the pipeline) --------------------------------------
     def _ingest(self, desc: dict) -> dict:
