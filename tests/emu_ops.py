@@ -378,6 +378,42 @@ def resize_gray_u8(src, dst):
     return dst
 
 
+def ransac_homography(k0, k1, b_ids, counts, n, hw0_c, hw1_c, scale, thr=8.0, hyps=1024, seed=0):
+    """gf_ransac_homography's OUTPUT CONTRACT (hm [2,n,9] = H and H^-1 as fp32, has_h [n], inlier [m], ascending anchor
+    lists aidx [2,n,cap] + acnt [2,n]; all first-pass matches are anchors when a sample has no homography) with
+    OpenCV as the estimator: exercises the host glue of GeoFormer.ransac == 'gpu' (the device estimator itself is not
+    bit-identical to OpenCV and is judged geometrically on the GPU, tests/test_gpu_ransac.py)."""
+    import cv2
+    import numpy as np
+    _count("ransac_homography")
+    m = int(k0.shape[0])
+    l0, l1 = hw0_c[0] * hw0_c[1], hw1_c[0] * hw1_c[1]
+    cap = max(l0, l1)
+    hm = torch.zeros(2, n, 9)
+    has_h = torch.zeros(n, dtype=torch.int32)
+    inlier = torch.ones(max(m, 1), dtype=torch.int32)
+    aidx = torch.zeros(2, n, cap, dtype=torch.int32)
+    acnt = torch.zeros(2, n, dtype=torch.int32)
+    offs = np.concatenate([[0], np.cumsum(counts.numpy())])
+    for b in range(n):
+        a = k0[offs[b]:offs[b + 1]].numpy().astype(np.int64)
+        c = k1[offs[b]:offs[b + 1]].numpy().astype(np.int64)
+        keep = np.ones(len(a), dtype=bool)
+        if len(a) > 8:
+            M, mask = cv2.findHomography(a, c, cv2.RANSAC, thr)
+            if M is not None:
+                has_h[b] = 1
+                keep = mask[:, 0] == 1
+                hm[0, b] = torch.from_numpy(M.astype(np.float32).reshape(9))
+                hm[1, b] = torch.inverse(torch.from_numpy(M)).to(torch.float32).reshape(9)
+        inlier[offs[b]:offs[b + 1]] = torch.from_numpy(keep.astype(np.int32))
+        for side, (pts, wc) in enumerate(((a[keep], hw0_c[1]), (c[keep], hw1_c[1]))):
+            tok = np.unique((pts[:, 1] // scale) * wc + pts[:, 0] // scale)
+            acnt[side, b] = len(tok)
+            aidx[side, b, :len(tok)] = torch.from_numpy(tok.astype(np.int32))
+    return hm, has_h, inlier[:m], aidx, acnt
+
+
 # ------------------------------------------------------------------------------------------------ plumbing
 class _NoStream:
     cuda_stream = 0
@@ -392,7 +428,8 @@ class _NoStream:
 OPS = ("linear", "conv", "conv_ref", "stem_conv", "upsample_add", "add_posenc", "token_mask", "mask_rows_",
        "mask_fill_sim_", "linattn", "linattn_window", "fine_layer_fused", "similarity", "dual_softmax_", "mutual_nearest",
        "coarse_match_fused", "geo_window_table", "geo_self_attention", "geo_cross_attention", "select_rows_", "fine_gather",
-       "gather_rows", "fine_match", "resize_gray_u8", "conf_row_col_max")
+       "gather_rows", "fine_match", "resize_gray_u8", "conf_row_col_max",
+       "ransac_homography")
 
 
 def install(monkeypatch):

@@ -246,3 +246,21 @@ def test_in_place_weight_edits_invalidate_the_packed_weights(monkeypatch):
     m.load_state_dict({k: v.clone() for k, v in sd.items()})                              # back to the original weights
     d3 = _forward(m, a, b)
     assert m._packed is not pw2 and torch.equal(d3["mkpts0_f"], d0["mkpts0_f"]) and torch.equal(d3["j_ids"], d0["j_ids"])
+
+
+def test_device_ransac_branch_host_glue(monkeypatch):
+    """GeoFormer.ransac == 'gpu': the host glue around gf_ransac_homography (device-resident match lists in, 3n counters
+    back, anchor lists / homographies used straight from the device buffers) gives the cv2-mode result when the
+    estimator behind the contract is OpenCV itself."""
+    sd = synth.make_state_dict(7, True)
+    a, b = synth.make_pairs(3, 64, 96, "mixed", 4)
+    m = _model(monkeypatch, sd, 0.0, "accurate")
+    d_cv = _forward(m, a, b)
+    m.ransac = "gpu"
+    d_gpu = _forward(m, a, b)
+    assert emu.CALLS["ransac_homography"] == 1
+    for k in ("b_ids", "i_ids", "j_ids", "mkpts0_f", "mkpts1_f", "m_bids"):
+        assert torch.equal(d_cv[k], d_gpu[k]), k
+    gi_cv, gi_gpu = d_cv["_stages"]["geo_info"], d_gpu["_stages"]["geo_info"]
+    assert np.array_equal(gi_cv["has_h"], gi_gpu["has_h"]) and np.array_equal(gi_cv["anchor_cnt"], gi_gpu["anchor_cnt"])
+    assert np.allclose(gi_cv["hmat"], gi_gpu["hmat"])
