@@ -105,6 +105,9 @@ class GeoFormer(nn.Module):
         # "cv2": host cv2.findHomography as the reference (geo_module.py:48); "gpu": csrc/ransac.cu (not bit-identical)
         self.ransac = os.environ.get("GF_RANSAC", "cv2")
         self.ransac_hyps = 1024
+        # per-instance precision options, e.g. dict(linear="ref", similarity="ref", attention="ref", activations="f32") for
+        # the accurate configuration; None = the module-level options of geoformer_b200.ops (ops.precision_scope)
+        self.precision: Optional[dict] = None
         self.materialize = False       # also return conf_matrix / dect_conf_matrix / fine_matrix (training-side keys)
         self.capture = False           # keep per-stage tensors in data['_stages'] (tests)
         self._packed: Optional[engine.PackedWeights] = None
@@ -177,6 +180,9 @@ class GeoFormer(nn.Module):
         if not img0.is_cuda:
             raise RuntimeError("geoformer_b200.GeoFormer runs on CUDA (sm_100a) only; there is no CPU fallback")
         with torch.cuda.device(img0.device):       # kernels launch on the tensors' device and its current stream
+            if self.precision:
+                with ops.precision_scope(**self.precision):
+                    return self._forward(data, img0, img1)
             return self._forward(data, img0, img1)
 
     def _forward(self, data, img0, img1):

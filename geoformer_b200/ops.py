@@ -6,6 +6,7 @@ current CUDA stream.  PyTorch is used for device memory and streams only.
 from __future__ import annotations
 
 import os
+import threading
 from typing import Optional, Tuple
 
 import torch
@@ -43,6 +44,31 @@ def set_precision(linear: Optional[str] = None, similarity: Optional[str] = None
     if similarity is not None:
         assert similarity in ("f16x3", "ref")
         _SIM_IMPL = similarity
+
+
+_PRECISION_LOCK = threading.RLock()
+
+
+class precision_scope:
+    """`with precision_scope(linear=..., similarity=..., attention=..., activations=...)`: run a block under its own
+    precision options and restore the module-level ones afterwards.  The options are process-wide, so the scope holds a
+    lock for its whole duration: blocks with an override run one at a time (GeoFormer.precision uses this; the default,
+    no override, takes no lock and keeps MatchPipeline's batches concurrent)."""
+
+    def __init__(self, **opts):
+        self.opts = opts
+
+    def __enter__(self):
+        _PRECISION_LOCK.acquire()
+        self.saved = (_LINEAR_IMPL, _SIM_IMPL, _ATTN_IMPL, _ACT16)
+        set_precision(**self.opts)
+        return self
+
+    def __exit__(self, *exc):
+        global _LINEAR_IMPL, _SIM_IMPL, _ATTN_IMPL, _ACT16
+        _LINEAR_IMPL, _SIM_IMPL, _ATTN_IMPL, _ACT16 = self.saved
+        _PRECISION_LOCK.release()
+        return False
 
 
 class _Profile:

@@ -264,3 +264,41 @@ def test_device_ransac_branch_host_glue(monkeypatch):
     gi_cv, gi_gpu = d_cv["_stages"]["geo_info"], d_gpu["_stages"]["geo_info"]
     assert np.array_equal(gi_cv["has_h"], gi_gpu["has_h"]) and np.array_equal(gi_cv["anchor_cnt"], gi_gpu["anchor_cnt"])
     assert np.allclose(gi_cv["hmat"], gi_gpu["hmat"])
+
+
+def test_per_instance_precision_scope(monkeypatch):
+    """GeoFormer.precision: the instance's options apply during ITS forward only (module-level options restored
+    afterwards, also on error), overrides of different instances never mix, and the default (None) takes no lock."""
+    import contextlib
+    import threading
+    import types
+    from geoformer_b200.model.full_model import GeoFormer
+    from geoformer_b200.model.geo_config import default_cfg as geo_cfg
+    from geoformer_b200.model.loftr_src.loftr.utils.cvpr_ds_config import default_cfg
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    seen = []
+
+    def fake_forward(self, data, a, b):
+        seen.append((self.tag, ops._LINEAR_IMPL, ops._SIM_IMPL, ops._ATTN_IMPL, ops.act16()))
+        if data.get("boom"):
+            raise RuntimeError("boom")
+        return data
+    monkeypatch.setattr(GeoFormer, "_forward", fake_forward)
+    img = types.SimpleNamespace(is_cuda=True, device="cpu")
+    acc, fast = (GeoFormer(copy.deepcopy(default_cfg), dict(geo_cfg)).eval() for _ in range(2))
+    acc.tag, fast.tag = "acc", "fast"
+    acc.precision = dict(linear="ref", similarity="ref", attention="ref", activations="f32")
+    acc({"image0": img, "image1": img}); fast({"image0": img, "image1": img}); acc({"image0": img, "image1": img})
+    assert seen == [("acc", "ref", "ref", "ref", False), ("fast", "tf32", "f16x3", "tf32", True), ("acc", "ref", "ref", "ref", False)]
+    with pytest.raises(RuntimeError):
+        acc({"image0": img, "image1": img, "boom": True})
+    assert (ops._LINEAR_IMPL, ops._SIM_IMPL, ops._ATTN_IMPL, ops.act16()) == ("tf32", "f16x3", "tf32", True)     # restored
+    # concurrent calls: an override never leaks into another thread's overridden forward
+    seen.clear()
+    other = GeoFormer(copy.deepcopy(default_cfg), dict(geo_cfg)).eval()
+    other.tag, other.precision = "other", dict(linear="tf32", similarity="ref", attention="tf32", activations="f32")
+    ts = [threading.Thread(target=lambda m=m: [m({"image0": img, "image1": img}) for _ in range(50)]) for m in (acc, other)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    assert len(seen) == 100
+    assert all(r[1:] == (("ref", "ref", "ref", False) if r[0] == "acc" else ("tf32", "ref", "tf32", False)) for r in seen)
+    assert ops._PRECISION_LOCK.acquire(blocking=False); ops._PRECISION_LOCK.release()
